@@ -1,0 +1,566 @@
+/*
+ * dnz_oracle.c -- CPU restatement of Denormalized's grouped streaming-window aggregate.
+ * TEST INFRASTRUCTURE ONLY (see dnz_oracle.h).  PARITY UNPINNED (see dnz_oracle.h).
+ *
+ * The code deliberately performs the same passes over the data as the reference does
+ * (two materialised filter copies per overlapping window, key interning, then one pass per
+ * accumulator), so that the same routine serves as ground truth and as the timed CPU baseline.
+ */
+#define _GNU_SOURCE
+#include "dnz_oracle.h"
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* small helpers                                                                               */
+
+static inline int bit_get(const uint8_t* bm, int64_t i) { return bm == NULL || ((bm[i >> 3] >> (i & 7)) & 1); }
+static inline void bit_set(uint8_t* bm, int64_t i) { bm[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+
+static void* xrealloc(void* p, size_t n) {
+  void* q = realloc(p, n ? n : 1);
+  if (!q) { fprintf(stderr, "dnz_oracle: out of memory (%zu)\n", n); abort(); }
+  return q;
+}
+static void* xcalloc(size_t n, size_t s) {
+  void* q = calloc(n ? n : 1, s ? s : 1);
+  if (!q) { fprintf(stderr, "dnz_oracle: out of memory\n"); abort(); }
+  return q;
+}
+
+static inline uint64_t hash_bytes(const uint8_t* p, int64_t n) {
+  /* any good hash will do: results do not depend on it (the reference uses ahash). */
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n * 0xff51afd7ed558ccdull);
+  while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 32; p += 8; n -= 8; }
+  uint64_t w = 0; if (n > 0) memcpy(&w, p, (size_t)n);
+  h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  return h;
+}
+
+/* IEEE-754 totalOrder, as f64::total_cmp (arrow-ord 53 cmp kernels for floats). */
+static inline int64_t total_order_key(double d) {
+  int64_t b; memcpy(&b, &d, 8);
+  b ^= (int64_t)(((uint64_t)(b >> 63)) >> 1);
+  return b;
+}
+static int total_cmp(double a, double b) {
+  int64_t x = total_order_key(a), y = total_order_key(b);
+  return (x > y) - (x < y);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a materialised (filtered) batch: what filter_record_batch produces                          */
+
+typedef struct {
+  int64_t n, cap, bytes_cap, bar_bytes_cap;
+  int64_t* ts; uint8_t* ts_valid;
+  double* val; uint8_t* val_valid;
+  int32_t* key_off; uint8_t* key_bytes; uint8_t* key_valid;
+  int64_t* occurred_at;
+  int32_t* barrier_off; uint8_t* barrier_bytes;
+  int has_ts_valid, has_val_valid, has_key_valid, has_occ, has_bar;
+} own_batch;
+
+static void own_batch_free(own_batch* o) {
+  free(o->ts); free(o->ts_valid); free(o->val); free(o->val_valid); free(o->key_off); free(o->key_bytes);
+  free(o->key_valid); free(o->occurred_at); free(o->barrier_off); free(o->barrier_bytes);
+  memset(o, 0, sizeof(*o));
+}
+
+static void own_batch_reserve(own_batch* o, int64_t n, int64_t key_bytes, int64_t bar_bytes) {
+  if (n + 1 > o->cap) {
+    int64_t c = n + 1;
+    o->ts = xrealloc(o->ts, c * 8); o->val = xrealloc(o->val, c * 8);
+    o->key_off = xrealloc(o->key_off, c * 4); o->barrier_off = xrealloc(o->barrier_off, c * 4);
+    o->occurred_at = xrealloc(o->occurred_at, c * 8);
+    o->ts_valid = xrealloc(o->ts_valid, (c + 7) / 8 + 1); o->val_valid = xrealloc(o->val_valid, (c + 7) / 8 + 1);
+    o->key_valid = xrealloc(o->key_valid, (c + 7) / 8 + 1);
+    o->cap = c;
+  }
+  if (key_bytes > o->bytes_cap) { o->key_bytes = xrealloc(o->key_bytes, key_bytes); o->bytes_cap = key_bytes; }
+  if (bar_bytes > o->bar_bytes_cap) { o->barrier_bytes = xrealloc(o->barrier_bytes, bar_bytes); o->bar_bytes_cap = bar_bytes; }
+}
+
+static orc_batch own_as_view(const own_batch* o) {
+  orc_batch v;
+  v.n = o->n; v.ts = o->ts; v.ts_valid = o->has_ts_valid ? o->ts_valid : NULL;
+  v.val = o->val; v.val_valid = o->has_val_valid ? o->val_valid : NULL;
+  v.key_off = o->key_off; v.key_bytes = o->key_bytes; v.key_valid = o->has_key_valid ? o->key_valid : NULL;
+  v.occurred_at = o->has_occ ? o->occurred_at : NULL;
+  v.barrier_off = o->has_bar ? o->barrier_off : NULL; v.barrier_bytes = o->has_bar ? o->barrier_bytes : NULL;
+  return v;
+}
+
+/* filter_record_batch(batch, mask): copies EVERY column (grouped_window_agg_stream.rs:573,600).
+ * mask semantics: null timestamp -> comparison is null -> row dropped. */
+static void filter_copy(const orc_batch* in, int cmp_ge, int64_t bound, own_batch* out) {
+  int64_t n = in->n;
+  int64_t kb = n > 0 ? (int64_t)in->key_off[n] - in->key_off[0] : 0;
+  int64_t bb = (in->barrier_off && n > 0) ? (int64_t)in->barrier_off[n] - in->barrier_off[0] : 0;
+  own_batch_reserve(out, n, kb, bb);
+  out->has_ts_valid = in->ts_valid != NULL; out->has_val_valid = in->val_valid != NULL;
+  out->has_key_valid = in->key_valid != NULL; out->has_occ = in->occurred_at != NULL;
+  out->has_bar = in->barrier_off != NULL;
+  if (out->has_ts_valid) memset(out->ts_valid, 0, (size_t)((n + 7) / 8 + 1));
+  if (out->has_val_valid) memset(out->val_valid, 0, (size_t)((n + 7) / 8 + 1));
+  if (out->has_key_valid) memset(out->key_valid, 0, (size_t)((n + 7) / 8 + 1));
+  int64_t m = 0; int32_t ko = 0, bo = 0;
+  out->key_off[0] = 0; out->barrier_off[0] = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (!bit_get(in->ts_valid, i)) continue;
+    int64_t t = in->ts[i];
+    int keep = cmp_ge ? (t >= bound) : (t < bound);
+    if (!keep) continue;
+    out->ts[m] = t; if (out->has_ts_valid) bit_set(out->ts_valid, m);
+    out->val[m] = in->val[i]; if (out->has_val_valid && bit_get(in->val_valid, i)) bit_set(out->val_valid, m);
+    int32_t a = in->key_off[i], b = in->key_off[i + 1];
+    memcpy(out->key_bytes + ko, in->key_bytes + a, (size_t)(b - a)); ko += b - a; out->key_off[m + 1] = ko;
+    if (out->has_key_valid && bit_get(in->key_valid, i)) bit_set(out->key_valid, m);
+    if (out->has_occ) out->occurred_at[m] = in->occurred_at[i];
+    if (out->has_bar) {
+      int32_t c = in->barrier_off[i], d = in->barrier_off[i + 1];
+      memcpy(out->barrier_bytes + bo, in->barrier_bytes + c, (size_t)(d - c)); bo += d - c; out->barrier_off[m + 1] = bo;
+    }
+    m++;
+  }
+  out->n = m;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GroupedAggWindowFrame                                                                       */
+
+typedef struct {
+  int64_t start_ms, end_ms;
+  /* GroupValues: open-addressing map key bytes -> dense group id (first-seen order) */
+  int64_t tab_cap;           /* power of two */
+  int32_t* tab_gid;          /* -1 empty */
+  uint64_t* tab_hash;
+  int64_t n_groups, g_cap;
+  int32_t* g_off; int64_t g_bytes_cap; uint8_t* g_bytes;  /* key arena; g_off[n_groups+1] */
+  int32_t null_gid;          /* -1 until a NULL key is seen */
+  /* accumulators, indexed by group id */
+  int64_t* cnt;              /* CountGroupsAccumulator */
+  double* mn; double* mx;    /* PrimitiveGroupsAccumulator<Float64> */
+  uint8_t* mn_seen; uint8_t* mx_seen;   /* NullState */
+  double* sum; uint64_t* avg_cnt;       /* AvgGroupsAccumulator */
+  /* scratch */
+  int64_t* gids; int64_t gids_cap;
+  own_batch f1, f2;
+} frame_t;
+
+static frame_t* frame_new(int64_t start_ms, int64_t end_ms) {
+  frame_t* f = xcalloc(1, sizeof(frame_t));
+  f->start_ms = start_ms; f->end_ms = end_ms; f->null_gid = -1;
+  f->tab_cap = 64; f->tab_gid = xrealloc(NULL, f->tab_cap * 4); f->tab_hash = xrealloc(NULL, f->tab_cap * 8);
+  for (int64_t i = 0; i < f->tab_cap; i++) f->tab_gid[i] = -1;
+  f->g_off = xcalloc(1, 4);
+  return f;
+}
+static void frame_free(frame_t* f) {
+  free(f->tab_gid); free(f->tab_hash); free(f->g_off); free(f->g_bytes); free(f->cnt); free(f->mn); free(f->mx);
+  free(f->mn_seen); free(f->mx_seen); free(f->sum); free(f->avg_cnt); free(f->gids);
+  own_batch_free(&f->f1); own_batch_free(&f->f2); free(f);
+}
+
+static void frame_grow_groups(frame_t* f, int64_t need) {
+  if (need <= f->g_cap) return;
+  int64_t c = f->g_cap ? f->g_cap * 2 : 64; while (c < need) c *= 2;
+  f->g_off = xrealloc(f->g_off, (c + 1) * 4);
+  f->cnt = xrealloc(f->cnt, c * 8); f->mn = xrealloc(f->mn, c * 8); f->mx = xrealloc(f->mx, c * 8);
+  f->mn_seen = xrealloc(f->mn_seen, c); f->mx_seen = xrealloc(f->mx_seen, c);
+  f->sum = xrealloc(f->sum, c * 8); f->avg_cnt = xrealloc(f->avg_cnt, c * 8);
+  f->g_cap = c;
+}
+static int32_t frame_new_group(frame_t* f, const uint8_t* p, int32_t len) {
+  frame_grow_groups(f, f->n_groups + 1);
+  int32_t g = (int32_t)f->n_groups++;
+  int32_t o = f->g_off[g];
+  if (o + len > f->g_bytes_cap) { int64_t c = f->g_bytes_cap ? f->g_bytes_cap * 2 : 1024; while (c < o + len) c *= 2; f->g_bytes = xrealloc(f->g_bytes, c); f->g_bytes_cap = c; }
+  if (len) memcpy(f->g_bytes + o, p, (size_t)len);
+  f->g_off[g + 1] = o + len;
+  /* accumulator starting values */
+  f->cnt[g] = 0; f->mn[g] = 1.7976931348623157e308 /* f64::MAX */; f->mx[g] = -1.7976931348623157e308 /* f64::MIN */;
+  f->mn_seen[g] = 0; f->mx_seen[g] = 0; f->sum[g] = 0.0; f->avg_cnt[g] = 0;
+  return g;
+}
+static void frame_rehash(frame_t* f) {
+  int64_t nc = f->tab_cap * 2;
+  int32_t* ng = xrealloc(NULL, nc * 4); uint64_t* nh = xrealloc(NULL, nc * 8);
+  for (int64_t i = 0; i < nc; i++) ng[i] = -1;
+  for (int64_t i = 0; i < f->tab_cap; i++) if (f->tab_gid[i] >= 0) {
+    int64_t s = (int64_t)(f->tab_hash[i] & (uint64_t)(nc - 1));
+    while (ng[s] >= 0) s = (s + 1) & (nc - 1);
+    ng[s] = f->tab_gid[i]; nh[s] = f->tab_hash[i];
+  }
+  free(f->tab_gid); free(f->tab_hash); f->tab_gid = ng; f->tab_hash = nh; f->tab_cap = nc;
+}
+/* GroupValues::intern for one Utf8 key column */
+static void frame_intern(frame_t* f, const orc_batch* b) {
+  if (b->n > f->gids_cap) { f->gids = xrealloc(f->gids, b->n * 8); f->gids_cap = b->n; }
+  for (int64_t i = 0; i < b->n; i++) {
+    if (!bit_get(b->key_valid, i)) {
+      if (f->null_gid < 0) f->null_gid = frame_new_group(f, NULL, 0);
+      f->gids[i] = f->null_gid; continue;
+    }
+    const uint8_t* p = b->key_bytes + b->key_off[i]; int32_t len = b->key_off[i + 1] - b->key_off[i];
+    uint64_t h = hash_bytes(p, len);
+    int64_t s = (int64_t)(h & (uint64_t)(f->tab_cap - 1));
+    for (;;) {
+      int32_t g = f->tab_gid[s];
+      if (g < 0) {
+        g = frame_new_group(f, p, len);
+        f->tab_gid[s] = g; f->tab_hash[s] = h; f->gids[i] = g;
+        if ((f->n_groups + 1) * 2 > f->tab_cap) frame_rehash(f);
+        break;
+      }
+      if (f->tab_hash[s] == h && g != f->null_gid && f->g_off[g + 1] - f->g_off[g] == len &&
+          memcmp(f->g_bytes + f->g_off[g], p, (size_t)len) == 0) { f->gids[i] = g; break; }
+      s = (s + 1) & (f->tab_cap - 1);
+    }
+  }
+}
+
+/* group_aggregate_batch (:501-537): intern, then one update_batch pass per accumulator */
+static void frame_aggregate(frame_t* f, const orc_batch* b) {
+  frame_intern(f, b);
+  const int64_t* g = f->gids; int64_t n = b->n;
+  /* count(reading) */
+  for (int64_t i = 0; i < n; i++) if (bit_get(b->val_valid, i)) f->cnt[g[i]] += 1;
+  /* min(reading): if *cur > new { *cur = new } */
+  for (int64_t i = 0; i < n; i++) if (bit_get(b->val_valid, i)) { double v = b->val[i]; f->mn_seen[g[i]] = 1; if (f->mn[g[i]] > v) f->mn[g[i]] = v; }
+  /* max(reading): if *cur < new { *cur = new } */
+  for (int64_t i = 0; i < n; i++) if (bit_get(b->val_valid, i)) { double v = b->val[i]; f->mx_seen[g[i]] = 1; if (f->mx[g[i]] < v) f->mx[g[i]] = v; }
+  /* avg(reading): sums[g] += v in row order; counts[g] += 1 */
+  for (int64_t i = 0; i < n; i++) if (bit_get(b->val_valid, i)) { f->sum[g[i]] += b->val[i]; f->avg_cnt[g[i]] += 1; }
+}
+
+/* GroupedAggWindowFrame::push (:548-605) */
+static void frame_push(frame_t* f, const orc_batch* b) {
+  filter_copy(b, 1, f->start_ms, &f->f1);              /* cmp::gt_eq(ts, window_start) + filter_record_batch */
+  orc_batch v1 = own_as_view(&f->f1);
+  filter_copy(&v1, 0, f->end_ms, &f->f2);              /* cmp::lt(ts, window_end) + filter_record_batch */
+  orc_batch v2 = own_as_view(&f->f2);
+  frame_aggregate(f, &v2);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* result set                                                                                  */
+
+typedef struct {
+  int64_t n, cap, bytes, bytes_cap;
+  int32_t* key_off; uint8_t* key_bytes; uint8_t* key_isnull;
+  int64_t* count; double* mn; double* mx; double* avg; uint8_t* agg_isnull;
+  int64_t* ws; int64_t* we; int64_t* seq;
+} results_t;
+
+static void results_free(results_t* r) {
+  free(r->key_off); free(r->key_bytes); free(r->key_isnull); free(r->count); free(r->mn); free(r->mx); free(r->avg);
+  free(r->agg_isnull); free(r->ws); free(r->we); free(r->seq); memset(r, 0, sizeof(*r));
+}
+static void results_push(results_t* r, const uint8_t* key, int32_t len, int key_isnull, int64_t count, double mn, double mx,
+                         double avg, int agg_isnull, int64_t ws, int64_t we, int64_t seq) {
+  if (r->n + 1 > r->cap) {
+    int64_t c = r->cap ? r->cap * 2 : 1024;
+    r->key_off = xrealloc(r->key_off, (c + 1) * 4); r->key_isnull = xrealloc(r->key_isnull, c);
+    r->count = xrealloc(r->count, c * 8); r->mn = xrealloc(r->mn, c * 8); r->mx = xrealloc(r->mx, c * 8);
+    r->avg = xrealloc(r->avg, c * 8); r->agg_isnull = xrealloc(r->agg_isnull, c);
+    r->ws = xrealloc(r->ws, c * 8); r->we = xrealloc(r->we, c * 8); r->seq = xrealloc(r->seq, c * 8);
+    if (r->cap == 0) r->key_off[0] = 0;
+    r->cap = c;
+  }
+  if (r->bytes + len > r->bytes_cap) { int64_t c = r->bytes_cap ? r->bytes_cap * 2 : 4096; while (c < r->bytes + len) c *= 2; r->key_bytes = xrealloc(r->key_bytes, c); r->bytes_cap = c; }
+  if (len) memcpy(r->key_bytes + r->bytes, key, (size_t)len);
+  r->bytes += len;
+  int64_t i = r->n++;
+  r->key_off[i + 1] = (int32_t)r->bytes; r->key_isnull[i] = (uint8_t)key_isnull;
+  r->count[i] = count; r->mn[i] = mn; r->mx[i] = mx; r->avg[i] = avg; r->agg_isnull[i] = (uint8_t)agg_isnull;
+  r->ws[i] = ws; r->we[i] = we; r->seq[i] = seq;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GroupedWindowAggStream                                                                      */
+
+struct orc_window {
+  orc_config cfg;
+  frame_t** frames; int64_t n_frames, frames_cap;   /* BTreeMap<SystemTime, frame>: kept sorted by start */
+  int has_wm; int64_t wm_ms;
+  int64_t seq;
+  results_t res;
+  char err[256];
+};
+
+orc_window* orc_create(const orc_config* cfg) {
+  orc_window* w = xcalloc(1, sizeof(orc_window));
+  w->cfg = *cfg;
+  return w;
+}
+void orc_destroy(orc_window* w) {
+  if (!w) return;
+  for (int64_t i = 0; i < w->n_frames; i++) frame_free(w->frames[i]);
+  free(w->frames); results_free(&w->res); free(w);
+}
+const char* orc_last_error(const orc_window* w) { return w->err; }
+int64_t orc_open_frames(const orc_window* w) { return w->n_frames; }
+int64_t orc_watermark(const orc_window* w) { return w->has_wm ? w->wm_ms : INT64_MIN; }
+void orc_clear_results(orc_window* w) { w->res.n = 0; w->res.bytes = 0; }
+void orc_get_results(orc_window* w, orc_result* o) {
+  static const int32_t zero_off[1] = {0};
+  o->n = w->res.n; o->key_off = w->res.key_off ? w->res.key_off : zero_off; o->key_bytes = w->res.key_bytes;
+  o->key_isnull = w->res.key_isnull; o->count = w->res.count; o->min = w->res.mn; o->max = w->res.mx; o->avg = w->res.avg;
+  o->agg_isnull = w->res.agg_isnull; o->window_start_ms = w->res.ws; o->window_end_ms = w->res.we; o->emit_seq = w->res.seq;
+}
+
+/* snap_to_window_start (streaming_window.rs:1088-1094): whole-second arithmetic */
+static int64_t snap_to_window_start(int64_t ts_ms, int64_t window_ms) {
+  int64_t wl_s = window_ms / 1000, t_s = ts_ms / 1000;
+  return (t_s / wl_s) * wl_s * 1000;
+}
+
+static frame_t* find_or_insert_frame(orc_window* w, int64_t start, int64_t end) {
+  int64_t lo = 0, hi = w->n_frames;
+  while (lo < hi) { int64_t mid = (lo + hi) / 2; if (w->frames[mid]->start_ms < start) lo = mid + 1; else hi = mid; }
+  if (lo < w->n_frames && w->frames[lo]->start_ms == start) return w->frames[lo];
+  if (w->n_frames + 1 > w->frames_cap) { w->frames_cap = w->frames_cap ? w->frames_cap * 2 : 16; w->frames = xrealloc(w->frames, w->frames_cap * sizeof(frame_t*)); }
+  memmove(w->frames + lo + 1, w->frames + lo, (size_t)(w->n_frames - lo) * sizeof(frame_t*));
+  w->frames[lo] = frame_new(start, end); w->n_frames++;
+  return w->frames[lo];
+}
+
+static int filter_pass(const orc_config* c, int64_t count, double mn, double mx, double avg, int agg_isnull) {
+  if (!c->has_filter) return 1;
+  int cmp;
+  if (c->filter_col == ORC_COL_COUNT) {
+    /* Int64 column against a literal: DataFusion coerces both sides to a common type; with a Float64
+     * literal the count is cast to Float64. */
+    cmp = total_cmp((double)count, c->filter_lit);
+  } else {
+    if (agg_isnull) return 0;      /* null predicate -> row dropped */
+    double v = c->filter_col == ORC_COL_MIN ? mn : c->filter_col == ORC_COL_MAX ? mx : avg;
+    cmp = total_cmp(v, c->filter_lit);
+  }
+  switch (c->filter_op) {
+    case ORC_OP_GT: return cmp > 0; case ORC_OP_GTE: return cmp >= 0; case ORC_OP_LT: return cmp < 0;
+    case ORC_OP_LTE: return cmp <= 0; case ORC_OP_EQ: return cmp == 0; default: return cmp != 0;
+  }
+}
+
+/* frame.evaluate() + add_window_columns_to_record_batch + FilterExec */
+static int64_t emit_frame(orc_window* w, frame_t* f) {
+  int64_t emitted = 0;
+  for (int64_t g = 0; g < f->n_groups; g++) {
+    int isnull = !f->mn_seen[g];                  /* NullState: null until first non-null value */
+    double avg = isnull ? 0.0 : f->sum[g] / (double)f->avg_cnt[g];
+    double mn = isnull ? 0.0 : f->mn[g], mx = isnull ? 0.0 : f->mx[g];
+    if (!filter_pass(&w->cfg, f->cnt[g], mn, mx, avg, isnull)) continue;
+    results_push(&w->res, f->g_bytes + f->g_off[g], f->g_off[g + 1] - f->g_off[g], (int32_t)g == f->null_gid,
+                 f->cnt[g], mn, mx, avg, isnull, f->start_ms, f->end_ms, w->seq);
+    emitted++;
+  }
+  return emitted;
+}
+
+static int batch_watermark(const orc_batch* b, int64_t* mn, int64_t* mx) {
+  int any = 0; int64_t lo = INT64_MAX, hi = INT64_MIN;
+  for (int64_t i = 0; i < b->n; i++) if (bit_get(b->ts_valid, i)) { int64_t t = b->ts[i]; any = 1; if (t < lo) lo = t; if (t > hi) hi = t; }
+  *mn = lo; *mx = hi; return any;
+}
+
+/* shared by the single- and multi-partition streams: everything poll_next_inner does for one
+ * non-empty batch EXCEPT that the batch watermark may be supplied by the caller (multi-partition mode). */
+static int64_t stream_push(orc_window* w, const orc_batch* b, int use_given_wm, int64_t given_min, int64_t given_max, int aggregate) {
+  int64_t L = w->cfg.window_ms, S = w->cfg.slide_ms;
+  int64_t mn, mx;
+  if (use_given_wm) { mn = given_min; mx = given_max; }
+  else if (!batch_watermark(b, &mn, &mx)) { snprintf(w->err, sizeof w->err, "all-null canonical_timestamp (reference: unwrap on None panics)"); return -1; }
+  if (L / 1000 == 0) { snprintf(w->err, sizeof w->err, "window length < 1 s: snap_to_window_start divides by zero"); return -2; }
+  if (mn < 0 || (S > 0 && mn - L < 0)) { snprintf(w->err, sizeof w->err, "timestamp before epoch(+window): duration_since(UNIX_EPOCH) panics"); return -3; }
+  if (aggregate) {
+    /* get_windows_for_watermark (streaming_window.rs:1053-1086) */
+    if (S > 0) {
+      int64_t cur = snap_to_window_start(mn - L, L);
+      while (cur <= mx) {
+        int64_t end = cur + L;
+        if (mn > end || mx < cur) { cur += S; continue; }
+        frame_push(find_or_insert_frame(w, cur, end), b);
+        cur += S;
+      }
+    } else {
+      int64_t cur = snap_to_window_start(mn, L);
+      while (cur <= mx) { int64_t end = cur + L; frame_push(find_or_insert_frame(w, cur, end), b); cur = end; }
+    }
+  }
+  /* process_watermark (:255-266) */
+  if (!w->has_wm || w->wm_ms <= mn) { w->wm_ms = mn; w->has_wm = 1; }
+  /* trigger_windows (:220-253) */
+  int64_t emitted = 0, keep = 0;
+  for (int64_t i = 0; i < w->n_frames; i++) {
+    frame_t* f = w->frames[i];
+    if (w->wm_ms >= f->end_ms) { emitted += emit_frame(w, f); frame_free(f); }
+    else w->frames[keep++] = f;
+  }
+  w->n_frames = keep;
+  return emitted;
+}
+
+int64_t orc_push(orc_window* w, const orc_batch* b) {
+  int64_t r = 0;
+  if (b->n > 0) r = stream_push(w, b, 0, 0, 0, 1);   /* empty batch: returns an empty batch, no trigger (:331,:343-345) */
+  w->seq++;
+  return r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* multi-threaded hash-partition mode (timed CPU baseline)                                     */
+
+struct orc_mt {
+  orc_config cfg; int P;
+  orc_window** parts;
+  /* per (partition) scratch batch for the current input batch: filled by the partitioning pass */
+  own_batch* sub;
+  char err[256];
+};
+
+orc_mt* orc_mt_create(const orc_config* cfg, int partitions) {
+  orc_mt* m = xcalloc(1, sizeof(orc_mt));
+  m->cfg = *cfg; m->P = partitions < 1 ? 1 : partitions;
+  m->parts = xcalloc(m->P, sizeof(orc_window*));
+  for (int p = 0; p < m->P; p++) m->parts[p] = orc_create(cfg);
+  return m;
+}
+void orc_mt_destroy(orc_mt* m) {
+  if (!m) return;
+  for (int p = 0; p < m->P; p++) orc_destroy(m->parts[p]);
+  free(m->parts); free(m);
+}
+
+typedef struct {
+  orc_mt* m; const orc_batch* batches; int64_t nb; int tid;
+  own_batch* subs;          /* [nb_chunk][P] sub-batches, produced in phase 1 */
+  int64_t* wm_min; int64_t* wm_max; int* wm_any;
+  int64_t c0, c1;           /* chunk range */
+  pthread_barrier_t* bar;
+  int64_t emitted; int err;
+} mt_arg;
+
+/* RepartitionExec(Hash): hash the key of every row and `take` the rows of each output partition
+ * (all columns are copied once more). */
+static void partition_batch(const orc_batch* b, int P, own_batch* subs /* [P] */) {
+  int64_t n = b->n;
+  int64_t kb = n > 0 ? (int64_t)b->key_off[n] - b->key_off[0] : 0;
+  int64_t bb = (b->barrier_off && n > 0) ? (int64_t)b->barrier_off[n] - b->barrier_off[0] : 0;
+  for (int p = 0; p < P; p++) {
+    own_batch* o = &subs[p];
+    own_batch_reserve(o, n, kb, bb);
+    o->n = 0; o->key_off[0] = 0; o->barrier_off[0] = 0;
+    o->has_ts_valid = b->ts_valid != NULL; o->has_val_valid = b->val_valid != NULL; o->has_key_valid = b->key_valid != NULL;
+    o->has_occ = b->occurred_at != NULL; o->has_bar = b->barrier_off != NULL;
+    if (o->has_ts_valid) memset(o->ts_valid, 0, (size_t)((n + 7) / 8 + 1));
+    if (o->has_val_valid) memset(o->val_valid, 0, (size_t)((n + 7) / 8 + 1));
+    if (o->has_key_valid) memset(o->key_valid, 0, (size_t)((n + 7) / 8 + 1));
+  }
+  for (int64_t i = 0; i < n; i++) {
+    int32_t a = b->key_off[i], e = b->key_off[i + 1];
+    uint64_t h = bit_get(b->key_valid, i) ? hash_bytes(b->key_bytes + a, e - a) : 0;
+    own_batch* o = &subs[(h >> 17) % (uint64_t)P];
+    int64_t m = o->n++;
+    o->ts[m] = b->ts[i]; if (o->has_ts_valid && bit_get(b->ts_valid, i)) bit_set(o->ts_valid, m);
+    o->val[m] = b->val[i]; if (o->has_val_valid && bit_get(b->val_valid, i)) bit_set(o->val_valid, m);
+    int32_t ko = o->key_off[m]; memcpy(o->key_bytes + ko, b->key_bytes + a, (size_t)(e - a)); o->key_off[m + 1] = ko + (e - a);
+    if (o->has_key_valid && bit_get(b->key_valid, i)) bit_set(o->key_valid, m);
+    if (o->has_occ) o->occurred_at[m] = b->occurred_at[i];
+    if (o->has_bar) { int32_t c = b->barrier_off[i], d = b->barrier_off[i + 1]; int32_t bo = o->barrier_off[m]; memcpy(o->barrier_bytes + bo, b->barrier_bytes + c, (size_t)(d - c)); o->barrier_off[m + 1] = bo + (d - c); }
+  }
+}
+
+static void* mt_worker(void* vp) {
+  mt_arg* a = (mt_arg*)vp; orc_mt* m = a->m; int P = m->P;
+  /* phase 1: threads split the chunk's batches and hash-partition them */
+  for (int64_t i = a->c0 + a->tid; i < a->c1; i += P) {
+    const orc_batch* b = &a->batches[i];
+    a->wm_any[i - a->c0] = batch_watermark(b, &a->wm_min[i - a->c0], &a->wm_max[i - a->c0]);
+    partition_batch(b, P, a->subs + (i - a->c0) * P);
+  }
+  pthread_barrier_wait(a->bar);
+  /* phase 2: thread p runs partition p's stream over its sub-batches in batch order */
+  orc_window* w = m->parts[a->tid];
+  for (int64_t i = a->c0; i < a->c1; i++) {
+    if (a->batches[i].n == 0) { w->seq++; continue; }
+    if (!a->wm_any[i - a->c0]) { a->err = -1; break; }
+    orc_batch v = own_as_view(&a->subs[(i - a->c0) * P + a->tid]);
+    int64_t r = stream_push(w, &v, 1, a->wm_min[i - a->c0], a->wm_max[i - a->c0], v.n > 0);
+    w->seq++;
+    if (r < 0) { a->err = (int)r; break; }
+    a->emitted += r;
+  }
+  return NULL;
+}
+
+int64_t orc_mt_push_many(orc_mt* m, const orc_batch* batches, int64_t nb) {
+  int P = m->P; const int64_t CH = 16;   /* batches per chunk: bounds the partition scratch */
+  own_batch* subs = xcalloc((size_t)(CH * P), sizeof(own_batch));
+  int64_t* wmn = xcalloc(CH, 8); int64_t* wmx = xcalloc(CH, 8); int* wany = xcalloc(CH, sizeof(int));
+  pthread_t* th = xcalloc(P, sizeof(pthread_t)); mt_arg* args = xcalloc(P, sizeof(mt_arg));
+  int64_t total = 0; int err = 0;
+  for (int64_t c0 = 0; c0 < nb && !err; c0 += CH) {
+    int64_t c1 = c0 + CH < nb ? c0 + CH : nb;
+    pthread_barrier_t bar; pthread_barrier_init(&bar, NULL, (unsigned)P);
+    for (int t = 0; t < P; t++) {
+      args[t] = (mt_arg){m, batches, nb, t, subs, wmn, wmx, wany, c0, c1, &bar, 0, 0};
+      pthread_create(&th[t], NULL, mt_worker, &args[t]);
+    }
+    for (int t = 0; t < P; t++) { pthread_join(th[t], NULL); total += args[t].emitted; if (args[t].err) err = args[t].err; }
+    pthread_barrier_destroy(&bar);
+  }
+  for (int64_t i = 0; i < CH * P; i++) own_batch_free(&subs[i]);
+  free(subs); free(wmn); free(wmx); free(wany); free(th); free(args);
+  return err ? err : total;
+}
+int64_t orc_mt_num_results(const orc_mt* m) { int64_t n = 0; for (int p = 0; p < m->P; p++) n += m->parts[p]->res.n; return n; }
+void orc_mt_get_results(orc_mt* m, int partition, orc_result* out) { orc_get_results(m->parts[partition], out); }
+void orc_mt_clear_results(orc_mt* m) { for (int p = 0; p < m->P; p++) orc_clear_results(m->parts[p]); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* synthetic sensor stream (emit_measurements.rs:30-33,45)                      */
+
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+int64_t orc_synth_fill(int64_t row0, int64_t n, uint64_t seed, int64_t groups, int64_t rows_per_ms, int64_t t0_ms,
+                       int32_t uuid_keys, int64_t* ts, double* val, int32_t* key_off, uint8_t* key_bytes) {
+  static const char hex[] = "0123456789abcdef";
+  int32_t o = 0; key_off[0] = 0;
+  for (int64_t k = 0; k < n; k++) {
+    uint64_t i = (uint64_t)(row0 + k);
+    uint64_t r = splitmix64(seed ^ i), r2 = splitmix64(r);
+    uint64_t key_id = (r >> 11) % (uint64_t)groups;
+    ts[k] = t0_ms + (int64_t)(i / (uint64_t)rows_per_ms);
+    val[k] = ((double)(r2 >> 11) * 0x1.0p-53) * 115.0;
+    uint8_t* p = key_bytes + o;
+    if (uuid_keys) {
+      uint64_t h1 = splitmix64(key_id), h2 = splitmix64(h1);
+      int q = 0;
+      for (int d = 0; d < 32; d++) {
+        uint64_t src = d < 16 ? h1 : h2; int sh = 60 - 4 * (d & 15);
+        if (d == 8 || d == 12 || d == 16 || d == 20) p[q++] = '-';
+        p[q++] = (uint8_t)hex[(src >> sh) & 15];
+      }
+      o += 36;
+    } else {
+      memcpy(p, "sensor_", 7);
+      char tmp[24]; int nd = 0; uint64_t v = key_id;
+      do { tmp[nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+      for (int d = 0; d < nd; d++) p[7 + d] = (uint8_t)tmp[nd - 1 - d];
+      o += 7 + nd;
+    }
+    key_off[k + 1] = o;
+  }
+  return o;
+}

@@ -1,0 +1,101 @@
+"""Shared test helpers: row-list <-> columnar batches, random streams, row comparison."""
+import math
+import struct
+
+import numpy as np
+
+from oracle import Batch
+
+
+def pack_bitmap(flags):
+    n = len(flags)
+    bm = np.zeros((n + 7) // 8 + 1, np.uint8)
+    for i, f in enumerate(flags):
+        if f:
+            bm[i >> 3] |= 1 << (i & 7)
+    return bm
+
+
+def rows_to_batch(rows, force_validity=False) -> Batch:
+    """rows: list of (ts|None, val|None, key(bytes)|None)."""
+    n = len(rows)
+    ts = np.array([r[0] if r[0] is not None else 0 for r in rows], np.int64).reshape(n)
+    val = np.array([r[1] if r[1] is not None else 0.0 for r in rows], np.float64).reshape(n)
+    off = np.zeros(n + 1, np.int32)
+    chunks = []
+    for i, r in enumerate(rows):
+        k = r[2] if r[2] is not None else b""
+        chunks.append(k)
+        off[i + 1] = off[i] + len(k)
+    kb = np.frombuffer(b"".join(chunks) + b"\0" * 16, np.uint8).copy()
+    b = Batch(ts=ts, val=val, key_off=off, key_bytes=kb)
+    if force_validity or any(r[0] is None for r in rows):
+        b.ts_valid = pack_bitmap([r[0] is not None for r in rows])
+    if force_validity or any(r[1] is None for r in rows):
+        b.val_valid = pack_bitmap([r[1] is not None for r in rows])
+    if force_validity or any(r[2] is None for r in rows):
+        b.key_valid = pack_bitmap([r[2] is not None for r in rows])
+    return b
+
+
+def batch_to_rows(b: Batch):
+    out = []
+    kb = b.key_bytes.tobytes()
+    for i in range(b.n):
+        def ok(bm):
+            return bm is None or (bm[i >> 3] >> (i & 7)) & 1
+        out.append((int(b.ts[i]) if ok(b.ts_valid) else None, float(b.val[i]) if ok(b.val_valid) else None,
+                    kb[b.key_off[i]:b.key_off[i + 1]] if ok(b.key_valid) else None))
+    return out
+
+
+def bits(d):
+    return None if d is None else struct.pack("<d", d)
+
+
+def assert_rows_equal(got, want, rel=1e-9, check_seq=False):
+    """count/min/max bit-exact, avg within `rel` relative (north_star tolerance)."""
+    def key(r):
+        return (r[0], r[1], r[2] is None, r[2] or b"", (r[7] if check_seq else 0))
+    g, w = sorted(got, key=key), sorted(want, key=key)
+    assert len(g) == len(w), f"row count {len(g)} != {len(w)}"
+    for a, b in zip(g, w):
+        assert a[:4] == b[:4], f"{a} != {b}"
+        assert bits(a[4]) == bits(b[4]), f"min differs: {a} != {b}"
+        assert bits(a[5]) == bits(b[5]), f"max differs: {a} != {b}"
+        if a[6] is None or b[6] is None:
+            assert a[6] is None and b[6] is None, f"{a} != {b}"
+        elif math.isnan(b[6]) or math.isinf(b[6]):
+            assert bits(a[6]) == bits(b[6]) or (math.isnan(a[6]) and math.isnan(b[6])), f"{a} != {b}"
+        else:
+            assert abs(a[6] - b[6]) <= rel * max(abs(b[6]), 1e-300), f"avg differs: {a} != {b}"
+        if check_seq:
+            assert a[7] == b[7], f"emit seq differs: {a} != {b}"
+
+
+def random_stream(rng, n_batches, rows_per_batch, n_keys, t0=1_700_000_000_000, span_ms=400, jitter_ms=0,
+                  null_frac=0.0, special_vals=False, ragged=False):
+    """Mostly in-order batches of (ts,val,key) rows; jitter_ms>0 makes batches overlap / arrive late."""
+    batches = []
+    t = t0
+    for _ in range(n_batches):
+        n = int(rng.integers(0, rows_per_batch + 1)) if ragged else rows_per_batch
+        rows = []
+        for _ in range(n):
+            ts = t + int(rng.integers(0, span_ms)) - (int(rng.integers(0, jitter_ms)) if jitter_ms else 0)
+            k = int(rng.integers(0, n_keys))
+            key = b"sensor_%d" % k if k % 7 else b"k" * (k % 40)   # some long / empty keys
+            val = float(rng.random() * 115.0)
+            if special_vals:
+                val = [val, 0.0, -0.0, float("nan"), float("inf"), float("-inf"), 1e308, -1e308][int(rng.integers(0, 8))]
+            r = [ts, val, key]
+            if null_frac:
+                for j in range(3):
+                    if rng.random() < null_frac:
+                        r[j] = None
+            rows.append(tuple(r))
+        if rows and all(r[0] is None for r in rows):
+            rows[0] = (t, rows[0][1], rows[0][2])
+        batches.append(rows)
+        t += span_ms
+    return batches
