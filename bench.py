@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- rows/s of the windowed group-aggregate hot path on synthetic sensor batches (BASELINE.json metric).
+
+Own arm   : `python bench.py --gpus N --steps K --warmup W`   (N>1: one rank per GPU under torchrun)
+Reference : `python bench.py --impl reference ...`            (the CPU restatement of the reference algorithm -- the Rust
+            reference cannot be built in this image -- on all host cores; rank 0 only)
+
+A "step" is one pass of the operator over the whole synthetic stream of the workload (configs[1] of BASELINE.json:
+tumbling 1 s, key sensor_name, count/min/max/avg(reading), 1e9 rows, 100K groups, 64Ki-row batches) with a fresh
+operator handle: push every batch, close the last window, collect the emitted rows.
+  value : inputs already resident in HBM (dnz_window_push_device / poll_device), device timed with CUDA events on the
+          stream the kernels run on.
+  e2e   : the same metric through the reference-facing C ABI with HOST Arrow buffers in pinned memory
+          (dnz_window_push / dnz_window_poll): host->device copies of the inputs and device->host copies of the emitted
+          rows are inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T0 = 1_700_000_000_000
+WORKLOADS = {
+    # name: (rows, groups, rows_per_ms, window_ms, slide_ms, filter, uuid_keys)
+    "cfg1": dict(rows=10_000_000, groups=1_000, rows_per_ms=1_000, window_ms=1000, slide_ms=0, filt=None, uuid=False),
+    "cfg2": dict(rows=1_000_000_000, groups=100_000, rows_per_ms=10_000, window_ms=1000, slide_ms=0, filt=None, uuid=False),
+    "cfg3": dict(rows=1_000_000_000, groups=1_000_000, rows_per_ms=10_000, window_ms=10_000, slide_ms=1000, filt=None, uuid=False),
+    "cfg4": dict(rows=1_000_000_000, groups=100_000, rows_per_ms=10_000, window_ms=1000, slide_ms=0, filt=("max", ">", 113.0), uuid=False),
+    "cfg5": dict(rows=1_000_000_000, groups=10_000_000, rows_per_ms=8_000, window_ms=60_000, slide_ms=5000, filt=None, uuid=True),
+}
+BATCH_ROWS = 65536
+AGGS = [("count", "reading", "count"), ("min", "reading", "min"), ("max", "reading", "max"), ("avg", "reading", "average")]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's row count (debugging only)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the stream fed from host memory in the e2e leg (0 = auto)")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--max-rows-per-launch", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / baseline here, never the thing shipped)
+def cpu_baseline(wl, rows, threads):
+    """Times the multi-threaded CPU restatement of the reference algorithm on a bounded sample of the workload."""
+    from oracle import OracleMT, synth_batch
+    from tests.helpers import rows_to_batch
+    nb = max(1, rows // BATCH_ROWS)
+    batches = [synth_batch(i * BATCH_ROWS, BATCH_ROWS, groups=wl["groups"], rows_per_ms=wl["rows_per_ms"], uuid_keys=wl["uuid"],
+                           extra_columns=True) for i in range(nb)]
+    last = int(batches[-1].ts[-1])
+    # closing batch: one row per key would be needed per partition in the reference; the deterministic shared watermark of
+    # the restatement lets a single sentinel row close every partition's windows
+    batches.append(rows_to_batch([((last // 1000 + 1) * 1000 + 2 * wl["window_ms"], 1.0, b"sentinel")]))
+    m = OracleMT(wl["window_ms"], wl["slide_ms"], wl["filt"], partitions=threads)
+    t = time.perf_counter()
+    m.push_many(batches)
+    dt = time.perf_counter() - t
+    out_rows = m.num_results()
+    m.close()
+    return nb * BATCH_ROWS / dt, dt, nb * BATCH_ROWS, out_rows
+
+
+def auto_cpu_rows(wl, threads):
+    # ~10-30 s of CPU work: single-thread rate of the restatement is ~5-10 M rows/s per overlapping window
+    per_row_windows = max(1, wl["window_ms"] // (wl["slide_ms"] or wl["window_ms"]))
+    est_rate = 4e6 * min(threads, 32) / per_row_windows
+    return int(max(BATCH_ROWS * 8, min(200_000_000, est_rate * 15)) // BATCH_ROWS * BATCH_ROWS)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = args.cpu_rows or auto_cpu_rows(wl, threads)
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, n, _ = cpu_baseline(wl, rows, threads)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    sample = f"{rows} rows ({rows // BATCH_ROWS} batches of {BATCH_ROWS}) of the {args.workload} stream per step"
+    line = {"impl": "reference", "metric": "rows/sec windowed group-agg on synthetic sensor batches", "value": value, "unit": "rows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([d for _, d in rates]) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, wl, 1),
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference algorithm (oracle/, hash-partitioned over all host cores); the Rust "
+                    "reference itself cannot be built in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, world):
+    return {"workload": f"{args.workload}: {'tumbling' if not wl['slide_ms'] else 'sliding'} {wl['window_ms']}ms"
+                        f"{'/' + str(wl['slide_ms']) + 'ms' if wl['slide_ms'] else ''}, key sensor_name, count/min/max/avg(reading), "
+                        f"{wl['rows']} rows/GPU, {wl['groups']} groups/GPU, {BATCH_ROWS}-row batches"
+                        f"{', filter ' + ' '.join(map(str, wl['filt'])) if wl['filt'] else ''}",
+            "rows_per_gpu": wl["rows"], "groups_per_gpu": wl["groups"], "batch_rows": BATCH_ROWS, "window_ms": wl["window_ms"],
+            "slide_ms": wl["slide_ms"], "parallelism": f"key-hash partitions x{world} (one operator per GPU, disjoint key sets, no data-path collective)",
+            "l2": "inputs (>= 10x L2) are streamed once per step; no explicit flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def pinned_host_batches(d, wl, rows, rank, world):
+    """Arrow RecordBatches of the canonical schema whose buffers live in page-locked memory from dnz_host_alloc."""
+    import pyarrow as pa
+    from oracle import lib as olib
+    L, OL = d.lib(), olib()
+    nb = rows // BATCH_ROWS
+    maxlen = 36 if wl["uuid"] else 8 + len(str((wl["groups"] - 1) * world + rank))
+    sizes = dict(ts=8 * BATCH_ROWS, val=8 * BATCH_ROWS, off=4 * (BATCH_ROWS + 1), kb=maxlen * BATCH_ROWS)
+    stride = sum((v + 255) // 256 * 256 for v in sizes.values())
+    base = L.dnz_host_alloc(stride * nb)
+    if not base:
+        raise MemoryError("dnz_host_alloc failed")
+    barrier = pa.array(["no_barrier"] * BATCH_ROWS, pa.utf8())
+    schema = d.canonical_schema()
+    meta_fields = list(schema.field(3).type)
+    batches, in_bytes = [], 0
+
+    def fill(b):
+        p = base + b * stride
+        a_ts, a_val = p, p + 8 * BATCH_ROWS
+        a_off = a_val + 8 * BATCH_ROWS
+        a_kb = (a_off + 4 * (BATCH_ROWS + 1) + 255) // 256 * 256
+        used = OL.orc_synth_fill(b * BATCH_ROWS, BATCH_ROWS, 42 + rank, wl["groups"], wl["rows_per_ms"], T0, 1 if wl["uuid"] else 0,
+                                 world, rank, a_ts, a_val, a_off, a_kb)
+        return a_ts, a_val, a_off, a_kb, used
+    # generate with a few threads (ctypes releases the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        addrs = list(ex.map(fill, range(nb)))
+    keep = (L, base)
+    for a_ts, a_val, a_off, a_kb, used in addrs:
+        fb = lambda a, n: pa.foreign_buffer(a, n, base=keep)
+        ts = pa.Array.from_buffers(pa.timestamp("ms"), BATCH_ROWS, [None, fb(a_ts, 8 * BATCH_ROWS)])
+        occ = pa.Array.from_buffers(pa.int64(), BATCH_ROWS, [None, fb(a_ts, 8 * BATCH_ROWS)])
+        val = pa.Array.from_buffers(pa.float64(), BATCH_ROWS, [None, fb(a_val, 8 * BATCH_ROWS)])
+        key = pa.Array.from_buffers(pa.utf8(), BATCH_ROWS, [None, fb(a_off, 4 * (BATCH_ROWS + 1)), fb(a_kb, max(used, 1))])
+        meta = pa.StructArray.from_arrays([barrier, ts], fields=meta_fields)
+        batches.append(pa.RecordBatch.from_arrays([occ, val, key, meta], schema=schema))
+        in_bytes += 20 * BATCH_ROWS + 4 + used
+    return batches, in_bytes, base
+
+
+def export_all(d, batches):
+    """Pre-export RecordBatches to Arrow C-Data structs (binding overhead, outside the timed region)."""
+    arr = (d.capi.ArrowArrayC * len(batches))()
+    for i, b in enumerate(batches):
+        b._export_to_c(C.addressof(arr[i]))
+    return arr
+
+
+def main():
+    args = parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.rows:
+        wl["rows"] = args.rows
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import denormalized_b200 as d
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = d.lib()
+    stream = torch.cuda.current_stream()
+    rows, G = wl["rows"], wl["groups"]
+    last_ts = T0 + (rows - 1) // wl["rows_per_ms"]
+    close_wm = (last_ts // 1000 + 1) * 1000 + 2 * wl["window_ms"]
+
+    # ---- device-resident input: every rank owns a disjoint key set (key id * world + rank), same window structure
+    dev = d.DeviceBatches(rows, BATCH_ROWS, seed=42 + rank, groups=G, rows_per_ms=wl["rows_per_ms"], uuid_keys=wl["uuid"], device=local,
+                          key_mul=world, key_add=rank)
+
+    def new_window(flags=0):
+        return d.GpuStreamingWindow(d.canonical_schema(), "sensor_name", AGGS, wl["window_ms"], wl["slide_ms"], wl["filt"], device=local,
+                                    flags=flags, expected_groups=G, max_rows_per_launch=args.max_rows_per_launch,
+                                    cuda_stream=stream.cuda_stream)
+
+    def step_device(w):
+        w.push_device(dev)
+        w.flush(close_wm)
+        return w.poll_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out_rows = 0
+    for _ in range(args.warmup):
+        w = new_window(); r = step_device(w); out_rows = r.n_rows; w.close()
+    wins = [new_window(d.capi.FLAG_KERNEL_TIMING) for _ in range(args.steps)]
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for w in wins:
+        step_device(w)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    stats = [w.stats() for w in wins]
+    for w in wins:
+        w.close()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = rows * world * args.steps / (ms * 1e-3)
+    agg_ms = sum(s["agg_kernel_ms"] for s in stats); agg_bytes = sum(s["agg_algorithmic_bytes"] for s in stats)
+    agg_launches = sum(s["agg_launches"] for s in stats); launches = sum(s["total_launches"] for s in stats)
+    peak, peak_src = measured_peak()
+    achieved = agg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "agg_kernel_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- e2e: host Arrow buffers (pinned) through dnz_window_push / dnz_window_poll
+    e2e = None
+    if not args.no_e2e:
+        free_gb = 64.0
+        try:
+            import psutil
+            free_gb = psutil.virtual_memory().available / 2**30
+        except Exception:
+            pass
+        e2e_rows = args.e2e_rows or int(min(rows, 268_435_456, max(BATCH_ROWS, (free_gb / 4 / world) * 2**30 / 40)))
+        e2e_rows = max(BATCH_ROWS, e2e_rows // BATCH_ROWS * BATCH_ROWS)
+        hb, in_bytes, base = pinned_host_batches(d, wl, e2e_rows, rank, world)
+        e_last = T0 + (e2e_rows - 1) // wl["rows_per_ms"]
+        e_close = (e_last // 1000 + 1) * 1000 + 2 * wl["window_ms"]
+        n_e2e_steps = args.warmup + args.steps
+        exported = [export_all(d, hb) for _ in range(n_e2e_steps)]
+        e_wins = [new_window() for _ in range(n_e2e_steps)]
+        ca, cs, has = d.capi.ArrowArrayC(), d.capi.ArrowSchemaC(), C.c_int32(0)
+        push, poll, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_flush
+        rel = C.CFUNCTYPE(None, C.c_void_p)
+
+        def step_host(i):
+            h = e_wins[i]._h
+            arr = exported[i]
+            for k in range(len(hb)):
+                rc = push(h, C.byref(arr[k]))
+                if rc:
+                    raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
+            rc = flush(h, e_close) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))
+            if rc:
+                raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
+            n_out = ca.length
+            rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
+            return n_out
+        for i in range(args.warmup):
+            step_host(i)
+        d2h0 = sum(w.stats()["d2h_bytes"] for w in e_wins)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, n_e2e_steps):
+            e_out = step_host(i)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3 * 0.0)   # device clock; the wall clock is reported beside it
+        te = torch.tensor([ems, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ems, wall_ms = float(te[0].item()), float(te[1].item())
+        d2h = (sum(w.stats()["d2h_bytes"] for w in e_wins) - d2h0) // args.steps
+        h2d = e_wins[-1].stats()["h2d_bytes"]
+        for w in e_wins:
+            w.close()
+        e2e = {"value": e2e_rows * world * args.steps / (ems * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows * world, "ms_per_step": ems / args.steps,
+               "wall_ms_per_step": wall_ms / args.steps, "rows_out_per_step": int(e_out),
+               "sample": f"first {e2e_rows} rows/GPU of the stream, Arrow buffers in pinned host memory (dnz_host_alloc)"}
+        del hb, exported
+        L.dnz_host_free(base)
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        crow = args.cpu_rows or auto_cpu_rows(wl, threads)
+        rate, dt, n, _ = cpu_baseline(wl, crow, threads)
+        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{n} rows ({n // BATCH_ROWS} batches) of the {args.workload} stream, {dt:.1f} s, oracle/ hash-partitioned over {threads} threads"}
+
+    if rank == 0:
+        line = {"metric": "rows/sec windowed group-agg on synthetic sensor batches", "value": value, "unit": "rows/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, wl, world),
+                "rows_out_per_step": int(out_rows), "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_aggregate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                             "launches": int(agg_launches), "avg_launch_ms": agg_ms / max(agg_launches, 1),
+                             "algorithmic_bytes_per_row": agg_bytes / max(rows * args.steps, 1)},
+                "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

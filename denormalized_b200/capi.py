@@ -1,0 +1,308 @@
+"""ctypes binding of include/dnz_gpu.h (the drop-in boundary).  Test/bench convenience only: the reference-facing
+host code is the C++ mirror in cpp/ (and the Rust shim sketched in INTEGRATION.md).
+
+`GpuStreamingWindow` plays the role of one partition's GroupedWindowAggStream
+(crates/core/src/physical_plan/continuous/grouped_window_agg_stream.rs:63-82): push RecordBatches, poll emitted
+windows.  It fails loudly when the CUDA library is missing; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdnz_gpu.so")
+
+AGG_KINDS = {"count": 0, "min": 1, "max": 2, "avg": 3, "average": 3, "sum": 4}
+OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
+FLAG_KERNEL_TIMING = 1
+FLAG_FORCE_GENERIC = 2
+INTERNAL_METADATA_COLUMN = "_streaming_internal_metadata"   # crates/common/src/lib.rs:5
+
+
+class DnzError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dnz error {code}: {msg}")
+        self.code = code
+
+
+class ArrowSchemaC(C.Structure):
+    pass
+
+
+class ArrowArrayC(C.Structure):
+    pass
+
+
+ArrowSchemaC._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                         ("n_children", C.c_int64), ("children", C.POINTER(C.POINTER(ArrowSchemaC))),
+                         ("dictionary", C.POINTER(ArrowSchemaC)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+ArrowArrayC._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                        ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)),
+                        ("children", C.POINTER(C.POINTER(ArrowArrayC))), ("dictionary", C.POINTER(ArrowArrayC)),
+                        ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class _Agg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("arg_column", C.c_int32), ("alias", C.c_char_p)]
+
+
+class _Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("key_column", C.c_int32), ("n_aggs", C.c_int32),
+                ("aggs", C.POINTER(_Agg)), ("window_ms", C.c_int64), ("slide_ms", C.c_int64), ("has_filter", C.c_int32),
+                ("filter_agg", C.c_int32), ("filter_op", C.c_int32), ("flags", C.c_uint32), ("filter_literal", C.c_double),
+                ("expected_groups", C.c_int64), ("max_rows_per_launch", C.c_int64), ("cuda_stream", C.c_void_p)]
+
+
+class DeviceBatchC(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("ts", C.c_void_p), ("ts_valid", C.c_void_p), ("val", C.c_void_p),
+                ("val_valid", C.c_void_p), ("key_off", C.c_void_p), ("key_bytes", C.c_void_p), ("key_valid", C.c_void_p)]
+
+
+class DeviceResultC(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("key_bytes_len", C.c_int64), ("key_off", C.c_void_p), ("key_bytes", C.c_void_p),
+                ("key_valid", C.c_void_p), ("count", C.c_void_p), ("min", C.c_void_p), ("max", C.c_void_p),
+                ("avg", C.c_void_p), ("sum", C.c_void_p), ("agg_valid", C.c_void_p), ("window_start_ms", C.c_void_p),
+                ("window_end_ms", C.c_void_p)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("rows_in", C.c_int64), ("batches_in", C.c_int64), ("rows_out", C.c_int64), ("windows_emitted", C.c_int64),
+                ("groups", C.c_int64), ("agg_launches", C.c_int64), ("total_launches", C.c_int64),
+                ("agg_kernel_ms", C.c_double), ("agg_algorithmic_bytes", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("deferred_rows", C.c_int64), ("generic_tiles", C.c_int64),
+                ("fast_tiles", C.c_int64), ("late_batches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_device",
+           "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
+           "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_export_partials",
+           "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
+           "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free"]
+
+_lib = None
+
+
+def library_path() -> str:
+    return _SO
+
+
+def lib():
+    """Load libdnz_gpu.so.  Raises if it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C denormalized_b200/csrc).  denormalized_b200 has no CPU fallback.")
+        L = C.CDLL(_SO)
+        L.dnz_window_create.restype = C.c_int32
+        L.dnz_window_create.argtypes = [C.POINTER(_Config), C.POINTER(ArrowSchemaC), C.POINTER(C.c_void_p)]
+        L.dnz_window_push.restype = C.c_int32
+        L.dnz_window_push.argtypes = [C.c_void_p, C.POINTER(ArrowArrayC)]
+        L.dnz_window_push_device.restype = C.c_int32
+        L.dnz_window_push_device.argtypes = [C.c_void_p, C.POINTER(DeviceBatchC), C.c_int64]
+        L.dnz_window_poll.restype = C.c_int32
+        L.dnz_window_poll.argtypes = [C.c_void_p, C.POINTER(ArrowArrayC), C.POINTER(ArrowSchemaC), C.POINTER(C.c_int32)]
+        L.dnz_window_poll_device.restype = C.c_int32
+        L.dnz_window_poll_device.argtypes = [C.c_void_p, C.POINTER(DeviceResultC)]
+        L.dnz_window_flush.restype = C.c_int32
+        L.dnz_window_flush.argtypes = [C.c_void_p, C.c_int64]
+        L.dnz_window_stats.restype = C.c_int32
+        L.dnz_window_stats.argtypes = [C.c_void_p, C.POINTER(StatsC)]
+        L.dnz_window_reset_stats.restype = C.c_int32
+        L.dnz_window_reset_stats.argtypes = [C.c_void_p]
+        L.dnz_window_watermark.restype = C.c_int64
+        L.dnz_window_watermark.argtypes = [C.c_void_p]
+        L.dnz_window_last_error.restype = C.c_char_p
+        L.dnz_window_last_error.argtypes = [C.c_void_p]
+        L.dnz_window_destroy.argtypes = [C.c_void_p]
+        L.dnz_window_set_exchange.restype = C.c_int32
+        L.dnz_window_set_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.dnz_host_alloc.restype = C.c_void_p
+        L.dnz_host_alloc.argtypes = [C.c_int64]
+        L.dnz_host_free.argtypes = [C.c_void_p]
+        L.dnz_device_alloc.restype = C.c_void_p
+        L.dnz_device_alloc.argtypes = [C.c_int32, C.c_int64]
+        L.dnz_device_free.argtypes = [C.c_int32, C.c_void_p]
+        L.dnz_device_count.restype = C.c_int32
+        L.dnz_memcpy.restype = C.c_int32
+        L.dnz_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        L.dnz_synth_generate.restype = C.c_int32
+        L.dnz_synth_generate.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(DeviceBatchC), C.c_int64]
+        L.dnz_synth_bytes.restype = C.c_int64
+        L.dnz_synth_bytes.argtypes = [C.c_void_p]
+        L.dnz_synth_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def canonical_schema() -> pa.Schema:
+    """The reference's canonical Kafka schema for the sensor example (kafka_config.rs:186-214)."""
+    meta = pa.struct([pa.field("barrier_batch", pa.utf8(), nullable=False),
+                      pa.field("canonical_timestamp", pa.timestamp("ms"))])
+    return pa.schema([pa.field("occurred_at_ms", pa.int64()), pa.field("reading", pa.float64()),
+                      pa.field("sensor_name", pa.utf8()), pa.field(INTERNAL_METADATA_COLUMN, meta, nullable=False)])
+
+
+def _bitmap_to_mask(bm, n):
+    if bm is None:
+        return None
+    bits = np.unpackbits(np.asarray(bm, np.uint8), bitorder="little")[:n]
+    return bits == 0          # pyarrow mask: True = null
+
+
+def make_record_batch(ts, val, key_off, key_bytes, ts_valid=None, val_valid=None, key_valid=None) -> pa.RecordBatch:
+    """Canonical-schema RecordBatch from columnar numpy buffers (validity = Arrow LSB bitmaps or None)."""
+    n = len(ts)
+
+    def vbuf(bm):
+        return None if bm is None else pa.py_buffer(np.ascontiguousarray(bm[:(n + 7) // 8 + 1]))
+    ts_arr = pa.Array.from_buffers(pa.timestamp("ms"), n, [vbuf(ts_valid), pa.py_buffer(np.ascontiguousarray(ts, np.int64))])
+    val_arr = pa.Array.from_buffers(pa.float64(), n, [vbuf(val_valid), pa.py_buffer(np.ascontiguousarray(val, np.float64))])
+    key_arr = pa.Array.from_buffers(pa.utf8(), n, [vbuf(key_valid), pa.py_buffer(np.ascontiguousarray(key_off, np.int32)),
+                                                   pa.py_buffer(np.ascontiguousarray(key_bytes, np.uint8))])
+    occ = pa.array(np.where(np.ones(n, bool) if ts_valid is None else ~_bitmap_to_mask(ts_valid, n), ts, 0), pa.int64())
+    barrier = pa.array(["no_barrier"] * n, pa.utf8())
+    meta = pa.StructArray.from_arrays([barrier, ts_arr], fields=list(canonical_schema().field(3).type))
+    return pa.RecordBatch.from_arrays([occ, val_arr, key_arr, meta], schema=canonical_schema())
+
+
+class DeviceBatches:
+    """Synthetic sensor batches generated directly in device memory (dnz_synth_generate)."""
+
+    def __init__(self, n_rows, batch_rows=65536, *, row0=0, seed=42, groups=1000, rows_per_ms=1000,
+                 t0_ms=1_700_000_000_000, uuid_keys=False, device=0, key_mul=1, key_add=0):
+        L = lib()
+        self.n_batches = (n_rows + batch_rows - 1) // batch_rows
+        self.n_rows = n_rows
+        self.array = (DeviceBatchC * self.n_batches)()
+        self._arena = C.c_void_p()
+        rc = L.dnz_synth_generate(device, row0, n_rows, batch_rows, seed, groups, rows_per_ms, t0_ms, 1 if uuid_keys else 0,
+                                  key_mul, key_add, C.byref(self._arena), self.array, self.n_batches)
+        if rc != 0:
+            raise DnzError(rc, L.dnz_window_last_error(None).decode())
+        self.algorithmic_bytes = int(L.dnz_synth_bytes(self._arena))
+
+    def free(self):
+        if self._arena:
+            lib().dnz_synth_free(self._arena)
+            self._arena = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class GpuStreamingWindow:
+    """One partition of the GPU streaming-window operator (StreamingWindowExec::execute ->
+    GroupedWindowAggStream, streaming_window.rs:421-482) with the FilterExec above it fused in.
+
+    aggs: list of (kind, input column name, alias); filt: (alias, op, literal) or None."""
+
+    def __init__(self, schema: pa.Schema, key, aggs, window_ms, slide_ms=0, filt=None, *, device=0, flags=0,
+                 expected_groups=0, max_rows_per_launch=0, cuda_stream=None):
+        self._L = lib()
+        self._h = C.c_void_p()
+        names = schema.names
+        self._aliases = [a[2].encode() for a in aggs]
+        arr = (_Agg * len(aggs))(*[_Agg(AGG_KINDS[k], names.index(col), al) for (k, col, _), al in zip(aggs, self._aliases)])
+        cfg = _Config(1, device, names.index(key), len(aggs), arr, int(window_ms), int(slide_ms or 0), 0, 0, 0, flags, 0.0,
+                      expected_groups, max_rows_per_launch, cuda_stream)
+        if filt is not None:
+            alias, op, lit = filt
+            cfg.has_filter, cfg.filter_agg, cfg.filter_op, cfg.filter_literal = 1, [a[2] for a in aggs].index(alias), OPS[op], float(lit)
+        cs = ArrowSchemaC()
+        schema._export_to_c(C.addressof(cs))
+        try:
+            rc = self._L.dnz_window_create(C.byref(cfg), C.byref(cs), C.byref(self._h))
+        finally:
+            if cs.release:
+                C.CFUNCTYPE(None, C.POINTER(ArrowSchemaC))(cs.release)(C.byref(cs))
+        if rc != 0:
+            raise DnzError(rc, self._L.dnz_window_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DnzError(rc, self._L.dnz_window_last_error(self._h).decode())
+
+    def push(self, batch: pa.RecordBatch):
+        ca = ArrowArrayC()
+        batch._export_to_c(C.addressof(ca))
+        rc = self._L.dnz_window_push(self._h, C.byref(ca))
+        if ca.release:   # not moved (error path)
+            C.CFUNCTYPE(None, C.POINTER(ArrowArrayC))(ca.release)(C.byref(ca))
+        self._check(rc)
+
+    def push_device(self, batches: DeviceBatches | None = None, array=None, n=None):
+        arr = batches.array if batches is not None else array
+        cnt = batches.n_batches if batches is not None else n
+        self._check(self._L.dnz_window_push_device(self._h, arr, cnt))
+
+    def poll(self) -> pa.RecordBatch:
+        ca, cs, has = ArrowArrayC(), ArrowSchemaC(), C.c_int32(0)
+        self._check(self._L.dnz_window_poll(self._h, C.byref(ca), C.byref(cs), C.byref(has)))
+        return pa.RecordBatch._import_from_c(C.addressof(ca), C.addressof(cs))
+
+    def poll_device(self) -> DeviceResultC:
+        r = DeviceResultC()
+        self._check(self._L.dnz_window_poll_device(self._h, C.byref(r)))
+        return r
+
+    def fetch_device_result(self, r: DeviceResultC) -> pa.RecordBatch | None:
+        """Copy a device-resident result to host arrays (test helper)."""
+        n = r.n_rows
+
+        def get(ptr, dt, m):
+            a = np.empty(m, dt)
+            if m:
+                rc = self._L.dnz_memcpy(a.ctypes.data, ptr, a.nbytes, 2)
+                if rc:
+                    raise DnzError(rc, "memcpy")
+            return a
+        off = np.concatenate([get(r.key_off, np.int32, n), np.array([r.key_bytes_len], np.int32)])
+        kb = get(r.key_bytes, np.uint8, r.key_bytes_len).tobytes()
+        kv = get(r.key_valid, np.uint8, n)
+        av = get(r.agg_valid, np.uint8, n)
+        return {"key": [kb[off[i]:off[i + 1]] if kv[i] else None for i in range(n)],
+                "count": get(r.count, np.int64, n), "min": get(r.min, np.float64, n), "max": get(r.max, np.float64, n),
+                "avg": get(r.avg, np.float64, n), "sum": get(r.sum, np.float64, n), "agg_valid": av,
+                "window_start": get(r.window_start_ms, np.int64, n), "window_end": get(r.window_end_ms, np.int64, n)}
+
+    def flush(self, watermark_ms: int):
+        self._check(self._L.dnz_window_flush(self._h, int(watermark_ms)))
+
+    def stats(self) -> dict:
+        s = StatsC()
+        self._L.dnz_window_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._L.dnz_window_reset_stats(self._h)
+
+    @property
+    def watermark(self):
+        v = int(self._L.dnz_window_watermark(self._h))
+        return None if v == -(2 ** 63) else v
+
+    def set_exchange(self, rank, world):
+        self._check(self._L.dnz_window_set_exchange(self._h, rank, world))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dnz_window_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,447 @@
+// dnz_kernels.cu -- sm_100a kernels of the windowed grouped aggregate.
+//
+//   k_tile_scan      per-tile byte ranges + timestamp min/max  (RecordBatchWatermark::try_from, utils/time.rs:31-57)
+//   k_aggregate      TMA-staged (cp.async.bulk + mbarrier ring) key interning + count/min/max/sum reduction
+//                    (GroupedAggWindowFrame::push + group_aggregate_batch, grouped_window_agg_stream.rs:501-605;
+//                     DataFusion GroupValues::intern + GroupsAccumulator::update_batch x4)
+//   k_aggregate_generic / k_deferred   same arithmetic with direct global loads (bitmaps, unaligned or very long keys,
+//                    rows replayed after a table grew)
+//   k_emit           pane combine + avg + FilterExec predicate (totalOrder) + stream compaction into Arrow columns
+//                    (trigger_windows / evaluate, :220-253, :609-629; continuous/mod.rs:64-89; FilterExec)
+//
+// No tensor-core work exists on this path (no dense contraction); the kernels are HBM/L2-transaction bound.
+#include "dnz_device.cuh"
+
+namespace dnz {
+
+// =================================================================================================
+// k_tile_scan
+// =================================================================================================
+__global__ void k_init_minmax(BatchMinMax* mm, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].pad = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__ batches, int64_t n_batches, int64_t n_tiles,
+                                                    int64_t pane_ms, TileDesc* __restrict__ tiles, BatchMinMax* mm, int allow_fast) {
+  int64_t t = blockIdx.x;
+  if (t >= n_tiles) return;
+  // batch that owns tile t: last b with tile0 <= t
+  int64_t lo = 0, hi = n_batches - 1;
+  while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (batches[mid].tile0 <= t) lo = mid; else hi = mid - 1; }
+  const BatchDesc bd = batches[lo];
+  int64_t row0 = (t - bd.tile0) * TILE;
+  int n = (int)min((int64_t)TILE, bd.n_rows - row0);
+  long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    bool ok = bd.ts_valid == nullptr || bit_at(bd.ts_valid, bd.ts_vbit + row0 + r);
+    if (ok) { long long v = bd.ts[row0 + r]; mn = min(mn, v); mx = max(mx, v); cnt++; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  __shared__ long long smn[8], smx[8]; __shared__ int scnt[8];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { smn[w] = mn; smx[w] = mx; scnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) { mn = min(mn, smn[i]); mx = max(mx, smx[i]); cnt += scnt[i]; }
+    TileDesc td;
+    td.batch = (int32_t)lo; td.row0 = (int32_t)row0; td.n_rows = n; td.flags = 0;
+    int32_t o0 = bd.off[row0], o1 = bd.off[row0 + n];
+    td.byte0 = o0; td.byte_len = o1 - o0; td.pad = 0;
+    td.ts_min = mn; td.ts_max = mx; td.pane_lo = 0;
+    if (cnt == 0) td.flags |= TILE_EMPTY;
+    else {
+      td.pane_lo = mn / pane_ms;                       // timestamps >= 0 are enforced on the host before aggregation
+      if (mx / pane_ms == td.pane_lo) td.flags |= TILE_PANE_UNIFORM;
+      atomicMin((long long*)&mm[lo].ts_min, mn); atomicMax((long long*)&mm[lo].ts_max, mx);
+      atomicAdd((unsigned long long*)&mm[lo].n_valid, (unsigned long long)cnt);
+    }
+    bool aligned = ((reinterpret_cast<uintptr_t>(bd.ts + row0) | reinterpret_cast<uintptr_t>(bd.val + row0) |
+                     reinterpret_cast<uintptr_t>(bd.off + row0) | reinterpret_cast<uintptr_t>(bd.bytes)) & 15u) == 0;
+    if (allow_fast && (bd.flags & BATCH_BULK_OK) && aligned && !bd.ts_valid && !bd.val_valid && !bd.key_valid &&
+        td.byte_len <= BCAP && cnt > 0)
+      td.flags |= TILE_FAST;
+    tiles[t] = td;
+  }
+}
+
+cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_t n_tiles, int64_t pane_ms, TileDesc* tiles,
+                             BatchMinMax* minmax, bool allow_fast, cudaStream_t s) {
+  if (n_batches <= 0 || n_tiles <= 0) return cudaSuccess;
+  k_init_minmax<<<(unsigned)((n_batches + 255) / 256), 256, 0, s>>>(minmax, n_batches);
+  k_tile_scan<<<(unsigned)n_tiles, 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// row application shared by every aggregate path
+// =================================================================================================
+// Returns false when the row had to be deferred (nothing was modified).
+__device__ __forceinline__ bool apply_row(const AggParams& P, uint32_t tile, uint32_t row, int64_t pane, bool val_ok, double v,
+                                          uint32_t gid, unsigned long long rowseq) {
+  int64_t pi = pane - P.panes.pane0;
+  if (pi < 0 || pi >= P.panes.n_panes) return true;           // cannot happen: the host sizes the table from the tile scan
+  GroupState* m = P.panes.main[pi];
+  GroupState* l = P.panes.late[pi];
+  if (!val_ok) {
+    unsigned long long* nm = m ? P.panes.nullrows_main[pi] : nullptr;
+    unsigned long long* nl = l ? P.panes.nullrows_late[pi] : nullptr;
+    if ((m && !nm) || (l && !nl)) { defer_row(P.defer, tile, row, DEFER_NEED_NULLROWS); return false; }
+    if (nm) red_add_u64(nm + gid, 1ull);
+    if (nl) red_add_u64(nl + gid, 1ull);
+    return true;
+  }
+  unsigned long long* fm = nullptr; unsigned long long* fl = nullptr;
+  if (v == 0.0) {
+    fm = m ? P.panes.fz_main[pi] : nullptr; fl = l ? P.panes.fz_late[pi] : nullptr;
+    if ((m && !fm) || (l && !fl)) { defer_row(P.defer, tile, row, DEFER_NEED_FZ); return false; }
+  }
+  if (m) state_update(m, fm, gid, v, rowseq);
+  if (l) state_update(l, fl, gid, v, rowseq);
+  return true;
+}
+
+// One row read straight from global memory (bitmaps honoured).
+__device__ __forceinline__ void process_row_generic(const AggParams& P, uint32_t tile, const TileDesc& td, const BatchDesc& bd,
+                                                    uint32_t r) {
+  int64_t row = (int64_t)td.row0 + r;
+  if (bd.ts_valid && !bit_at(bd.ts_valid, bd.ts_vbit + row)) return;          // null timestamp: row vanishes (§8a-1)
+  int64_t ts = bd.ts[row];
+  bool val_ok = !bd.val_valid || bit_at(bd.val_valid, bd.val_vbit + row);
+  double v = val_ok ? bd.val[row] : 0.0;
+  bool key_ok = !bd.key_valid || bit_at(bd.key_valid, bd.key_vbit + row);
+  uint32_t gid;
+  if (key_ok) {
+    int32_t o0 = bd.off[row], o1 = bd.off[row + 1];
+    KeyRef k; load_key<false>(bd.bytes + o0, (uint32_t)(o1 - o0), k);
+    gid = dict_lookup(P.dict, k, false);
+  } else gid = dict_lookup_null(P.dict);
+  if (gid == GID_DEFER_GROUPS) { defer_row(P.defer, tile, r, DEFER_GROUPS_FULL); return; }
+  if (gid == GID_DEFER_ARENA) { defer_row(P.defer, tile, r, DEFER_ARENA_FULL); return; }
+  int64_t pane = (td.flags & TILE_PANE_UNIFORM) ? td.pane_lo : ts / P.panes.pane_ms;
+  unsigned long long rowseq = ((unsigned long long)bd.seq << 32) | (unsigned long long)row;
+  apply_row(P, tile, r, pane, val_ok, v, gid, rowseq);
+}
+
+__global__ void __launch_bounds__(256) k_aggregate_generic(const __grid_constant__ AggParams P) {
+  for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x) {
+    const TileDesc td = P.tiles[t];
+    if (td.flags & TILE_EMPTY) continue;
+    const BatchDesc bd = P.batches[td.batch];
+    for (uint32_t r = threadIdx.x; r < (uint32_t)td.n_rows; r += blockDim.x) process_row_generic(P, (uint32_t)(t - P.tile_begin), td, bd, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggParams P, uint64_t n_entries, const DeferEntry* entries) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_entries; i += (uint64_t)gridDim.x * blockDim.x) {
+    DeferEntry e = entries[i];
+    const TileDesc td = P.tiles[P.tile_begin + e.tile];
+    const BatchDesc bd = P.batches[td.batch];
+    process_row_generic(P, e.tile, td, bd, e.row);
+  }
+}
+
+// =================================================================================================
+// k_aggregate: persistent, warp-specialised.  Warp 16 (one elected lane) is the TMA producer: for every tile it
+// issues four 1-D bulk copies (timestamps, values, key offsets, key bytes) into a 4-deep shared-memory ring and
+// arms the stage's `full` mbarrier with the byte count.  Warps 0-15 consume: two rows per thread, both dictionary
+// probes and both accumulator pre-reads kept in flight together, reductions fire-and-forget to L2.
+// =================================================================================================
+struct __align__(128) Stage {
+  long long ts[TILE];
+  double val[TILE];
+  int32_t off[TILE + 4];
+  uint8_t bytes[BCAP + 32];
+};
+struct AggSmem {
+  Stage st[STAGES];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+};
+
+__device__ __forceinline__ uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
+
+__global__ void __launch_bounds__(AGG_THREADS, 1) k_aggregate(const __grid_constant__ AggParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  AggSmem& S = *reinterpret_cast<AggSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x, it++) {
+        const int s = it % STAGES;
+        mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
+        const TileDesc td = P.tiles[t];
+        if (td.flags & TILE_FAST) {
+          const BatchDesc& bd = P.batches[td.batch];
+          const int64_t* gts = bd.ts + td.row0; const double* gval = bd.val + td.row0; const int32_t* goff = bd.off + td.row0;
+          uint32_t nts = round16((uint32_t)td.n_rows * 8u), noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
+          int64_t a0 = td.byte0 & ~(int64_t)15;
+          uint32_t nby = round16((uint32_t)(td.byte0 + td.byte_len - a0));
+          mbar_arrive_expect_tx(&S.full[s], nts * 2u + noff + nby);
+          bulk_g2s(S.st[s].ts, gts, nts, &S.full[s]);
+          bulk_g2s(S.st[s].val, gval, nts, &S.full[s]);
+          bulk_g2s(S.st[s].off, goff, noff, &S.full[s]);
+          if (nby) bulk_g2s(S.st[s].bytes, bd.bytes + a0, nby, &S.full[s]);
+        } else {
+          mbar_arrive(&S.full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  const DictView& D = P.dict;
+  uint32_t it = 0;
+  for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x, it++) {
+    const int s = it % STAGES;
+    const TileDesc td = P.tiles[t];
+    mbar_wait(&S.full[s], (it / STAGES) & 1u);
+    const uint32_t tile_rel = (uint32_t)(t - P.tile_begin);
+    if (!(td.flags & TILE_FAST)) {
+      if (!(td.flags & TILE_EMPTY)) {
+        const BatchDesc bd = P.batches[td.batch];
+        for (uint32_t r = tid; r < (uint32_t)td.n_rows; r += CONSUMER_WARPS * 32) process_row_generic(P, tile_rel, td, bd, r);
+      }
+    } else {
+      const Stage& st = S.st[s];
+      const long long seq = P.batches[td.batch].seq;
+      const int32_t a0 = (int32_t)(td.byte0 & ~(int64_t)15);
+      KeyRef key[2]; uint32_t idx[2], gid[2]; bool active[2], live[2]; long long ts[2]; double v[2]; uint32_t rr[2];
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        uint32_t r = (uint32_t)tid + (uint32_t)i * (CONSUMER_WARPS * 32);
+        rr[i] = r; live[i] = r < (uint32_t)td.n_rows; active[i] = live[i]; gid[i] = 0;
+        if (live[i]) {
+          ts[i] = st.ts[r]; v[i] = st.val[r];
+          int32_t o0 = st.off[r], o1 = st.off[r + 1];
+          load_key<true>(st.bytes + (o0 - a0), (uint32_t)(o1 - o0), key[i]);
+          idx[i] = (uint32_t)key[i].hash & D.mask;
+        } else { ts[i] = 0; v[i] = 0.0; idx[i] = 0; key[i].len = 0; key[i].k0 = key[i].k1 = key[i].k2 = key[i].hash = 0; key[i].ptr = nullptr; }
+      }
+      // interleaved dictionary probes: both 32 B slot reads are issued before either is examined
+      while (active[0] || active[1]) {
+        uint64_t a[2], b[2], c[2], w3[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) if (active[i]) ld_slot(D.slots + idx[i], a[i], b[i], c[i], w3[i]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          if (!active[i]) continue;
+          uint32_t len = (uint32_t)w3[i], state = (uint32_t)(w3[i] >> 32);
+          if (state == SLOT_EMPTY) {
+            uint32_t g = dict_try_insert(D, D.slots + idx[i], idx[i], key[i], true);
+            if (g != 0xFFFFFFFFu) { gid[i] = g; active[i] = false; }
+          } else if (state != SLOT_LOCKED) {
+            bool eq;
+            if (key[i].len <= (uint32_t)INLINE_KEY) eq = len == key[i].len && a[i] == key[i].k0 && b[i] == key[i].k1 && c[i] == key[i].k2;
+            else eq = len == key[i].len && a[i] == key[i].k0 && dict_long_equal(D, b[i], key[i], true);
+            if (eq) { gid[i] = state - 1; active[i] = false; } else idx[i] = (idx[i] + 1) & D.mask;
+          }
+        }
+      }
+      // accumulate
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        if (!live[i]) continue;
+        if (gid[i] == GID_DEFER_GROUPS) { defer_row(P.defer, tile_rel, rr[i], DEFER_GROUPS_FULL); continue; }
+        if (gid[i] == GID_DEFER_ARENA) { defer_row(P.defer, tile_rel, rr[i], DEFER_ARENA_FULL); continue; }
+        long long pane = (td.flags & TILE_PANE_UNIFORM) ? td.pane_lo : ts[i] / P.panes.pane_ms;
+        unsigned long long rowseq = ((unsigned long long)seq << 32) | (unsigned long long)(td.row0 + rr[i]);
+        apply_row(P, tile_rel, rr[i], pane, true, v[i], gid[i], rowseq);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[s]);
+  }
+}
+
+static int g_agg_smem = 0;
+cudaError_t agg_kernel_setup() {
+  g_agg_smem = (int)sizeof(AggSmem);
+  return cudaFuncSetAttribute(k_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, g_agg_smem);
+}
+
+cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s) {
+  int64_t n_tiles = p.tile_end - p.tile_begin;
+  if (n_tiles <= 0) return cudaSuccess;
+  if (!g_agg_smem) { cudaError_t e = agg_kernel_setup(); if (e != cudaSuccess) return e; }
+  int grid = (int)(n_tiles < (int64_t)sm_count ? n_tiles : (int64_t)sm_count);
+  k_aggregate<<<grid, AGG_THREADS, g_agg_smem, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_aggregate_generic(const AggParams& p, int sm_count, cudaStream_t s) {
+  int64_t n_tiles = p.tile_end - p.tile_begin;
+  if (n_tiles <= 0) return cudaSuccess;
+  int grid = (int)(n_tiles < (int64_t)sm_count * 8 ? n_tiles : (int64_t)sm_count * 8);
+  k_aggregate_generic<<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n_entries, cudaStream_t s) {
+  if (!n_entries) return cudaSuccess;
+  uint64_t gb = (n_entries + 255) / 256; int grid = (int)(gb < 148 * 8 ? gb : 148 * 8);
+  k_deferred<<<grid, 256, 0, s>>>(p, n_entries, in);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// k_emit: one thread per group id.  Combines the window's panes (count +, sum + in ascending pane order, min/max
+// over the ordered keys, first-zero sign), evaluates the post-aggregate predicate with IEEE totalOrder (arrow-ord
+// cmp on Float64) and compacts the survivors: warp ballot + block scan -> one 64-bit atomic per block reserves
+// (rows, key bytes) contiguously so that the Utf8 offsets stay monotone.
+// =================================================================================================
+__device__ __forceinline__ bool predicate(int op, long long a, long long b) {
+  switch (op) { case 0: return a > b; case 1: return a >= b; case 2: return a < b; case 3: return a <= b; case 4: return a == b; default: return a != b; }
+}
+
+__device__ __forceinline__ uint64_t key_hash_of_gid(const DictView& d, uint32_t gid, uint32_t& len_out, uint32_t& slot_out) {
+  uint32_t si = d.slot_of_gid[gid];
+  slot_out = si;
+  if (si == 0xFFFFFFFFu) { len_out = 0; return 0; }            // NULL key hashes to 0 (owner = rank 0)
+  const DictSlot& sl = d.slots[si];
+  len_out = sl.len;
+  return sl.len <= (uint32_t)INLINE_KEY ? hash_inline(sl.k0, sl.k1, sl.k2, sl.len) : sl.k0;
+}
+
+struct Combined { unsigned long long cnt, nullrows, mnk, mxk, fz; double sum; bool present; };
+
+__device__ __forceinline__ Combined combine_panes(const EmitParams& P, uint32_t g) {
+  Combined c; c.cnt = 0; c.nullrows = 0; c.mnk = 0; c.mxk = 0; c.fz = ~0ull; c.sum = 0.0;
+  bool first = true;
+  for (int p = 0; p < P.n_panes; p++) {
+    const GroupState s = P.panes[p][g];
+    if (s.cnt) { c.sum = first ? s.sum : c.sum + s.sum; first = false; }   // no "+ 0.0" for absent panes: keeps -0.0 sums exact
+    c.cnt += s.cnt; c.mnk = max(c.mnk, s.minkey); c.mxk = max(c.mxk, s.maxkey);
+    if (P.nullrows[p]) c.nullrows += P.nullrows[p][g];
+    if (P.fz[p]) c.fz = min(c.fz, P.fz[p][g]);
+  }
+  c.present = (c.cnt | c.nullrows) != 0;
+  return c;
+}
+
+__global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams P) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool keep = false; uint32_t klen = 0, slot = 0; Combined c; c.cnt = 0; c.sum = 0; c.mnk = c.mxk = 0; c.fz = ~0ull; c.nullrows = 0; c.present = false;
+  double mn = 0, mx = 0, avg = 0;
+  bool agg_ok = false;
+  if (g < P.n_groups) {
+    c = combine_panes(P, g);
+    if (c.present) {
+      uint64_t h = key_hash_of_gid(P.dict, g, klen, slot);
+      keep = P.world <= 1 || (int)(h % (uint64_t)P.world) == P.rank;
+      agg_ok = c.cnt != 0;
+      if (agg_ok) {
+        unsigned long long bmn = unord_bits(ORD_F64_MAX - c.mnk), bmx = unord_bits(c.mxk + ORD_F64_MIN);
+        unsigned long long zsign = (c.fz != ~0ull) ? ((c.fz & 1ull) << 63) : 0ull;
+        if ((bmn << 1) == 0) bmn = zsign;             // min is a zero: sign of the first zero seen
+        if ((bmx << 1) == 0) bmx = zsign;
+        mn = __longlong_as_double((long long)bmn); mx = __longlong_as_double((long long)bmx);
+        avg = c.sum / (double)c.cnt;
+      }
+      if (keep && P.has_filter) {
+        long long lit = total_key((unsigned long long)__double_as_longlong(P.filter_lit));
+        if (P.filter_col == 0) keep = predicate(P.filter_op, total_key((unsigned long long)__double_as_longlong((double)(long long)c.cnt)), lit);
+        else if (!agg_ok) keep = false;               // null predicate drops the row
+        else {
+          double x = P.filter_col == 1 ? mn : P.filter_col == 2 ? mx : P.filter_col == 3 ? avg : c.sum;
+          keep = predicate(P.filter_op, total_key((unsigned long long)__double_as_longlong(x)), lit);
+        }
+      }
+    }
+  }
+  // block-level exclusive scan of (rows, bytes)
+  uint32_t kb = keep ? klen : 0u;
+  uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+  uint32_t row_pre = __popc(ballot & ((1u << lane) - 1u));
+  uint32_t byte_inc = kb;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, byte_inc, o); if (lane >= o) byte_inc += x; }
+  __shared__ uint32_t wrows[8], wbytes[8]; __shared__ unsigned long long base;
+  if (lane == 31) { wrows[warp] = __popc(ballot); wbytes[warp] = byte_inc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tr = 0, tb = 0;
+    for (int i = 0; i < 8; i++) { uint32_t r = wrows[i], b = wbytes[i]; wrows[i] = tr; wbytes[i] = tb; tr += r; tb += b; }
+    unsigned long long res = 0;
+    if (tr) res = atomicAdd(P.out.cursor, ((unsigned long long)tr << 32) | tb);
+    base = res;
+    if (tr && ((res >> 32) + tr > P.out.row_cap || (res & 0xFFFFFFFFull) + tb > P.out.byte_cap)) { atomicOr(P.out.overflow, 1u); base = ~0ull; }
+  }
+  __syncthreads();
+  if (!keep || base == ~0ull) return;
+  uint64_t row = (base >> 32) + wrows[warp] + row_pre;
+  uint32_t boff = (uint32_t)(base & 0xFFFFFFFFull) + wbytes[warp] + (byte_inc - kb);
+  const EmitOut& O = P.out;
+  O.key_off[row] = (int32_t)boff;
+  O.key_valid[row] = slot != 0xFFFFFFFFu;
+  if (slot != 0xFFFFFFFFu) {
+    const DictSlot& sl = P.dict.slots[slot];
+    if (klen <= (uint32_t)INLINE_KEY) {
+      uint64_t w[3] = {sl.k0, sl.k1, sl.k2};
+      for (uint32_t i = 0; i < klen; i++) O.key_bytes[boff + i] = (uint8_t)(w[i >> 3] >> ((i & 7) * 8));
+    } else {
+      const uint8_t* src = P.dict.arena + sl.k1;
+      for (uint32_t i = 0; i < klen; i++) O.key_bytes[boff + i] = src[i];
+    }
+  }
+  O.count[row] = (long long)c.cnt;
+  O.mn[row] = mn; O.mx[row] = mx; O.avg[row] = avg; O.sum[row] = agg_ok ? c.sum : 0.0;
+  O.agg_valid[row] = agg_ok;
+  O.wstart[row] = P.wstart; O.wend[row] = P.wend;
+}
+
+cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
+  if (!p.n_groups) return cudaSuccess;
+  k_emit<<<(p.n_groups + 255) / 256, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// small utilities
+// =================================================================================================
+__global__ void k_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  uint64_t gb = (n + 255) / 256; int grid = (int)(gb < 148 * 16 ? gb : 148 * 16);
+  k_fill_u64<<<grid, 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+// re-insert every occupied slot of the old table into the (zeroed) new one; group ids are preserved
+__global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    DictSlot s = old_slots[i];
+    if (s.state == SLOT_EMPTY || s.state == SLOT_LOCKED) continue;
+    uint64_t h = s.len <= (uint32_t)INLINE_KEY ? hash_inline(s.k0, s.k1, s.k2, s.len) : s.k0;
+    uint32_t idx = (uint32_t)h & nd.mask;
+    for (;;) {
+      uint32_t old = atomicCAS(&nd.slots[idx].state, SLOT_EMPTY, SLOT_LOCKED);
+      if (old == SLOT_EMPTY) break;
+      idx = (idx + 1) & nd.mask;
+    }
+    DictSlot* d = nd.slots + idx;
+    d->k0 = s.k0; d->k1 = s.k1; d->k2 = s.k2; d->len = s.len;
+    nd.slot_of_gid[s.state - 1] = idx;
+    __threadfence();
+    d->state = s.state;
+  }
+}
+cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd, cudaStream_t s) {
+  uint64_t gb = ((uint64_t)old_cap + 255) / 256; int grid = (int)(gb < 148 * 16 ? gb : 148 * 16);
+  k_dict_rehash<<<grid, 256, 0, s>>>(old_slots, old_cap, nd);
+  return cudaGetLastError();
+}
+
+}  // namespace dnz

@@ -1,0 +1,148 @@
+// dnz_kernels.h -- device data layout + kernel launch wrappers (internal; the public boundary is include/dnz_gpu.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dnz {
+
+// ------------------------------------------------------------------------------------------------
+// Tiling of the input.  One tile = up to TILE consecutive rows of ONE RecordBatch.
+constexpr int TILE = 1024;            // rows per tile
+constexpr int STAGES = 4;             // TMA ring depth per CTA
+constexpr int BCAP = 16384;           // staged key bytes per tile (16 B/row average); longer tiles take the generic path
+constexpr int CONSUMER_WARPS = 16;    // 512 consumer threads x 2 rows = TILE
+constexpr int AGG_THREADS = (CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
+constexpr int INLINE_KEY = 24;        // key bytes stored inline in a dictionary slot
+
+enum : int32_t {
+  TILE_FAST = 1,          // all four column slices can be staged with cp.async.bulk (16 B aligned, fits BCAP, no bitmaps)
+  TILE_PANE_UNIFORM = 2,  // every valid timestamp of the tile falls in pane_lo
+  TILE_EMPTY = 4,         // no valid timestamp
+};
+
+struct BatchDesc {
+  const int64_t* ts; const double* val; const int32_t* off; const uint8_t* bytes;
+  const uint8_t* ts_valid; const uint8_t* val_valid; const uint8_t* key_valid;
+  int32_t ts_vbit, val_vbit, key_vbit;   // bit offset of row 0 inside the bitmaps (sliced arrays)
+  int32_t flags;                          // bit0: buffers are padded/aligned for bulk copies
+  int64_t n_rows;
+  int64_t seq;                            // arrival sequence number of the batch
+  int64_t tile0;                          // first tile of the batch inside the launch set
+};
+enum : int32_t { BATCH_BULK_OK = 1 };
+
+struct TileDesc {
+  int32_t batch, row0, n_rows, flags;
+  int64_t byte0;        // off[row0]
+  int32_t byte_len;     // off[row0+n_rows] - off[row0]
+  int32_t pad;
+  int64_t ts_min, ts_max;
+  int64_t pane_lo;      // floor(ts_min / pane_ms)
+};
+
+struct BatchMinMax { int64_t ts_min, ts_max, n_valid; int64_t pad; };
+
+// ------------------------------------------------------------------------------------------------
+// Key dictionary: open addressing, one 32 B sector per slot, keys <= 24 B inline.
+struct __align__(32) DictSlot {
+  uint64_t k0, k1, k2;   // inline: zero padded key bytes; long keys: k0 = hash64, k1 = arena offset
+  uint32_t len;          // key length in bytes
+  uint32_t state;        // 0 empty, 0xFFFFFFFF locked (insert in flight), else gid + 1
+};
+constexpr uint32_t SLOT_EMPTY = 0u, SLOT_LOCKED = 0xFFFFFFFFu;
+
+struct DictView {
+  DictSlot* slots; uint32_t mask;     // capacity - 1 (power of two, >= 2 * gcap)
+  uint32_t gcap;                      // group ids must stay < gcap (capacity of the per-pane state arrays)
+  uint32_t* n_groups;                 // device counter
+  uint32_t* null_gid;                 // 0 = unassigned, 0xFFFFFFFF locked, else gid + 1 (group of the NULL key)
+  uint32_t* slot_of_gid;              // gid -> slot (0xFFFFFFFF for the NULL-key group)
+  uint8_t* arena; unsigned long long* arena_used; uint64_t arena_cap;   // bytes of keys longer than INLINE_KEY
+  unsigned long long* key_bytes_total;                                  // sum of key lengths over all groups
+};
+
+// Per (pane, group) partial aggregate: exactly one 32 B sector.
+struct __align__(32) GroupState {
+  unsigned long long cnt;      // non-null values
+  double sum;
+  unsigned long long minkey;   // ORD(f64::MAX) - ord(v): 0 == f64::MAX (accumulator start), larger == smaller value
+  unsigned long long maxkey;   // ord(v) - ORD(f64::MIN): 0 == f64::MIN
+};
+
+struct PaneTable {             // uploaded per launch
+  int64_t pane0;               // pane id of entry 0
+  int32_t n_panes; int32_t pad;
+  int64_t pane_ms;
+  GroupState* const* main;     // [n_panes] nullable: pane no longer needed by any open window
+  GroupState* const* late;     // [n_panes] nullable: rows re-opening already emitted windows (exact late path)
+  unsigned long long* const* nullrows_main; unsigned long long* const* nullrows_late;   // rows with NULL value, nullable
+  unsigned long long* const* fz_main; unsigned long long* const* fz_late;               // first +-0.0 row (seq<<1|sign), nullable
+};
+
+struct DeferEntry { uint32_t tile, row; };
+struct DeferList { DeferEntry* entries; unsigned long long* count; uint64_t cap; uint32_t* flags; };
+enum : uint32_t { DEFER_GROUPS_FULL = 1, DEFER_ARENA_FULL = 2, DEFER_NEED_FZ = 4, DEFER_LIST_OVERFLOW = 8, DEFER_NEED_NULLROWS = 16 };
+
+struct AggParams {
+  const BatchDesc* batches; const TileDesc* tiles; int64_t tile_begin, tile_end;
+  DictView dict; PaneTable panes; DeferList defer;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Emission: combine the panes of one window, evaluate the predicate, compact into Arrow-shaped columns.
+constexpr int MAX_WINDOW_PANES = 64;
+struct EmitOut {
+  int32_t* key_off; uint8_t* key_bytes; uint8_t* key_valid;
+  int64_t* count; double* mn; double* mx; double* avg; double* sum; uint8_t* agg_valid;
+  int64_t* wstart; int64_t* wend;
+  unsigned long long* cursor;    // (rows << 32) | key bytes reserved so far
+  uint64_t row_cap, byte_cap;
+  uint32_t* overflow;
+};
+struct EmitParams {
+  const GroupState* panes[MAX_WINDOW_PANES];
+  const unsigned long long* nullrows[MAX_WINDOW_PANES];
+  const unsigned long long* fz[MAX_WINDOW_PANES];
+  int32_t n_panes; int32_t has_filter; int32_t filter_col /*0 count 1 min 2 max 3 avg 4 sum*/; int32_t filter_op;
+  double filter_lit;
+  int64_t wstart, wend;
+  uint32_t n_groups;
+  int32_t rank, world;           // multi-GPU: emit only keys with hash64 % world == rank (world <= 1: all)
+  DictView dict;
+  EmitOut out;
+};
+
+// Multi-GPU partial-state packets (DNZ_PARTIAL_BYTES = 64)
+struct __align__(16) PartialEntry {
+  int64_t wstart;
+  unsigned long long cnt; double sum; unsigned long long minkey, maxkey;
+  unsigned long long nullrows, fz;
+  uint32_t key_off, key_len;     // into the accompanying key byte arena; key_len == 0xFFFFFFFF: NULL key
+};
+static_assert(sizeof(PartialEntry) == 64, "packet size");
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers (dnz_kernels.cu)
+cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_t n_tiles, int64_t pane_ms,
+                             TileDesc* tiles, BatchMinMax* minmax, bool allow_fast, cudaStream_t s);
+cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_aggregate_generic(const AggParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n_entries, cudaStream_t s);
+cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
+cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);
+cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd, cudaStream_t s);
+cudaError_t agg_kernel_setup();
+
+// exchange (multi-GPU)
+cudaError_t launch_pack_partials(const EmitParams& p, PartialEntry* entries, uint8_t* key_bytes,
+                                 unsigned long long* owner_cursor /*[world] (rows<<32|bytes)*/,
+                                 const unsigned long long* owner_base /*[world]*/, int pass, cudaStream_t s);
+cudaError_t launch_merge_partials(const PartialEntry* entries, int64_t n, const uint8_t* key_bytes, DictView dict,
+                                  PaneTable panes, int64_t window_ms, DeferList defer, cudaStream_t s);
+
+// synthetic generator (dnz_synth.cu)
+cudaError_t launch_synth(int64_t row0, int64_t n_rows, int64_t batch_rows, uint64_t seed, int64_t groups,
+                         int64_t rows_per_ms, int64_t t0_ms, int uuid_keys, int64_t key_mul, int64_t key_add, int64_t* ts, double* val, int32_t* off,
+                         uint8_t* bytes, int64_t bytes_stride, cudaStream_t s);
+
+}  // namespace dnz

@@ -1,0 +1,1039 @@
+// dnz_window.cu -- host side of the B200 streaming-window operator behind the C ABI of include/dnz_gpu.h.
+//
+// Mirrors GroupedWindowAggStream (crates/core/src/physical_plan/continuous/grouped_window_agg_stream.rs):
+//   push/poll           <-> poll_next_inner (:326-349): watermark -> windows -> frames.push -> process_watermark -> trigger
+//   PaneStore           <-> window_frames: BTreeMap<SystemTime, GroupedAggWindowFrame> (:63-82), re-organised as hop-sized
+//                           panes shared by the L/S windows that overlap them
+//   Dictionary          <-> GroupValues (one per frame in the reference; one per stream here, ids are stable)
+//   plan_runs           <-> the per-batch watermark rule (:255-266) + late rows re-opening emitted windows (§8a-3)
+// and the Arrow<->device buffer manager (host Arrow C-Data in, device columns, Arrow C-Data out).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/dnz_gpu.h"
+#include "dnz_kernels.h"
+
+using namespace dnz;
+
+namespace {
+
+struct DnzError {
+  int32_t code; std::string msg;
+};
+[[noreturn]] void fail(int32_t code, const char* fmt, ...) {
+  char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  throw DnzError{code, buf};
+}
+#define CK(expr)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) fail(DNZ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+thread_local std::string g_last_error;
+
+inline int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// device memory helpers
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void alloc(size_t n) { release(); if (n == 0) n = 256; CK(cudaMalloc(&p, n)); bytes = n; }
+  // grow without preserving contents
+  void reserve(size_t n) { if (n > bytes) alloc(std::max(n, bytes + bytes / 2)); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr; size_t bytes = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void reserve(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    size_t want = std::max(n, bytes * 2);
+    CK(cudaMallocHost(&p, want)); bytes = want;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// bump allocator for the device copies of pushed host batches
+struct Arena {
+  std::vector<DevBuf> slabs; size_t cur = 0, off = 0;
+  static constexpr size_t SLAB = 256ull << 20;
+  void* alloc(size_t n) {
+    n = round_up(n + 32, 256);
+    while (true) {
+      if (cur < slabs.size() && off + n <= slabs[cur].bytes) { void* r = (char*)slabs[cur].p + off; off += n; return r; }
+      if (cur + 1 < slabs.size() && n <= slabs[cur + 1].bytes) { cur++; off = 0; continue; }
+      DevBuf b; b.alloc(std::max(n, SLAB));
+      slabs.insert(slabs.begin() + (slabs.empty() ? 0 : cur + 1), std::move(b));
+      if (slabs.size() > 1) cur++;
+      off = 0;
+    }
+  }
+  void reset() { cur = 0; off = 0; }
+};
+
+struct Pane {
+  int64_t id = 0;
+  DevBuf st, nullrows, fz;
+};
+
+struct PendingBatch {
+  BatchDesc d{};
+  int64_t key_bytes = 0;
+  bool has_moved = false;
+  ArrowArray moved{};
+};
+
+struct ResultSet {             // device columns of the rows emitted since the last poll
+  DevBuf key_off, key_bytes, key_valid, count, mn, mx, avg, sum, agg_valid, wstart, wend;
+  uint64_t row_cap = 0, byte_cap = 0;
+  uint64_t rows = 0, bytes = 0;   // host view of the cursor (exact after sync_cursor)
+};
+
+enum { COL_COUNT = 0, COL_MIN = 1, COL_MAX = 2, COL_AVG = 3, COL_SUM = 4 };
+
+}  // namespace
+
+struct dnz_window {
+  dnz_window_config cfg{};
+  std::vector<dnz_agg> aggs; std::vector<std::string> aliases;
+  std::string key_name;
+  int key_col = -1, val_col = -1, meta_col = -1, ts_child = -1, n_input_cols = 0;
+  int dev = 0; int sm_count = 148;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t L = 0, S = 0, pane_ms = 0; int panes_per_window = 1;
+  int64_t max_rows = 16ll << 20;
+
+  // dictionary
+  DevBuf slots, slot_of_gid, arena, counters;   // counters: [0] n_groups(u32) [1] null_gid(u32) [2..3] arena_used(u64) [4..5] key_bytes_total(u64)
+  uint32_t dict_cap = 0, gcap = 0; uint64_t arena_cap = 0;
+  uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0;
+
+  // panes
+  std::map<int64_t, std::unique_ptr<Pane>> panes;
+  std::vector<std::unique_ptr<Pane>> pane_pool;
+  bool need_nullrows = false, need_fz = false;
+  bool has_wm = false; int64_t wm = 0;
+  int64_t emitted_upto = INT64_MIN;
+
+  // pending input
+  std::vector<PendingBatch> pending; int64_t pending_rows = 0; int64_t next_seq = 0;
+  Arena in_arena; bool copies_in_flight = false;
+
+  // scratch
+  DevBuf d_batches, d_tiles, d_minmax, d_ptrs, d_defer[2], d_defer_ctl, d_cursor;
+  PinnedBuf h_stage, h_minmax, h_tiles, h_small;
+  ResultSet res; bool res_consumed = false;
+
+  // multi-GPU
+  int rank = 0, world = 1;
+
+  dnz_stats stats{};
+  std::string err; int32_t sticky = 0;
+
+  ~dnz_window();
+  void init(const dnz_window_config* c, const ArrowSchema* schema);
+  DictView dict_view() const;
+  void dict_alloc(uint32_t new_gcap);
+  void dict_grow();
+  void arena_grow();
+  void sync_counters();
+  Pane* get_pane(int64_t id, bool create);
+  std::unique_ptr<Pane> new_pane(int64_t id);
+  void ensure_side_arrays(Pane* p);
+  void retire_panes();
+  void push_host(ArrowArray* batch);
+  void push_dev(const dnz_device_batch* b, int64_t n);
+  void process_pending();
+  void process_chunk(size_t b0, size_t b1);
+  void execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0, size_t rb1,
+                   bool dirty, int64_t horizon, int64_t wm_after);
+  void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
+  void emit_normal(int64_t wm_new);
+  void ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes);
+  void sync_cursor();
+  void reset_results();
+  void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output);
+  void fill_schema(ArrowSchema* schema);
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Arrow C-Data export plumbing
+struct ExportPrivate {
+  std::vector<void*> pinned;               // cudaMallocHost allocations
+  std::vector<std::unique_ptr<ArrowArray>> children; std::vector<ArrowArray*> child_ptrs;
+  std::vector<std::vector<const void*>> buffers;
+};
+void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  if (a->private_data) {
+    auto* p = static_cast<ExportPrivate*>(a->private_data);
+    for (void* q : p->pinned) cudaFreeHost(q);
+    delete p;
+  }
+  a->release = nullptr;
+}
+void release_child(ArrowArray* a) { a->release = nullptr; }
+
+struct SchemaPrivate {
+  std::vector<std::unique_ptr<ArrowSchema>> children; std::vector<ArrowSchema*> child_ptrs; std::vector<std::string> names;
+};
+void release_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  if (s->private_data) delete static_cast<SchemaPrivate*>(s->private_data);
+  s->release = nullptr;
+}
+void release_child_schema(ArrowSchema* s) { s->release = nullptr; }
+
+const char* agg_format(int kind) { return kind == DNZ_AGG_COUNT ? "l" : "g"; }
+
+}  // namespace
+
+// =================================================================================================
+dnz_window::~dnz_window() {
+  cudaSetDevice(dev);
+  for (auto& pb : pending) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+  if (stream) cudaStreamSynchronize(stream);
+  if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+  if (copy_done) cudaEventDestroy(copy_done);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
+  if (!c || !schema) fail(DNZ_ERR_INVALID, "null config or schema");
+  if (c->abi_version != DNZ_ABI_VERSION) fail(DNZ_ERR_INVALID, "abi_version %u != %u", c->abi_version, DNZ_ABI_VERSION);
+  cfg = *c;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(DNZ_ERR_CUDA, "no CUDA device: the GPU operator has no CPU fallback");
+  if (c->device < 0 || c->device >= ndev) fail(DNZ_ERR_INVALID, "device %d out of range (%d devices)", c->device, ndev);
+  dev = c->device;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) fail(DNZ_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+  sm_count = prop.multiProcessorCount;
+
+  // ---- plan shape (planner/streaming_window.rs:36-66: plain column group keys; count/min/max/avg aggregates)
+  if (c->n_aggs <= 0 || !c->aggs) fail(DNZ_ERR_INVALID, "no aggregate expressions");
+  if (!schema->format || strcmp(schema->format, "+s") != 0) fail(DNZ_ERR_INVALID, "input schema must be a struct (RecordBatch)");
+  n_input_cols = (int)schema->n_children;
+  if (c->key_column < 0 || c->key_column >= n_input_cols) fail(DNZ_ERR_INVALID, "key_column out of range");
+  key_col = c->key_column;
+  const ArrowSchema* ks = schema->children[key_col];
+  if (strcmp(ks->format, "u") != 0) fail(DNZ_ERR_UNSUPPORTED, "group key column '%s' has format '%s'; only Utf8 keys are implemented", ks->name, ks->format);
+  key_name = ks->name ? ks->name : "key";
+  val_col = -1;
+  for (int i = 0; i < c->n_aggs; i++) {
+    const dnz_agg& a = c->aggs[i];
+    if (a.kind < DNZ_AGG_COUNT || a.kind > DNZ_AGG_SUM) fail(DNZ_ERR_UNSUPPORTED, "aggregate kind %d not implemented", a.kind);
+    if (a.arg_column < 0 || a.arg_column >= n_input_cols) fail(DNZ_ERR_INVALID, "aggregate %d: arg_column out of range", i);
+    if (strcmp(schema->children[a.arg_column]->format, "g") != 0) fail(DNZ_ERR_UNSUPPORTED, "aggregate %d: argument must be Float64", i);
+    if (val_col >= 0 && val_col != a.arg_column) fail(DNZ_ERR_UNSUPPORTED, "all aggregates must share one argument column (got %d and %d)", val_col, a.arg_column);
+    val_col = a.arg_column;
+    aggs.push_back(a);
+    aliases.push_back(a.alias ? a.alias : (a.kind == DNZ_AGG_COUNT ? "count" : a.kind == DNZ_AGG_MIN ? "min" : a.kind == DNZ_AGG_MAX ? "max" : a.kind == DNZ_AGG_AVG ? "average" : "sum"));
+  }
+  for (size_t i = 0; i < aggs.size(); i++) aggs[i].alias = aliases[i].c_str();
+  meta_col = -1;
+  for (int i = 0; i < n_input_cols; i++)
+    if (schema->children[i]->name && strcmp(schema->children[i]->name, "_streaming_internal_metadata") == 0) meta_col = i;
+  if (meta_col < 0) fail(DNZ_ERR_INVALID, "input schema lacks the `_streaming_internal_metadata` struct column");
+  const ArrowSchema* ms = schema->children[meta_col];
+  if (strcmp(ms->format, "+s") != 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` must be a struct");
+  ts_child = -1;
+  for (int i = 0; i < ms->n_children; i++)
+    if (ms->children[i]->name && strcmp(ms->children[i]->name, "canonical_timestamp") == 0) ts_child = i;
+  if (ts_child < 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` lacks `canonical_timestamp`");
+  if (strncmp(ms->children[ts_child]->format, "tsm:", 4) != 0) fail(DNZ_ERR_INVALID, "`canonical_timestamp` must be Timestamp(Millisecond)");
+  if (c->has_filter && (c->filter_agg < 0 || c->filter_agg >= c->n_aggs || c->filter_op < DNZ_OP_GT || c->filter_op > DNZ_OP_NEQ))
+    fail(DNZ_ERR_INVALID, "bad filter");
+
+  // ---- window geometry (streaming_window.rs:1053-1094)
+  L = c->window_ms; S = c->slide_ms;
+  if (L <= 0 || S < 0) fail(DNZ_ERR_INVALID, "window length must be positive");
+  if (L < 1000) fail(DNZ_ERR_DATA, "window length < 1 s: the reference divides by zero in snap_to_window_start");
+  if (L % 1000 != 0) fail(DNZ_ERR_UNSUPPORTED, "window length must be whole seconds (the reference aligns windows in whole seconds)");
+  if (S > 0 && L % S != 0) fail(DNZ_ERR_UNSUPPORTED, "sliding windows need window_ms %% slide_ms == 0 (pane sharing)");
+  pane_ms = S > 0 ? S : L;
+  panes_per_window = (int)(L / pane_ms);
+  if (panes_per_window > MAX_WINDOW_PANES) fail(DNZ_ERR_UNSUPPORTED, "window/slide ratio %d exceeds %d", panes_per_window, MAX_WINDOW_PANES);
+  if (c->max_rows_per_launch > 0) max_rows = c->max_rows_per_launch;
+
+  if (c->cuda_stream) { stream = (cudaStream_t)c->cuda_stream; own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+  CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(agg_kernel_setup());
+
+  counters.alloc(64); CK(cudaMemsetAsync(counters.p, 0, 64, stream));
+  d_defer_ctl.alloc(64); d_cursor.alloc(64);
+  CK(cudaMemsetAsync(d_cursor.p, 0, 64, stream));
+  uint64_t eg = c->expected_groups > 0 ? (uint64_t)c->expected_groups : (1ull << 16);
+  uint64_t g0 = 1024; while (g0 < eg + eg / 8) g0 <<= 1;
+  if (g0 > (1ull << 30)) fail(DNZ_ERR_INVALID, "expected_groups too large");
+  dict_alloc((uint32_t)g0);
+  arena_cap = 1 << 20; arena.alloc(arena_cap);
+  CK(cudaStreamSynchronize(stream));
+}
+
+DictView dnz_window::dict_view() const {
+  DictView d;
+  d.slots = slots.as<DictSlot>(); d.mask = dict_cap - 1; d.gcap = gcap;
+  uint32_t* c32 = counters.as<uint32_t>();
+  d.n_groups = c32; d.null_gid = c32 + 1;
+  d.arena_used = reinterpret_cast<unsigned long long*>(c32 + 2);
+  d.key_bytes_total = reinterpret_cast<unsigned long long*>(c32 + 4);
+  d.slot_of_gid = slot_of_gid.as<uint32_t>();
+  d.arena = arena.as<uint8_t>(); d.arena_cap = arena_cap;
+  return d;
+}
+
+// (re)allocate dictionary + per-pane state arrays for `new_gcap` groups, preserving contents
+void dnz_window::dict_alloc(uint32_t new_gcap) {
+  uint32_t new_cap = new_gcap * 2;
+  DevBuf ns, ng;
+  ns.alloc((size_t)new_cap * sizeof(DictSlot)); CK(cudaMemsetAsync(ns.p, 0, ns.bytes, stream));
+  ng.alloc((size_t)new_gcap * 4); CK(cudaMemsetAsync(ng.p, 0xFF, ng.bytes, stream));
+  if (dict_cap) {
+    CK(cudaMemcpyAsync(ng.p, slot_of_gid.p, (size_t)gcap * 4, cudaMemcpyDeviceToDevice, stream));
+    DictView nd = dict_view(); nd.slots = ns.as<DictSlot>(); nd.mask = new_cap - 1; nd.gcap = new_gcap; nd.slot_of_gid = ng.as<uint32_t>();
+    CK(launch_dict_rehash(slots.as<DictSlot>(), dict_cap, nd, stream)); stats.total_launches++;
+    // grow every live pane
+    auto grow = [&](DevBuf& b, size_t elem, int fill) {
+      if (!b.p) return;
+      DevBuf nb; nb.alloc((size_t)new_gcap * elem);
+      CK(cudaMemcpyAsync(nb.p, b.p, (size_t)gcap * elem, cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemsetAsync((char*)nb.p + (size_t)gcap * elem, fill, (size_t)(new_gcap - gcap) * elem, stream));
+      CK(cudaStreamSynchronize(stream));
+      b = std::move(nb);
+    };
+    for (auto& kv : panes) { grow(kv.second->st, sizeof(GroupState), 0); grow(kv.second->nullrows, 8, 0); grow(kv.second->fz, 8, 0xFF); }
+    pane_pool.clear();
+    CK(cudaStreamSynchronize(stream));
+  }
+  slots = std::move(ns); slot_of_gid = std::move(ng);
+  dict_cap = new_cap; gcap = new_gcap;
+}
+void dnz_window::dict_grow() {
+  if (gcap >= (1u << 30)) fail(DNZ_ERR_NOMEM, "more than 2^30 groups");
+  dict_alloc(gcap * 2);
+}
+void dnz_window::arena_grow() {
+  DevBuf na; na.alloc(arena_cap * 2);
+  CK(cudaMemcpyAsync(na.p, arena.p, arena_cap, cudaMemcpyDeviceToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  arena = std::move(na); arena_cap *= 2;
+}
+void dnz_window::sync_counters() {
+  h_small.reserve(64);
+  CK(cudaMemcpyAsync(h_small.p, counters.p, 32, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  n_groups_host = h_small.as<uint32_t>()[0];
+  key_bytes_total_host = reinterpret_cast<uint64_t*>(h_small.as<uint32_t>() + 4)[0];
+  stats.groups = n_groups_host;
+}
+
+std::unique_ptr<Pane> dnz_window::new_pane(int64_t id) {
+  std::unique_ptr<Pane> p;
+  if (!pane_pool.empty()) { p = std::move(pane_pool.back()); pane_pool.pop_back(); }
+  else { p.reset(new Pane()); p->st.alloc((size_t)gcap * sizeof(GroupState)); }
+  p->id = id;
+  CK(cudaMemsetAsync(p->st.p, 0, (size_t)gcap * sizeof(GroupState), stream));
+  ensure_side_arrays(p.get());
+  if (p->nullrows.p) CK(cudaMemsetAsync(p->nullrows.p, 0, (size_t)gcap * 8, stream));
+  if (p->fz.p) CK(cudaMemsetAsync(p->fz.p, 0xFF, (size_t)gcap * 8, stream));
+  return p;
+}
+void dnz_window::ensure_side_arrays(Pane* p) {
+  if (need_nullrows && !p->nullrows.p) { p->nullrows.alloc((size_t)gcap * 8); CK(cudaMemsetAsync(p->nullrows.p, 0, (size_t)gcap * 8, stream)); }
+  if (need_fz && !p->fz.p) { p->fz.alloc((size_t)gcap * 8); CK(cudaMemsetAsync(p->fz.p, 0xFF, (size_t)gcap * 8, stream)); }
+}
+Pane* dnz_window::get_pane(int64_t id, bool create) {
+  auto it = panes.find(id);
+  if (it != panes.end()) return it->second.get();
+  if (!create) return nullptr;
+  auto p = new_pane(id);
+  Pane* r = p.get();
+  panes[id] = std::move(p);
+  return r;
+}
+// a pane is dropped once the last window that covers it (start == pane start) has been emitted
+void dnz_window::retire_panes() {
+  if (!has_wm) return;
+  for (auto it = panes.begin(); it != panes.end();) {
+    if (it->first * pane_ms + L <= wm) { if (pane_pool.size() < 8) pane_pool.push_back(std::move(it->second)); it = panes.erase(it); }
+    else ++it;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input
+static const void* buf_at(const ArrowArray* a, int i) { return a->n_buffers > i ? a->buffers[i] : nullptr; }
+
+void dnz_window::push_host(ArrowArray* batch) {
+  if (!batch || !batch->release) fail(DNZ_ERR_INVALID, "released or null ArrowArray");
+  if (batch->n_children != n_input_cols) fail(DNZ_ERR_INVALID, "batch has %lld columns, schema has %d", (long long)batch->n_children, n_input_cols);
+  int64_t n = batch->length;
+  if (n >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
+  if (pending_rows > 0 && pending_rows + n > max_rows) process_pending();
+  PendingBatch pb;
+  pb.d.n_rows = n; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
+  if (n > 0) {
+    const int64_t po = batch->offset;
+    const ArrowArray* key = batch->children[key_col];
+    const ArrowArray* val = batch->children[val_col];
+    const ArrowArray* meta = batch->children[meta_col];
+    const ArrowArray* ts = meta->children[ts_child];
+    if (key->length < po + n || val->length < po + n || ts->length < po + meta->offset + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
+    auto copy_in = [&](const void* src, size_t bytes) -> void* {
+      void* d = in_arena.alloc(bytes);
+      CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream));
+      stats.h2d_bytes += (int64_t)bytes;
+      return d;
+    };
+    auto copy_bitmap = [&](const ArrowArray* a, int64_t eff_off, const uint8_t*& dptr, int32_t& vbit) {
+      dptr = nullptr; vbit = 0;
+      const uint8_t* bm = (const uint8_t*)buf_at(a, 0);
+      if (!bm || a->null_count == 0) return;
+      int64_t b0 = eff_off >> 3, b1 = (eff_off + n + 7) >> 3;
+      dptr = (const uint8_t*)copy_in(bm + b0, (size_t)(b1 - b0));
+      vbit = (int32_t)(eff_off & 7);
+    };
+    // timestamps
+    int64_t to = po + meta->offset + ts->offset;
+    pb.d.ts = (const int64_t*)copy_in((const int64_t*)buf_at(ts, 1) + to, (size_t)n * 8);
+    copy_bitmap(ts, to, pb.d.ts_valid, pb.d.ts_vbit);
+    if (meta->null_count != 0 && buf_at(meta, 0)) fail(DNZ_ERR_UNSUPPORTED, "null `_streaming_internal_metadata` structs are not supported");
+    // values
+    int64_t vo = po + val->offset;
+    pb.d.val = (const double*)copy_in((const double*)buf_at(val, 1) + vo, (size_t)n * 8);
+    copy_bitmap(val, vo, pb.d.val_valid, pb.d.val_vbit);
+    // keys
+    int64_t ko = po + key->offset;
+    const int32_t* hoff = (const int32_t*)buf_at(key, 1) + ko;
+    pb.d.off = (const int32_t*)copy_in(hoff, (size_t)(n + 1) * 4);
+    int64_t o0 = hoff[0], o1 = hoff[n];
+    int64_t a0 = o0 & ~(int64_t)15;
+    pb.key_bytes = o1 - o0;
+    const uint8_t* hb = (const uint8_t*)buf_at(key, 2);
+    uint8_t* db = (uint8_t*)in_arena.alloc((size_t)(o1 - a0) + 16);
+    if (o1 > a0) { CK(cudaMemcpyAsync(db, hb + a0, (size_t)(o1 - a0), cudaMemcpyHostToDevice, copy_stream)); stats.h2d_bytes += o1 - a0; }
+    pb.d.bytes = db - a0;     // only [o0, o1) is ever dereferenced
+    copy_bitmap(key, ko, pb.d.key_valid, pb.d.key_vbit);
+    copies_in_flight = true;
+  }
+  pb.has_moved = true; pb.moved = *batch; batch->release = nullptr;   // moved
+  pending.push_back(pb);
+  pending_rows += n;
+  stats.batches_in++; stats.rows_in += n;
+}
+
+void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
+  for (int64_t i = 0; i < nb; i++) {
+    const dnz_device_batch& s = b[i];
+    if (s.n_rows >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
+    if (pending_rows > 0 && pending_rows + s.n_rows > max_rows) process_pending();
+    PendingBatch pb;
+    pb.d.ts = s.ts; pb.d.val = s.val; pb.d.off = s.key_off; pb.d.bytes = s.key_bytes;
+    pb.d.ts_valid = s.ts_valid; pb.d.val_valid = s.val_valid; pb.d.key_valid = s.key_valid;
+    pb.d.n_rows = s.n_rows; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
+    pb.key_bytes = -1;
+    pending.push_back(pb);
+    pending_rows += s.n_rows;
+    stats.batches_in++; stats.rows_in += s.n_rows;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+void dnz_window::process_pending() {
+  if (pending.empty()) return;
+  if (res_consumed) reset_results();
+  if (copies_in_flight) { CK(cudaEventRecord(copy_done, copy_stream)); CK(cudaStreamWaitEvent(stream, copy_done, 0)); }
+  struct Cleanup {
+    dnz_window* w;
+    ~Cleanup() {
+      if (w->copies_in_flight) cudaStreamSynchronize(w->copy_stream);
+      for (auto& pb : w->pending) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+      w->pending.clear(); w->pending_rows = 0; w->in_arena.reset(); w->copies_in_flight = false;
+    }
+  } cleanup{this};
+  // chunks of <= max_rows rows (a single batch larger than that forms its own chunk)
+  size_t b0 = 0;
+  while (b0 < pending.size()) {
+    size_t b1 = b0; int64_t rows = 0;
+    while (b1 < pending.size() && (b1 == b0 || rows + pending[b1].d.n_rows <= max_rows)) { rows += pending[b1].d.n_rows; b1++; }
+    process_chunk(b0, b1);
+    b0 = b1;
+  }
+}
+
+void dnz_window::process_chunk(size_t b0, size_t b1) {
+  const size_t nb = b1 - b0;
+  // ---- batch descriptors + tile scan (RecordBatchWatermark per batch)
+  std::vector<BatchDesc> bds(nb);
+  int64_t n_tiles = 0;
+  for (size_t i = 0; i < nb; i++) { bds[i] = pending[b0 + i].d; bds[i].tile0 = n_tiles; n_tiles += (bds[i].n_rows + TILE - 1) / TILE; }
+  if (n_tiles == 0) return;                 // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
+  // empty batches own no tile; give them the tile0 of their successor so that the binary search never selects them
+  d_batches.reserve(nb * sizeof(BatchDesc)); d_tiles.reserve((size_t)n_tiles * sizeof(TileDesc)); d_minmax.reserve(nb * sizeof(BatchMinMax));
+  h_stage.reserve(nb * sizeof(BatchDesc));
+  // the scan picks the LAST batch with tile0 <= t, so empty batches (same tile0 as their successor) are never chosen
+  // unless they are at the end; move trailing empties' tile0 past the end.
+  for (size_t i = nb; i-- > 0;) { if (bds[i].n_rows == 0) bds[i].tile0 = n_tiles + 1; else break; }
+  memcpy(h_stage.p, bds.data(), nb * sizeof(BatchDesc));
+  CK(cudaMemcpyAsync(d_batches.p, h_stage.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
+  bool allow_fast = !(cfg.flags & DNZ_FLAG_FORCE_GENERIC);
+  CK(launch_tile_scan(d_batches.as<BatchDesc>(), (int64_t)nb, n_tiles, pane_ms, d_tiles.as<TileDesc>(), d_minmax.as<BatchMinMax>(), allow_fast, stream));
+  stats.total_launches += 2;
+  h_minmax.reserve(nb * sizeof(BatchMinMax)); h_tiles.reserve((size_t)n_tiles * sizeof(TileDesc));
+  CK(cudaMemcpyAsync(h_minmax.p, d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(h_tiles.p, d_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  std::vector<BatchMinMax> mm(h_minmax.as<BatchMinMax>(), h_minmax.as<BatchMinMax>() + nb);
+  std::vector<TileDesc> tiles(h_tiles.as<TileDesc>(), h_tiles.as<TileDesc>() + n_tiles);
+
+  // ---- validation: inputs the reference panics on
+  for (size_t i = 0; i < nb; i++) {
+    if (bds[i].n_rows == 0) continue;
+    if (mm[i].n_valid == 0) fail(DNZ_ERR_DATA, "batch %lld: all-null canonical_timestamp (the reference unwraps None and panics)", (long long)bds[i].seq);
+    if (mm[i].ts_min < 0 || (S > 0 && mm[i].ts_min - L < 0)) fail(DNZ_ERR_DATA, "batch %lld: timestamp before epoch (+window): the reference panics in duration_since(UNIX_EPOCH)", (long long)bds[i].seq);
+  }
+
+  // ---- runs: maximal sequences of batches without late rows are aggregated by ONE launch; a batch that contains rows
+  // for an already emitted window ("dirty") is aggregated alone so that the re-opened windows hold exactly its rows.
+  bool cur_has_wm = has_wm; int64_t cur_wm = wm;
+  size_t run_start = nb; int64_t run_wm_after = 0;
+  for (size_t i = 0; i < nb; i++) {
+    if (bds[i].n_rows == 0) continue;
+    int64_t mn = mm[i].ts_min;
+    int64_t first_pane_end = (floor_div(mn, pane_ms) + 1) * pane_ms;
+    bool dirty = cur_has_wm && first_pane_end <= cur_wm;
+    int64_t new_wm = (!cur_has_wm || cur_wm <= mn) ? mn : cur_wm;     // process_watermark (:255-266)
+    if (dirty) {
+      if (run_start != nb) { execute_run(mm, tiles, b0, run_start, i, false, 0, run_wm_after); run_start = nb; }
+      execute_run(mm, tiles, b0, i, i + 1, true, cur_wm, new_wm);
+      stats.late_batches++;
+    } else {
+      if (run_start == nb) run_start = i;
+      run_wm_after = new_wm;
+    }
+    cur_has_wm = true; cur_wm = new_wm;
+  }
+  if (run_start != nb) execute_run(mm, tiles, b0, run_start, nb, false, 0, run_wm_after);
+}
+
+// Aggregates batches [rb0, rb1) of the chunk (indices relative to the chunk) and triggers.
+void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0,
+                             size_t rb1, bool dirty, int64_t horizon, int64_t wm_after) {
+  // tile range of the run
+  int64_t t0 = -1, t1 = -1; int64_t rows = 0; double alg_bytes = 0;
+  {
+    int64_t acc = 0;
+    for (size_t i = 0; i < rb1; i++) {
+      int64_t nt = (pending[chunk_b0 + i].d.n_rows + TILE - 1) / TILE;
+      if (i == rb0) t0 = acc;
+      acc += nt;
+    }
+    t1 = acc;
+  }
+  if (t1 <= t0) { return; }
+  // ---- panes touched by the run
+  int64_t pmin = INT64_MAX, pmax = INT64_MIN; int64_t fast = 0, generic = 0;
+  for (int64_t t = t0; t < t1; t++) {
+    const TileDesc& td = tiles[t];
+    rows += td.n_rows; alg_bytes += 20.0 * td.n_rows + td.byte_len;
+    if (td.flags & TILE_EMPTY) continue;
+    if (td.flags & TILE_FAST) fast++; else generic++;
+    pmin = std::min(pmin, td.pane_lo); pmax = std::max(pmax, floor_div(td.ts_max, pane_ms));
+  }
+  stats.fast_tiles += fast; stats.generic_tiles += generic;
+  std::map<int64_t, std::unique_ptr<Pane>> late_panes;
+  if (pmin <= pmax) {
+    int64_t np = pmax - pmin + 1;
+    if (np > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one launch spans %lld panes (timestamps too sparse); limit 65536", (long long)np);
+    bool val_nulls = false;
+    for (size_t i = rb0; i < rb1; i++) if (pending[chunk_b0 + i].d.val_valid) val_nulls = true;
+    if (val_nulls && !need_nullrows) { need_nullrows = true; for (auto& kv : panes) ensure_side_arrays(kv.second.get()); }
+    std::vector<uint8_t> touched((size_t)np, 0);
+    for (int64_t t = t0; t < t1; t++) {
+      const TileDesc& td = tiles[t];
+      if (td.flags & TILE_EMPTY) continue;
+      for (int64_t p = td.pane_lo; p <= floor_div(td.ts_max, pane_ms); p++) touched[(size_t)(p - pmin)] = 1;
+    }
+    for (int64_t p = pmin; p <= pmax; p++) {
+      if (!touched[(size_t)(p - pmin)]) continue;
+      bool need_main = !dirty || p * pane_ms + L > horizon;             // some covering window is still open
+      bool need_late = dirty && (p + 1) * pane_ms <= horizon;           // some covering window was already emitted
+      if (need_main) get_pane(p, true);
+      if (need_late) late_panes[p] = new_pane(p);
+    }
+    // ---- aggregate, replaying deferred rows until every table is large enough
+    const size_t defer_cap = (size_t)std::max<int64_t>(rows, 1);
+    d_defer[0].reserve(defer_cap * sizeof(DeferEntry));
+    int in_list = 0; uint64_t n_in = 0;
+    for (int iter = 0;; iter++) {
+      if (iter > 64) fail(DNZ_ERR_NOMEM, "deferred rows did not converge");
+      // pane pointer table
+      size_t pb = (size_t)np * sizeof(void*);
+      h_stage.reserve(6 * pb); d_ptrs.reserve(6 * pb);
+      void** hp = h_stage.as<void*>();
+      for (int64_t p = pmin; p <= pmax; p++) {
+        size_t k = (size_t)(p - pmin);
+        Pane* m = (!dirty || p * pane_ms + L > horizon) ? get_pane(p, false) : nullptr;
+        auto lit = late_panes.find(p); Pane* l = lit == late_panes.end() ? nullptr : lit->second.get();
+        if (m) ensure_side_arrays(m);
+        if (l) ensure_side_arrays(l);
+        hp[0 * np + k] = m ? m->st.p : nullptr; hp[1 * np + k] = l ? l->st.p : nullptr;
+        hp[2 * np + k] = m ? m->nullrows.p : nullptr; hp[3 * np + k] = l ? l->nullrows.p : nullptr;
+        hp[4 * np + k] = m ? m->fz.p : nullptr; hp[5 * np + k] = l ? l->fz.p : nullptr;
+      }
+      CK(cudaMemcpyAsync(d_ptrs.p, hp, 6 * pb, cudaMemcpyHostToDevice, stream));
+      CK(cudaMemsetAsync(d_defer_ctl.p, 0, 16, stream));
+      AggParams P;
+      P.batches = d_batches.as<BatchDesc>(); P.tiles = d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
+      P.dict = dict_view();
+      char* dp = d_ptrs.as<char>();
+      P.panes.pane0 = pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
+      P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
+      P.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); P.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
+      P.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); P.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+      const int out_list = iter == 0 ? 0 : (in_list ^ 1);
+      d_defer[out_list].reserve(defer_cap * sizeof(DeferEntry));
+      P.defer.entries = d_defer[out_list].as<DeferEntry>();
+      P.defer.count = d_defer_ctl.as<unsigned long long>(); P.defer.cap = defer_cap;
+      P.defer.flags = d_defer_ctl.as<uint32_t>() + 2;
+      const bool timing = iter == 0 && (cfg.flags & DNZ_FLAG_KERNEL_TIMING);
+      if (iter == 0) {
+        if (timing) CK(cudaEventRecord(ev0, stream));
+        if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
+        else CK(launch_aggregate(P, sm_count, stream));
+        if (timing) CK(cudaEventRecord(ev1, stream));
+        stats.agg_launches++; stats.total_launches++;
+      } else {
+        CK(launch_deferred(P, d_defer[in_list].as<DeferEntry>(), n_in, stream));   // replays the rows of the previous pass
+        stats.total_launches++;
+      }
+      h_small.reserve(64);
+      CK(cudaMemcpyAsync(h_small.p, d_defer_ctl.p, 16, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      if (timing) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += alg_bytes;
+      }
+      uint64_t cnt = h_small.as<uint64_t>()[0]; uint32_t flags = h_small.as<uint32_t>()[2];
+      if (cnt == 0) break;
+      if (flags & DEFER_LIST_OVERFLOW) fail(DNZ_ERR_NOMEM, "deferred-row list overflow");
+      stats.deferred_rows += (int64_t)cnt;
+      if (flags & DEFER_GROUPS_FULL) dict_grow();
+      if (flags & DEFER_ARENA_FULL) arena_grow();
+      if (flags & DEFER_NEED_FZ) need_fz = true;
+      if (flags & DEFER_NEED_NULLROWS) need_nullrows = true;
+      if (flags & (DEFER_NEED_FZ | DEFER_NEED_NULLROWS)) for (auto& kv : panes) ensure_side_arrays(kv.second.get());
+      in_list = out_list; n_in = cnt;
+    }
+  }
+  // ---- process_watermark + trigger_windows
+  if (dirty) {
+    // windows that were already emitted (end <= horizon) and received rows from this batch are re-opened and emitted
+    // again immediately with ONLY this batch's rows (§8a-3)
+    std::set<int64_t> starts;
+    for (auto& kv : late_panes)
+      for (int j = 0; j < panes_per_window; j++) {
+        int64_t s = (kv.first - j) * pane_ms;
+        if (s >= 0 && s + L <= horizon) starts.insert(s);
+      }
+    std::map<int64_t, Pane*> src;
+    for (auto& kv : late_panes) src[kv.first] = kv.second.get();
+    emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src);
+    CK(cudaStreamSynchronize(stream));
+    for (auto& kv : late_panes) if (pane_pool.size() < 8) pane_pool.push_back(std::move(kv.second));
+    late_panes.clear();
+  }
+  emit_normal(wm_after);
+}
+
+void dnz_window::emit_normal(int64_t wm_new) {
+  if (!has_wm || wm <= wm_new) { wm = wm_new; has_wm = true; }
+  std::set<int64_t> starts;
+  for (auto& kv : panes)
+    for (int j = 0; j < panes_per_window; j++) {
+      int64_t s = (kv.first - j) * pane_ms;
+      if (s >= 0 && s + L <= wm && s + L > emitted_upto) starts.insert(s);
+    }
+  std::map<int64_t, Pane*> src;
+  for (auto& kv : panes) src[kv.first] = kv.second.get();
+  emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src);
+  emitted_upto = std::max(emitted_upto, wm);
+  retire_panes();
+}
+
+void dnz_window::sync_cursor() {
+  h_small.reserve(64);
+  CK(cudaMemcpyAsync(h_small.p, d_cursor.p, 16, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  uint64_t c = h_small.as<uint64_t>()[0];
+  res.rows = c >> 32; res.bytes = c & 0xFFFFFFFFull;
+  if (h_small.as<uint32_t>()[2]) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+}
+
+void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
+  uint64_t need_rows = res.rows + add_rows, need_bytes = res.bytes + add_bytes;
+  if (need_bytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes between polls (Utf8 offsets are 32-bit); poll more often");
+  if (need_rows <= res.row_cap && need_bytes <= res.byte_cap) return;
+  auto grow = [&](DevBuf& b, size_t elem, uint64_t used, uint64_t cap) {
+    DevBuf nb; nb.alloc((size_t)cap * elem + 64);
+    if (used && b.p) CK(cudaMemcpyAsync(nb.p, b.p, (size_t)used * elem, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    b = std::move(nb);
+  };
+  if (need_rows > res.row_cap) {
+    uint64_t cap = std::max<uint64_t>(need_rows, res.row_cap * 2);
+    grow(res.key_off, 4, res.rows, cap + 1); grow(res.key_valid, 1, res.rows, cap); grow(res.count, 8, res.rows, cap);
+    grow(res.mn, 8, res.rows, cap); grow(res.mx, 8, res.rows, cap); grow(res.avg, 8, res.rows, cap); grow(res.sum, 8, res.rows, cap);
+    grow(res.agg_valid, 1, res.rows, cap); grow(res.wstart, 8, res.rows, cap); grow(res.wend, 8, res.rows, cap);
+    res.row_cap = cap;
+  }
+  if (need_bytes > res.byte_cap) {
+    uint64_t cap = std::max<uint64_t>(need_bytes, res.byte_cap * 2);
+    grow(res.key_bytes, 1, res.bytes, cap);
+    res.byte_cap = cap;
+  }
+}
+
+void dnz_window::reset_results() {
+  CK(cudaMemsetAsync(d_cursor.p, 0, 16, stream));
+  res.rows = 0; res.bytes = 0; res_consumed = false;
+}
+
+// One k_emit launch per window: combine its panes, apply the fused FilterExec predicate, compact.
+void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src) {
+  if (starts.empty()) return;
+  sync_counters();
+  if (n_groups_host == 0) return;
+  sync_cursor();
+  ensure_result_capacity((uint64_t)starts.size() * n_groups_host, (uint64_t)starts.size() * key_bytes_total_host);
+  for (int64_t s : starts) {
+    EmitParams E; memset(&E, 0, sizeof E);
+    int64_t p0 = s / pane_ms; int k = 0;
+    for (int j = 0; j < panes_per_window; j++) {
+      auto it = src.find(p0 + j);
+      if (it == src.end()) continue;
+      E.panes[k] = it->second->st.as<GroupState>();
+      E.nullrows[k] = it->second->nullrows.as<unsigned long long>();
+      E.fz[k] = it->second->fz.as<unsigned long long>();
+      k++;
+    }
+    if (k == 0) continue;
+    E.n_panes = k; E.has_filter = cfg.has_filter;
+    E.filter_col = cfg.has_filter ? aggs[cfg.filter_agg].kind : 0; E.filter_op = cfg.filter_op; E.filter_lit = cfg.filter_literal;
+    E.wstart = s; E.wend = s + L; E.n_groups = n_groups_host; E.rank = rank; E.world = world;
+    E.dict = dict_view();
+    E.out.key_off = res.key_off.as<int32_t>(); E.out.key_bytes = res.key_bytes.as<uint8_t>(); E.out.key_valid = res.key_valid.as<uint8_t>();
+    E.out.count = res.count.as<int64_t>(); E.out.mn = res.mn.as<double>(); E.out.mx = res.mx.as<double>(); E.out.avg = res.avg.as<double>();
+    E.out.sum = res.sum.as<double>(); E.out.agg_valid = res.agg_valid.as<uint8_t>(); E.out.wstart = res.wstart.as<int64_t>(); E.out.wend = res.wend.as<int64_t>();
+    E.out.cursor = d_cursor.as<unsigned long long>(); E.out.row_cap = res.row_cap; E.out.byte_cap = res.byte_cap;
+    E.out.overflow = d_cursor.as<uint32_t>() + 2;
+    CK(launch_emit(E, stream));
+    stats.total_launches++; stats.windows_emitted++;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+void dnz_window::fill_schema(ArrowSchema* schema) {
+  auto* sp = new SchemaPrivate();
+  size_t nc = 1 + aggs.size() + 2;
+  sp->names.reserve(nc);
+  auto add = [&](const std::string& name, const char* fmt, int64_t flags) {
+    sp->names.push_back(name);
+    auto c = std::make_unique<ArrowSchema>();
+    memset(c.get(), 0, sizeof(ArrowSchema));
+    c->format = fmt; c->flags = flags; c->release = release_child_schema;
+    sp->children.push_back(std::move(c));
+  };
+  add(key_name, "u", ARROW_FLAG_NULLABLE);
+  for (size_t i = 0; i < aggs.size(); i++) add(aliases[i], agg_format(aggs[i].kind), aggs[i].kind == DNZ_AGG_COUNT ? 0 : ARROW_FLAG_NULLABLE);
+  add("window_start_time", "tsm:", 0);     // continuous/mod.rs:42-62: Timestamp(ms, None), non-null
+  add("window_end_time", "tsm:", 0);
+  for (size_t i = 0; i < nc; i++) { sp->children[i]->name = sp->names[i].c_str(); sp->child_ptrs.push_back(sp->children[i].get()); }
+  memset(schema, 0, sizeof(*schema));
+  schema->format = "+s"; schema->name = ""; schema->n_children = (int64_t)nc; schema->children = sp->child_ptrs.data();
+  schema->release = release_schema; schema->private_data = sp;
+}
+
+void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output) {
+  sync_cursor();
+  const uint64_t n = res.rows, nbytes = res.bytes;
+  auto* ep = new ExportPrivate();
+  std::unique_ptr<ExportPrivate> guard(ep);
+  auto pinned = [&](size_t bytes) -> void* { void* p = nullptr; CK(cudaMallocHost(&p, std::max<size_t>(bytes, 64))); ep->pinned.push_back(p); return p; };
+  auto fetch = [&](const DevBuf& b, size_t bytes) -> void* {
+    void* h = pinned(bytes);
+    if (bytes) { CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (int64_t)bytes; }
+    return h;
+  };
+  int32_t* koff = (int32_t*)pinned((n + 1) * 4);
+  if (n) { CK(cudaMemcpyAsync(koff, res.key_off.p, n * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (int64_t)n * 4; }
+  uint8_t* kbytes = (uint8_t*)fetch(res.key_bytes, nbytes);
+  uint8_t* kvalid = (uint8_t*)fetch(res.key_valid, n);
+  int64_t* count = (int64_t*)fetch(res.count, n * 8);
+  double* mn = (double*)fetch(res.mn, n * 8); double* mx = (double*)fetch(res.mx, n * 8);
+  double* avg = (double*)fetch(res.avg, n * 8); double* sum = (double*)fetch(res.sum, n * 8);
+  uint8_t* avalid = (uint8_t*)fetch(res.agg_valid, n);
+  int64_t* ws = (int64_t*)fetch(res.wstart, n * 8); int64_t* we = (int64_t*)fetch(res.wend, n * 8);
+  CK(cudaStreamSynchronize(stream));
+  koff[n] = (int32_t)nbytes;
+  // byte-per-row validity -> Arrow bitmaps
+  auto pack = [&](const uint8_t* v, int64_t& nulls) -> uint8_t* {
+    nulls = 0;
+    for (uint64_t i = 0; i < n; i++) nulls += !v[i];
+    if (!nulls) return nullptr;
+    uint8_t* bm = (uint8_t*)pinned((n + 7) / 8 + 8);
+    memset(bm, 0, (n + 7) / 8 + 8);
+    for (uint64_t i = 0; i < n; i++) if (v[i]) bm[i >> 3] |= (uint8_t)(1u << (i & 7));
+    return bm;
+  };
+  int64_t key_nulls = 0, agg_nulls = 0;
+  uint8_t* kbm = pack(kvalid, key_nulls);
+  uint8_t* abm = pack(avalid, agg_nulls);
+  size_t nc = 1 + aggs.size() + 2;
+  auto add_child = [&](std::vector<const void*> bufs, int64_t nulls) {
+    ep->buffers.push_back(std::move(bufs));
+    auto c = std::make_unique<ArrowArray>();
+    memset(c.get(), 0, sizeof(ArrowArray));
+    c->length = (int64_t)n; c->null_count = nulls; c->n_buffers = (int64_t)ep->buffers.back().size();
+    c->buffers = ep->buffers.back().data(); c->release = release_child;
+    ep->children.push_back(std::move(c));
+  };
+  ep->buffers.reserve(nc + 1);
+  add_child({kbm, koff, kbytes}, key_nulls);
+  for (auto& a : aggs) {
+    switch (a.kind) {
+      case DNZ_AGG_COUNT: add_child({nullptr, count}, 0); break;
+      case DNZ_AGG_MIN: add_child({abm, mn}, agg_nulls); break;
+      case DNZ_AGG_MAX: add_child({abm, mx}, agg_nulls); break;
+      case DNZ_AGG_AVG: add_child({abm, avg}, agg_nulls); break;
+      default: add_child({abm, sum}, agg_nulls); break;
+    }
+  }
+  add_child({nullptr, ws}, 0);
+  add_child({nullptr, we}, 0);
+  for (auto& c : ep->children) ep->child_ptrs.push_back(c.get());
+  ep->buffers.push_back({nullptr});
+  memset(out, 0, sizeof(*out));
+  out->length = (int64_t)n; out->null_count = 0; out->n_buffers = 1; out->buffers = ep->buffers.back().data();
+  out->n_children = (int64_t)nc; out->children = ep->child_ptrs.data(); out->release = release_array;
+  out->private_data = guard.release();
+  if (schema) fill_schema(schema);
+  if (has_output) *has_output = n > 0;
+  stats.rows_out += (int64_t)n;
+  reset_results();
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define DNZ_TRY(w)                                                                  \
+  if (!(w)) { g_last_error = "null handle"; return DNZ_ERR_INVALID; }               \
+  if ((w)->sticky) return (w)->sticky;                                              \
+  cudaSetDevice((w)->dev);                                                          \
+  try {
+#define DNZ_CATCH(w)                                                                \
+  } catch (const DnzError& e) {                                                     \
+    (w)->err = e.msg; g_last_error = e.msg;                                         \
+    if (e.code == DNZ_ERR_CUDA) (w)->sticky = e.code;                               \
+    return e.code;                                                                  \
+  } catch (const std::exception& e) {                                               \
+    (w)->err = e.what(); g_last_error = e.what(); return DNZ_ERR_NOMEM;             \
+  }                                                                                 \
+  return DNZ_OK;
+
+extern "C" {
+
+int32_t dnz_window_create(const dnz_window_config* cfg, const struct ArrowSchema* input_schema, dnz_window** out) {
+  if (!out) { g_last_error = "null out"; return DNZ_ERR_INVALID; }
+  *out = nullptr;
+  dnz_window* w = nullptr;
+  try {
+    w = new dnz_window();
+    w->init(cfg, input_schema);
+    *out = w;
+    return DNZ_OK;
+  } catch (const DnzError& e) {
+    g_last_error = e.msg; delete w; return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what(); delete w; return DNZ_ERR_NOMEM;
+  }
+}
+
+int32_t dnz_window_push(dnz_window* w, struct ArrowArray* batch) {
+  DNZ_TRY(w)
+  w->push_host(batch);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_push_device(dnz_window* w, const dnz_device_batch* batches, int64_t n) {
+  DNZ_TRY(w)
+  if (n < 0 || (n > 0 && !batches)) fail(DNZ_ERR_INVALID, "bad batch list");
+  w->push_dev(batches, n);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output) {
+  DNZ_TRY(w)
+  if (!out) fail(DNZ_ERR_INVALID, "null out");
+  w->process_pending();
+  if (w->res_consumed) w->reset_results();
+  w->export_arrow(out, out_schema, has_output);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out) {
+  DNZ_TRY(w)
+  if (!out) fail(DNZ_ERR_INVALID, "null out");
+  w->process_pending();
+  if (w->res_consumed) w->reset_results();
+  w->sync_cursor();
+  out->n_rows = (int64_t)w->res.rows; out->key_bytes_len = (int64_t)w->res.bytes;
+  out->key_off = w->res.key_off.as<int32_t>(); out->key_bytes = w->res.key_bytes.as<uint8_t>(); out->key_valid = w->res.key_valid.as<uint8_t>();
+  out->count = w->res.count.as<int64_t>(); out->min = w->res.mn.as<double>(); out->max = w->res.mx.as<double>();
+  out->avg = w->res.avg.as<double>(); out->sum = w->res.sum.as<double>(); out->agg_valid = w->res.agg_valid.as<uint8_t>();
+  out->window_start_ms = w->res.wstart.as<int64_t>(); out->window_end_ms = w->res.wend.as<int64_t>();
+  w->stats.rows_out += (int64_t)w->res.rows;
+  w->res_consumed = true;         // buffers stay valid until the next call that produces output
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_flush(dnz_window* w, int64_t watermark_ms) {
+  DNZ_TRY(w)
+  w->process_pending();
+  if (w->res_consumed) w->reset_results();
+  w->emit_normal(watermark_ms);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_stats(const dnz_window* w, dnz_stats* out) {
+  if (!w || !out) return DNZ_ERR_INVALID;
+  *out = w->stats;
+  return DNZ_OK;
+}
+int32_t dnz_window_reset_stats(dnz_window* w) {
+  if (!w) return DNZ_ERR_INVALID;
+  int64_t g = w->stats.groups;
+  memset(&w->stats, 0, sizeof w->stats);
+  w->stats.groups = g;
+  return DNZ_OK;
+}
+int64_t dnz_window_watermark(const dnz_window* w) { return (w && w->has_wm) ? w->wm : INT64_MIN; }
+const char* dnz_window_last_error(const dnz_window* w) { return w ? w->err.c_str() : g_last_error.c_str(); }
+void dnz_window_destroy(dnz_window* w) { delete w; }
+
+int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
+  DNZ_TRY(w)
+  if (world < 1 || rank < 0 || rank >= world) fail(DNZ_ERR_INVALID, "bad rank/world");
+  w->rank = rank; w->world = world;
+  DNZ_CATCH(w)
+}
+int32_t dnz_window_export_partials(dnz_window* w, dnz_partials*) {
+  DNZ_TRY(w)
+  fail(DNZ_ERR_UNSUPPORTED, "pane exchange not built yet");
+  DNZ_CATCH(w)
+}
+int32_t dnz_window_import_partials(dnz_window* w, const uint8_t*, int64_t, const uint8_t*, int64_t) {
+  DNZ_TRY(w)
+  fail(DNZ_ERR_UNSUPPORTED, "pane exchange not built yet");
+  DNZ_CATCH(w)
+}
+
+void* dnz_host_alloc(int64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 64)) == cudaSuccess ? p : nullptr; }
+void dnz_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* dnz_device_alloc(int32_t device, int64_t bytes) {
+  void* p = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  return cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 256)) == cudaSuccess ? p : nullptr;
+}
+void dnz_device_free(int32_t device, void* p) { if (p) { cudaSetDevice(device); cudaFree(p); } }
+int32_t dnz_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+int32_t dnz_memcpy(void* dst, const void* src, int64_t bytes, int32_t kind) {
+  if (bytes <= 0) return DNZ_OK;
+  cudaError_t e = cudaMemcpy(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return DNZ_ERR_CUDA; }
+  return DNZ_OK;
+}
+
+struct dnz_synth {
+  int dev; void* ts; void* val; void* off; void* bytes; int64_t alg_bytes;
+};
+
+int32_t dnz_synth_generate(int32_t device, int64_t row0, int64_t n_rows, int64_t batch_rows, uint64_t seed, int64_t groups,
+                           int64_t rows_per_ms, int64_t t0_ms, int32_t uuid_keys, int64_t key_mul, int64_t key_add, dnz_synth** arena,
+                           dnz_device_batch* out, int64_t n_batches) {
+  if (!arena || !out || n_rows <= 0 || batch_rows <= 0 || groups <= 0 || rows_per_ms <= 0) { g_last_error = "bad synth arguments"; return DNZ_ERR_INVALID; }
+  int64_t nb = (n_rows + batch_rows - 1) / batch_rows;
+  if (n_batches < nb) { g_last_error = "batch array too small"; return DNZ_ERR_INVALID; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "no such CUDA device"; return DNZ_ERR_CUDA; }
+  int maxlen = 36;
+  if (key_mul < 1) key_mul = 1;
+  if (!uuid_keys) { maxlen = 8; for (int64_t v = (groups - 1) * key_mul + key_add; v >= 10; v /= 10) maxlen++; }
+  int64_t off_stride = (batch_rows + 1 + 3) & ~(int64_t)3;
+  int64_t bytes_stride = (batch_rows * maxlen + 15 + 16) & ~(int64_t)15;
+  dnz_synth* a = new dnz_synth{device, nullptr, nullptr, nullptr, nullptr, 0};
+  auto bail = [&](const char* m) { g_last_error = m; dnz_synth_free(a); return DNZ_ERR_CUDA; };
+  if (cudaMalloc(&a->ts, (size_t)n_rows * 8 + 64) != cudaSuccess) return bail("cudaMalloc(ts) failed");
+  if (cudaMalloc(&a->val, (size_t)n_rows * 8 + 64) != cudaSuccess) return bail("cudaMalloc(val) failed");
+  if (cudaMalloc(&a->off, (size_t)nb * off_stride * 4 + 64) != cudaSuccess) return bail("cudaMalloc(off) failed");
+  if (cudaMalloc(&a->bytes, (size_t)nb * bytes_stride + 64) != cudaSuccess) return bail("cudaMalloc(bytes) failed");
+  if (launch_synth(row0, n_rows, batch_rows, seed, groups, rows_per_ms, t0_ms, uuid_keys, key_mul, key_add, (int64_t*)a->ts, (double*)a->val,
+                   (int32_t*)a->off, (uint8_t*)a->bytes, bytes_stride, nullptr) != cudaSuccess) return bail("synth launch failed");
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail("synth kernel failed");
+  // algorithmic bytes: 20 B/row + key bytes (last offset of every batch)
+  std::vector<int32_t> last((size_t)nb);
+  for (int64_t b = 0; b < nb; b++) {
+    int64_t n = std::min(batch_rows, n_rows - b * batch_rows);
+    if (cudaMemcpy(&last[(size_t)b], (int32_t*)a->off + b * off_stride + n, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return bail("memcpy failed");
+  }
+  a->alg_bytes = 20 * n_rows;
+  for (int64_t b = 0; b < nb; b++) {
+    int64_t n = std::min(batch_rows, n_rows - b * batch_rows);
+    a->alg_bytes += last[(size_t)b];
+    dnz_device_batch& d = out[b];
+    memset(&d, 0, sizeof d);
+    d.n_rows = n; d.ts = (int64_t*)a->ts + b * batch_rows; d.val = (double*)a->val + b * batch_rows;
+    d.key_off = (int32_t*)a->off + b * off_stride; d.key_bytes = (uint8_t*)a->bytes + b * bytes_stride;
+  }
+  *arena = a;
+  return DNZ_OK;
+}
+int64_t dnz_synth_bytes(const dnz_synth* a) { return a ? a->alg_bytes : 0; }
+void dnz_synth_free(dnz_synth* a) {
+  if (!a) return;
+  cudaSetDevice(a->dev);
+  cudaFree(a->ts); cudaFree(a->val); cudaFree(a->off); cudaFree(a->bytes);
+  delete a;
+}
+
+}  // extern "C"

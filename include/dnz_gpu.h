@@ -1,0 +1,195 @@
+/*
+ * dnz_gpu.h -- C ABI of the B200 windowed grouped aggregate (+ post-aggregate filter).
+ *
+ * This is the drop-in boundary for Denormalized's streaming-window hot path.  Every entry
+ * point names the reference interface it replaces (paths relative to /root/reference/crates/core/src).
+ * Plain C: opaque handles, plain pointers and sizes, Arrow C Data Interface structs for RecordBatches.
+ * No C++ exception crosses the boundary; every call returns a status (0 = ok, <0 = error) and the
+ * message is available from dnz_window_last_error().  There is NO CPU fallback: if no CUDA device or an
+ * unsupported plan shape is given the call fails.
+ *
+ * Threading (mirrors `Stream::poll_next(&mut self)`): a handle is externally synchronised (one caller at
+ * a time) but not thread-affine; distinct handles may be used concurrently.
+ */
+#ifndef DNZ_GPU_H
+#define DNZ_GPU_H
+#include <stdint.h>
+#include "arrow_c_data.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNZ_ABI_VERSION 1
+
+/* status codes */
+#define DNZ_OK 0
+#define DNZ_ERR_INVALID (-1)      /* bad argument / schema mismatch                                      */
+#define DNZ_ERR_UNSUPPORTED (-2)  /* plan shape the GPU operator does not implement (no CPU fallback)     */
+#define DNZ_ERR_CUDA (-3)         /* CUDA runtime error (sticky per handle)                               */
+#define DNZ_ERR_DATA (-4)         /* input the reference would panic on (all-null timestamps, ts<epoch)   */
+#define DNZ_ERR_NOMEM (-5)
+
+/* AggregateFunctionExpr kinds accepted in DataStream::window(.., aggr_expr, ..) (datastream.rs:178-196) */
+enum { DNZ_AGG_COUNT = 0, DNZ_AGG_MIN = 1, DNZ_AGG_MAX = 2, DNZ_AGG_AVG = 3, DNZ_AGG_SUM = 4 };
+/* BinaryExpr operators of the post-aggregate DataStream::filter(predicate) (datastream.rs:94-105) */
+enum { DNZ_OP_GT = 0, DNZ_OP_GTE = 1, DNZ_OP_LT = 2, DNZ_OP_LTE = 3, DNZ_OP_EQ = 4, DNZ_OP_NEQ = 5 };
+
+#define DNZ_FLAG_KERNEL_TIMING 1u  /* record CUDA events around every aggregate-kernel launch (dnz_stats) */
+#define DNZ_FLAG_FORCE_GENERIC 2u  /* testing: disable the TMA-staged fast path                           */
+
+typedef struct {
+  int32_t kind;          /* DNZ_AGG_*                                            */
+  int32_t arg_column;    /* top-level input column index of the Float64 argument */
+  const char* alias;     /* output column name (count/min/max/average ...)       */
+} dnz_agg;
+
+/* Arguments of StreamingWindowExec::try_new (physical_plan/continuous/streaming_window.rs:221-251):
+ * group_by -> key_column, aggr_expr -> aggs, window_type -> window_ms/slide_ms; plus the FilterExec that
+ * the planner stacks directly above the window as an optional fused predicate. */
+typedef struct {
+  uint32_t abi_version;      /* DNZ_ABI_VERSION                                                     */
+  int32_t device;            /* CUDA device ordinal                                                 */
+  int32_t key_column;        /* top-level index of the Utf8 group-key column (one plain column,
+                                planner/streaming_window.rs:36-66)                                  */
+  int32_t n_aggs;
+  const dnz_agg* aggs;
+  int64_t window_ms;         /* PhysicalStreamingWindowType::{Tumbling(len) | Sliding(len, slide)}  */
+  int64_t slide_ms;          /* 0 = tumbling                                                        */
+  int32_t has_filter;        /* FilterExec: aggs[filter_agg] <filter_op> filter_literal             */
+  int32_t filter_agg;
+  int32_t filter_op;
+  uint32_t flags;
+  double filter_literal;     /* literal already coerced to Float64 (lit(113) -> 113.0)              */
+  int64_t expected_groups;   /* capacity hint (0 = default); tables grow on demand                  */
+  int64_t max_rows_per_launch; /* rows aggregated per kernel launch (0 = default 16 Mi)             */
+  void* cuda_stream;         /* optional caller-owned cudaStream_t for all work (NULL = own stream) */
+} dnz_window_config;
+
+typedef struct dnz_window dnz_window;
+
+/* One RecordBatch whose needed column buffers are already resident in device memory (the
+ * Arrow<->device buffer manager's output format; also what dnz_synth_generate produces).
+ * Validity bitmaps: Arrow LSB-first, NULL = no nulls, bit 0 = row 0. */
+typedef struct {
+  int64_t n_rows;
+  const int64_t* ts;        const uint8_t* ts_valid;    /* _streaming_internal_metadata.canonical_timestamp (ms) */
+  const double* val;        const uint8_t* val_valid;   /* aggregate argument                                     */
+  const int32_t* key_off;   const uint8_t* key_bytes;   const uint8_t* key_valid;  /* Utf8 key: n_rows+1 offsets */
+} dnz_device_batch;
+
+/* Emitted rows, device resident (valid until the next call on the handle). */
+typedef struct {
+  int64_t n_rows;
+  int64_t key_bytes_len;
+  const int32_t* key_off;  const uint8_t* key_bytes;  const uint8_t* key_valid;   /* one byte per row, 1 = valid */
+  const int64_t* count;
+  const double* min; const double* max; const double* avg; const double* sum;
+  const uint8_t* agg_valid;         /* one byte per row, shared by min/max/avg/sum (0 = null: no non-null value seen) */
+  const int64_t* window_start_ms; const int64_t* window_end_ms;
+} dnz_device_result;
+
+typedef struct {
+  int64_t rows_in;              /* input rows consumed                                   */
+  int64_t batches_in;
+  int64_t rows_out;             /* rows emitted (after the filter)                       */
+  int64_t windows_emitted;
+  int64_t groups;               /* distinct keys interned so far                         */
+  int64_t agg_launches;         /* aggregate-kernel launches                             */
+  int64_t total_launches;       /* all kernel launches issued by the handle              */
+  double agg_kernel_ms;         /* sum of aggregate-kernel durations (DNZ_FLAG_KERNEL_TIMING) */
+  double agg_algorithmic_bytes; /* 8 ts + 8 val + 4 offset + key bytes, summed over rows of timed launches */
+  int64_t h2d_bytes; int64_t d2h_bytes;
+  int64_t deferred_rows;        /* rows replayed after a table grew                      */
+  int64_t generic_tiles; int64_t fast_tiles;
+  int64_t late_batches;         /* batches that contained late rows (exact re-open path) */
+} dnz_stats;
+
+/* replaces: StreamingWindowExec::try_new + ExecutionPlan::execute(partition, ctx)
+ * (streaming_window.rs:221-251, :421-482) -- one handle per output partition.
+ * input_schema: the upstream schema; must contain struct column `_streaming_internal_metadata` with child
+ * `canonical_timestamp: Timestamp(ms)` (grouped_window_agg_stream.rs:549-560, common/src/lib.rs:5). */
+int32_t dnz_window_create(const dnz_window_config* cfg, const struct ArrowSchema* input_schema, dnz_window** out);
+
+/* replaces: the `Some(Ok(batch))` arm of GroupedWindowAggStream::poll_next_inner
+ * (grouped_window_agg_stream.rs:326-342).  `batch` is a struct array (the C-Data form of a RecordBatch) in HOST
+ * memory; it is MOVED (released by the callee once its buffers have been copied to the device).  Batches are
+ * queued and aggregated max_rows_per_launch rows at a time; results appear at the next poll. */
+int32_t dnz_window_push(dnz_window* w, struct ArrowArray* batch);
+
+/* Same for batches already resident on the device (zero copy).  Buffers must stay valid until the next
+ * dnz_window_poll or dnz_window_poll_device call returns. */
+int32_t dnz_window_push_device(dnz_window* w, const dnz_device_batch* batches, int64_t n_batches);
+
+/* replaces: the RecordBatch returned by poll_next (trigger_windows + concat_batches,
+ * grouped_window_agg_stream.rs:220-253) with FilterExec applied.  Aggregates everything queued, then returns ALL
+ * rows emitted since the previous poll as one RecordBatch (struct array) with schema
+ * key | aggs... | window_start_time | window_end_time (continuous/mod.rs:42-62).  *has_output = 0 and an
+ * empty batch when nothing closed (the reference returns an empty batch, :343-348). */
+int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output);
+
+/* As dnz_window_poll but leaves the emitted rows on the device. */
+int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out);
+
+/* Test/bench only (the reference has no flush: open windows are never emitted, :348): advance the watermark
+ * to watermark_ms as process_watermark would and trigger. */
+int32_t dnz_window_flush(dnz_window* w, int64_t watermark_ms);
+
+/* replaces: ExecutionPlan::metrics() / BaselineMetrics (streaming_window.rs:491-493) */
+int32_t dnz_window_stats(const dnz_window* w, dnz_stats* out);
+int32_t dnz_window_reset_stats(dnz_window* w);
+/* current watermark (ms) or INT64_MIN: GroupedWindowAggStream::latest_watermark */
+int64_t dnz_window_watermark(const dnz_window* w);
+/* replaces: DataFusionError message; valid until the next call on the handle (w may be NULL: global error) */
+const char* dnz_window_last_error(const dnz_window* w);
+/* replaces: Drop for GroupedWindowAggStream */
+void dnz_window_destroy(dnz_window* w);
+
+/* ---- multi-GPU pane exchange: the exchange of per-window partial aggregates replaces
+ * RepartitionExec(Hash(group keys)) (physical_optimizer/coalesce_before_streaming_window_aggregate.rs:63-73).
+ * A rank exports, for every window that closed, the partial states of the keys it does NOT own, packed by
+ * owner rank; the caller moves the packets with one all-to-all (NCCL, via torch.distributed) and the owner
+ * merges them before it emits.  owner(key) = hash64(key) % world. ------------------------------------- */
+typedef struct {
+  int64_t n_entries;            /* packed entries (sorted by owner rank)                       */
+  const uint8_t* entries;       /* device: n_entries * DNZ_PARTIAL_BYTES                        */
+  const int64_t* owner_counts;  /* host: entries per owner rank (world entries)                 */
+  int64_t key_bytes_len;        /* device key byte arena accompanying the entries               */
+  const uint8_t* key_bytes;
+  const int64_t* owner_key_bytes; /* host: key bytes per owner rank                             */
+} dnz_partials;
+#define DNZ_PARTIAL_BYTES 64
+int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world);
+/* Aggregates everything queued; packs the partial states of all windows that closed. */
+int32_t dnz_window_export_partials(dnz_window* w, dnz_partials* out);
+/* Merges packets received from the other ranks (device pointers), then the next poll emits owned keys. */
+int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, int64_t n_entries,
+                                   const uint8_t* key_bytes, int64_t key_bytes_len);
+
+/* ---- Arrow<->device buffer manager helpers ---------------------------------------------------------- */
+/* Page-locked host allocation: Arrow buffers placed here are copied host->device at full PCIe speed without a
+ * staging copy (arrow-rs: Buffer::from_custom_allocation). */
+void* dnz_host_alloc(int64_t bytes);
+void dnz_host_free(void* p);
+void* dnz_device_alloc(int32_t device, int64_t bytes);
+void dnz_device_free(int32_t device, void* p);
+int32_t dnz_device_count(void);
+/* plain cudaMemcpy for callers that hold device pointers from this library (kind: 1 = host->device, 2 = device->host) */
+int32_t dnz_memcpy(void* dst, const void* src, int64_t bytes, int32_t kind);
+
+/* ---- synthetic sensor stream (examples/examples/emit_measurements.rs:30-33,45) -------- */
+/* Generates rows [row0, row0+n_rows) of the counter-based stream directly into device buffers laid out as
+ * consecutive batches of batch_rows rows; fills `out` (n_batches = ceil(n_rows/batch_rows) entries).  The
+ * buffers belong to the returned arena handle and are freed by dnz_synth_free. */
+typedef struct dnz_synth dnz_synth;
+int32_t dnz_synth_generate(int32_t device, int64_t row0, int64_t n_rows, int64_t batch_rows, uint64_t seed,
+                           int64_t groups, int64_t rows_per_ms, int64_t t0_ms, int32_t uuid_keys,
+                           int64_t key_mul, int64_t key_add, /* key id = id * key_mul + key_add (rank sharding) */
+                           dnz_synth** arena, dnz_device_batch* out, int64_t n_batches);
+int64_t dnz_synth_bytes(const dnz_synth* arena);   /* algorithmic bytes held: 20*rows + key bytes */
+void dnz_synth_free(dnz_synth* arena);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -80,7 +80,7 @@ def lib():
         L.orc_mt_get_results.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
         L.orc_mt_clear_results.argtypes = [C.c_void_p]
         L.orc_synth_fill.restype = C.c_int64
-        L.orc_synth_fill.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+        L.orc_synth_fill.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -235,14 +235,14 @@ class OracleMT:
 
 
 def synth_batch(row0, n, *, seed=42, groups=1000, rows_per_ms=1000, t0_ms=1_700_000_000_000, uuid_keys=False,
-                extra_columns=False) -> Batch:
+                extra_columns=False, key_mul=1, key_add=0) -> Batch:
     """Rows [row0,row0+n) of the synthetic sensor stream."""
     L = lib()
     ts = np.empty(n, np.int64)
     val = np.empty(n, np.float64)
     off = np.empty(n + 1, np.int32)
     kb = np.empty(n * (36 if uuid_keys else 27) + 16, np.uint8)
-    used = L.orc_synth_fill(row0, n, seed, groups, rows_per_ms, t0_ms, 1 if uuid_keys else 0,
+    used = L.orc_synth_fill(row0, n, seed, groups, rows_per_ms, t0_ms, 1 if uuid_keys else 0, key_mul, key_add,
                             ts.ctypes.data, val.ctypes.data, off.ctypes.data, kb.ctypes.data)
     b = Batch(ts=ts, val=val, key_off=off, key_bytes=kb[:max(int(used), 1)])
     if extra_columns:

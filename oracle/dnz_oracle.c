@@ -534,13 +534,13 @@ static inline uint64_t splitmix64(uint64_t x) {
 }
 
 int64_t orc_synth_fill(int64_t row0, int64_t n, uint64_t seed, int64_t groups, int64_t rows_per_ms, int64_t t0_ms,
-                       int32_t uuid_keys, int64_t* ts, double* val, int32_t* key_off, uint8_t* key_bytes) {
+                       int32_t uuid_keys, int64_t key_mul, int64_t key_add, int64_t* ts, double* val, int32_t* key_off, uint8_t* key_bytes) {
   static const char hex[] = "0123456789abcdef";
   int32_t o = 0; key_off[0] = 0;
   for (int64_t k = 0; k < n; k++) {
     uint64_t i = (uint64_t)(row0 + k);
     uint64_t r = splitmix64(seed ^ i), r2 = splitmix64(r);
-    uint64_t key_id = (r >> 11) % (uint64_t)groups;
+    uint64_t key_id = ((r >> 11) % (uint64_t)groups) * (uint64_t)key_mul + (uint64_t)key_add;
     ts[k] = t0_ms + (int64_t)(i / (uint64_t)rows_per_ms);
     val[k] = ((double)(r2 >> 11) * 0x1.0p-53) * 115.0;
     uint8_t* p = key_bytes + o;

@@ -107,9 +107,10 @@ void orc_mt_clear_results(orc_mt* m);
 
 /* Synthetic sensor generator: counter-based, identical to the device generator.
  * Fills rows [row0, row0+n) of the global stream.  key_off must hold n+1 entries, key_bytes must hold
- * at least n*max_key_len bytes; returns bytes written.  uuid_keys != 0 -> 36-char UUID-shaped keys. */
+ * at least n*max_key_len bytes; returns bytes written.  uuid_keys != 0 -> 36-char UUID-shaped keys.
+ * key id = (r>>11) % groups * key_mul + key_add (key_mul=world, key_add=rank shards the key space by rank). */
 int64_t orc_synth_fill(int64_t row0, int64_t n, uint64_t seed, int64_t groups, int64_t rows_per_ms,
-                       int64_t t0_ms, int32_t uuid_keys,
+                       int64_t t0_ms, int32_t uuid_keys, int64_t key_mul, int64_t key_add,
                        int64_t* ts, double* val, int32_t* key_off, uint8_t* key_bytes);
 
 #ifdef __cplusplus

@@ -99,3 +99,52 @@ def random_stream(rng, n_batches, rows_per_batch, n_keys, t0=1_700_000_000_000, 
         batches.append(rows)
         t += span_ms
     return batches
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU-side helpers (import denormalized_b200 lazily so the CPU suite does not need the CUDA library)
+DEFAULT_AGGS = [("count", "reading", "count"), ("min", "reading", "min"), ("max", "reading", "max"), ("avg", "reading", "average")]
+
+
+def to_record_batch(b: Batch):
+    from denormalized_b200 import make_record_batch
+    return make_record_batch(b.ts, b.val, b.key_off, b.key_bytes, b.ts_valid, b.val_valid, b.key_valid)
+
+
+def record_batch_rows(rb, seq=0):
+    """Emitted RecordBatch (key|count|min|max|average|window_start_time|window_end_time) -> oracle-style row tuples."""
+    cols = {name: rb.column(i) for i, name in enumerate(rb.schema.names)}
+    keys = cols[rb.schema.names[0]].cast("binary").to_pylist()
+    cnt = cols["count"].to_pylist()
+    mn, mx, av = cols["min"].to_pylist(), cols["max"].to_pylist(), cols["average"].to_pylist()
+    ws = cols["window_start_time"].cast("int64").to_pylist()
+    we = cols["window_end_time"].cast("int64").to_pylist()
+    return [(ws[i], we[i], keys[i], cnt[i], mn[i], mx[i], av[i], seq) for i in range(rb.num_rows)]
+
+
+def gpu_window(L, S=0, filt=None, **kw):
+    from denormalized_b200 import GpuStreamingWindow, canonical_schema
+    return GpuStreamingWindow(canonical_schema(), "sensor_name", DEFAULT_AGGS, L, S, filt, **kw)
+
+
+def run_gpu(batches, L, S=0, filt=None, per_batch_poll=True, **kw):
+    """batches: list of oracle.Batch.  Returns rows (emit seq = index of the push that emitted them when per_batch_poll)."""
+    w = gpu_window(L, S, filt, **kw)
+    rows = []
+    for i, b in enumerate(batches):
+        w.push(to_record_batch(b))
+        if per_batch_poll:
+            rows += record_batch_rows(w.poll(), i)
+    if not per_batch_poll:
+        rows += record_batch_rows(w.poll(), 0)
+    st = w.stats()
+    w.close()
+    return rows, st
+
+
+def run_oracle_batches(batches, L, S=0, filt=None):
+    from oracle import OracleWindow
+    o = OracleWindow(L, S, filt)
+    for b in batches:
+        o.push(b)
+    return o.results()

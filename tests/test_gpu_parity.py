@@ -1,0 +1,143 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on identical inputs.  count/min/max bit-exact, avg within 1e-9 relative (north_star); rows compared as a multiset sorted
+by (window_start, key), plus the emitting push where polls are per batch."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import synth_batch
+from tests.helpers import (assert_rows_equal, random_stream, rows_to_batch, run_gpu, run_oracle_batches)
+
+pytestmark = pytest.mark.gpu
+T0 = 1_700_000_000_000
+
+
+def sentinel(ts):
+    return rows_to_batch([(ts, 1.0, b"sentinel")])
+
+
+@pytest.mark.parametrize("L,S", [(1000, 0), (2000, 0), (5000, 1000), (10_000, 1000), (4000, 2000)])
+@pytest.mark.parametrize("flags", [0, 2])
+def test_in_order_stream_per_batch(L, S, flags):
+    rng = np.random.default_rng(L + S)
+    batches = [rows_to_batch(r) for r in random_stream(rng, 30, 200, 17, span_ms=350, ragged=True)]
+    batches.append(sentinel(T0 + 30 * 350 + 3 * L))
+    got, st = run_gpu(batches, L, S, flags=flags)
+    want = run_oracle_batches(batches, L, S)
+    assert len(want) > 20
+    assert_rows_equal(got, want, check_seq=True)
+    assert st["late_batches"] == 0
+
+
+@pytest.mark.parametrize("L,S", [(1000, 0), (3000, 1000), (6000, 2000)])
+def test_late_rows_reopen_windows_exactly(L, S):
+    rng = np.random.default_rng(99 + L)
+    batches = [rows_to_batch(r) for r in random_stream(rng, 40, 60, 9, span_ms=350, jitter_ms=2500, ragged=True)]
+    batches.append(sentinel(T0 + 40 * 350 + 3 * L))
+    want = run_oracle_batches(batches, L, S)
+    got, st = run_gpu(batches, L, S)
+    assert st["late_batches"] > 0
+    assert_rows_equal(got, want, check_seq=True)
+    # queued mode (one poll for everything): same multiset of rows
+    got2, _ = run_gpu(batches, L, S, per_batch_poll=False)
+    assert_rows_equal(got2, want)
+
+
+@pytest.mark.parametrize("flags", [0, 2])
+def test_nulls_and_special_values(flags):
+    rng = np.random.default_rng(5)
+    raw = random_stream(rng, 25, 80, 6, span_ms=300, null_frac=0.15, special_vals=True)
+    raw[0] = raw[0] + [(T0 + 5, None, b"onlynull"), (T0 + 6, None, b"onlynull")]
+    batches = [rows_to_batch(r) for r in raw] + [sentinel(T0 + 25 * 300 + 9000)]
+    for L, S in [(1000, 0), (3000, 1000)]:
+        want = run_oracle_batches(batches, L, S)
+        got, _ = run_gpu(batches, L, S, flags=flags)
+        assert any(r[2] is None for r in want) and any(r[4] is None for r in want)
+        assert_rows_equal(got, want, check_seq=True)
+
+
+def test_min_max_quirks_and_filter_total_order():
+    rows = [(T0, float("nan"), b"nan"), (T0, -0.0, b"z1"), (T0 + 1, 0.0, b"z1"), (T0, 0.0, b"z2"), (T0 + 1, -0.0, b"z2"),
+            (T0, float("inf"), b"pinf"), (T0, float("-inf"), b"ninf"), (T0, 5.0, b"mix"), (T0, float("nan"), b"mix"),
+            (T0, 114.0, b"hi"), (T0, 112.0, b"lo"), (T0, None, b"null"), (T0, 113.0, b"eq")]
+    batches = [rows_to_batch(rows), sentinel(T0 + 3000)]
+    for filt in [None, ("max", ">", 113), ("average", ">", 113), ("count", ">=", 1), ("min", "<=", 0.0), ("max", "!=", 113)]:
+        want = run_oracle_batches(batches, 1000, 0, filt)
+        got, _ = run_gpu(batches, 1000, 0, filt)
+        assert_rows_equal(got, want, check_seq=True)
+    got = {r[2]: r for r in run_gpu(batches, 1000)[0]}
+    assert math.copysign(1, got[b"z1"][4]) == -1 and math.copysign(1, got[b"z2"][4]) == 1
+
+
+def test_long_and_empty_keys_and_dictionary_growth():
+    rng = np.random.default_rng(3)
+    rows_all = []
+    for b in range(12):
+        rows = []
+        for i in range(3000):
+            k = int(rng.integers(0, 5000))
+            key = (b"%05d" % k) * (1 + k % 11)            # lengths 5..55: inline and arena keys
+            if k == 7:
+                key = b""
+            rows.append((T0 + b * 400 + int(rng.integers(0, 400)), float(rng.random()), key))
+        rows_all.append(rows)
+    batches = [rows_to_batch(r) for r in rows_all] + [sentinel(T0 + 20_000)]
+    want = run_oracle_batches(batches, 2000, 1000)
+    got, st = run_gpu(batches, 2000, 1000, expected_groups=64, per_batch_poll=False)   # forces table growth + deferred rows
+    assert st["deferred_rows"] > 0
+    assert_rows_equal(got, want)
+
+
+def test_empty_batches_and_errors():
+    from denormalized_b200 import DnzError
+    from tests.helpers import gpu_window, to_record_batch, record_batch_rows
+    w = gpu_window(1000)
+    w.push(to_record_batch(rows_to_batch([(T0 + 10, 1.0, b"a")])))
+    w.push(to_record_batch(rows_to_batch([])))
+    assert w.poll().num_rows == 0 and w.watermark == T0 + 10
+    w.push(to_record_batch(rows_to_batch([(T0 + 1500, 2.0, b"a")])))
+    rb = w.poll()
+    assert record_batch_rows(rb) == [(T0, T0 + 1000, b"a", 1, 1.0, 1.0, 1.0, 0)]
+    assert rb.schema.names == ["sensor_name", "count", "min", "max", "average", "window_start_time", "window_end_time"]
+    with pytest.raises(DnzError):     # the reference panics on an all-null timestamp column
+        w.push(to_record_batch(rows_to_batch([(None, 1.0, b"a")])))
+        w.poll()
+    with pytest.raises(DnzError):     # window < 1 s divides by zero in the reference
+        gpu_window(500)
+
+
+@pytest.mark.parametrize("L,S,G,rpm,filt", [(1000, 0, 1000, 1000, None), (1000, 0, 20_000, 2000, ("max", ">", 113)),
+                                             (10_000, 1000, 50_000, 200, None)])
+def test_synthetic_sensor_stream_matches_oracle(L, S, G, rpm, filt):
+    """Reduced-size cfg 1 / cfg 4 / cfg 3 shapes on the host-fed path (64K-row batches, queued, one poll)."""
+    nb, n = 24, 65536
+    batches = [synth_batch(i * n, n, groups=G, rows_per_ms=rpm) for i in range(nb)]
+    last = int(batches[-1].ts[-1])
+    batches.append(sentinel((last // 1000 + 1) * 1000 + 2 * L))
+    want = run_oracle_batches(batches, L, S, filt)
+    got, st = run_gpu(batches, L, S, filt, per_batch_poll=False, expected_groups=G)
+    assert len(want) > 1000 and st["fast_tiles"] > 0 and st["generic_tiles"] <= 1
+    assert_rows_equal(got, want)
+
+
+def test_device_resident_path_equals_host_path():
+    """dnz_synth_generate (device generator) + push_device/poll_device == host generator + oracle."""
+    from denormalized_b200 import DeviceBatches
+    from tests.helpers import gpu_window
+    n, G, rpm = 1_000_000, 3000, 500
+    dev = DeviceBatches(n, 65536, groups=G, rows_per_ms=rpm)
+    w = gpu_window(1000, 0, None, expected_groups=G, flags=1)
+    w.push_device(dev)
+    w.flush(T0 + n // rpm + 5000)
+    r = w.fetch_device_result(w.poll_device())
+    st = w.stats()
+    got = [(int(r["window_start"][i]), int(r["window_end"][i]), r["key"][i], int(r["count"][i]),
+            float(r["min"][i]), float(r["max"][i]), float(r["avg"][i]), 0) for i in range(len(r["key"]))]
+    hb = [synth_batch(i, min(65536, n - i), groups=G, rows_per_ms=rpm) for i in range(0, n, 65536)]
+    hb.append(sentinel(T0 + n // rpm + 5000))
+    want = run_oracle_batches(hb, 1000)
+    assert_rows_equal(got, want)
+    assert st["agg_kernel_ms"] > 0 and st["agg_algorithmic_bytes"] == dev.algorithmic_bytes
+    w.close()
+    dev.free()
