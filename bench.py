@@ -272,6 +272,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def log(msg):
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+    log(f"device input ready: {rows} rows, {dev.n_batches} batches, {dev.algorithmic_bytes / 1e9:.2f} GB algorithmic")
     out_rows = 0
     for _ in range(args.warmup):
         w = new_window(); r = step_device(w); out_rows = r.n_rows; w.close()
@@ -286,6 +290,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    log(f"device-resident: {ms / args.steps:.2f} ms/step")
     stats = [w.stats() for w in wins]
     for w in wins:
         w.close()
@@ -339,6 +344,7 @@ def main():
             n_out = ca.length
             rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
             return n_out
+        log(f"e2e host batches ready: {e2e_rows} rows")
         for i in range(args.warmup):
             step_host(i)
         d2h0 = sum(w.stats()["d2h_bytes"] for w in e_wins)
@@ -367,6 +373,7 @@ def main():
         del hb, exported
         L.dnz_host_free(base)
 
+    log("e2e done" if e2e else "e2e skipped")
     # ---- CPU baseline on the host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -36,9 +36,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// one 32 B sector in a single request (SASS: LDG.E.256)
+// one 32 B sector in a single request (SASS: LDG.E.256), always served by L2: slots are written by other SMs
+// (atomicCAS + release store) while we probe, and the per-SM L1 is not coherent -- an L1-cached copy of an
+// EMPTY/LOCKED slot would make the probe loop spin forever.
 __device__ __forceinline__ void ld_slot(const DictSlot* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
-  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -182,8 +184,9 @@ __device__ __forceinline__ uint32_t dict_try_insert(const DictView& d, DictSlot*
 }
 
 __device__ __forceinline__ bool dict_long_equal(const DictView& d, uint64_t arena_off, const KeyRef& k, bool key_shared) {
+  // __ldcg: arena bytes of OTHER keys sharing an L1 sector may have been cached before this key was written
   for (uint32_t i = 0; i < k.len; i++)
-    if (d.arena[arena_off + i] != ld_key_byte(k.ptr + i, key_shared)) return false;
+    if (__ldcg(d.arena + arena_off + i) != ld_key_byte(k.ptr + i, key_shared)) return false;
   return true;
 }
 

@@ -445,26 +445,32 @@ typedef struct {
   int64_t emitted; int err;
 } mt_arg;
 
-/* RepartitionExec(Hash): hash the key of every row and `take` the rows of each output partition
- * (all columns are copied once more). */
+/* RepartitionExec(Hash): hash the key of every row (create_hashes), build the row-index list of each output
+ * partition, then `take` the rows of each partition (all columns are copied once more). */
 static void partition_batch(const orc_batch* b, int P, own_batch* subs /* [P] */) {
   int64_t n = b->n;
-  int64_t kb = n > 0 ? (int64_t)b->key_off[n] - b->key_off[0] : 0;
-  int64_t bb = (b->barrier_off && n > 0) ? (int64_t)b->barrier_off[n] - b->barrier_off[0] : 0;
-  for (int p = 0; p < P; p++) {
-    own_batch* o = &subs[p];
-    own_batch_reserve(o, n, kb, bb);
-    o->n = 0; o->key_off[0] = 0; o->barrier_off[0] = 0;
-    o->has_ts_valid = b->ts_valid != NULL; o->has_val_valid = b->val_valid != NULL; o->has_key_valid = b->key_valid != NULL;
-    o->has_occ = b->occurred_at != NULL; o->has_bar = b->barrier_off != NULL;
-    if (o->has_ts_valid) memset(o->ts_valid, 0, (size_t)((n + 7) / 8 + 1));
-    if (o->has_val_valid) memset(o->val_valid, 0, (size_t)((n + 7) / 8 + 1));
-    if (o->has_key_valid) memset(o->key_valid, 0, (size_t)((n + 7) / 8 + 1));
-  }
+  uint16_t* part = xrealloc(NULL, (size_t)(n ? n : 1) * 2);
+  int64_t* cnt = xcalloc((size_t)P, 8); int64_t* kbytes = xcalloc((size_t)P, 8); int64_t* bbytes = xcalloc((size_t)P, 8);
   for (int64_t i = 0; i < n; i++) {
     int32_t a = b->key_off[i], e = b->key_off[i + 1];
     uint64_t h = bit_get(b->key_valid, i) ? hash_bytes(b->key_bytes + a, e - a) : 0;
-    own_batch* o = &subs[(h >> 17) % (uint64_t)P];
+    int p = (int)((h >> 17) % (uint64_t)P);
+    part[i] = (uint16_t)p; cnt[p]++; kbytes[p] += e - a;
+    if (b->barrier_off) bbytes[p] += b->barrier_off[i + 1] - b->barrier_off[i];
+  }
+  for (int p = 0; p < P; p++) {
+    own_batch* o = &subs[p];
+    own_batch_reserve(o, cnt[p], kbytes[p], bbytes[p]);
+    o->n = 0; o->key_off[0] = 0; o->barrier_off[0] = 0;
+    o->has_ts_valid = b->ts_valid != NULL; o->has_val_valid = b->val_valid != NULL; o->has_key_valid = b->key_valid != NULL;
+    o->has_occ = b->occurred_at != NULL; o->has_bar = b->barrier_off != NULL;
+    if (o->has_ts_valid) memset(o->ts_valid, 0, (size_t)((cnt[p] + 7) / 8 + 1));
+    if (o->has_val_valid) memset(o->val_valid, 0, (size_t)((cnt[p] + 7) / 8 + 1));
+    if (o->has_key_valid) memset(o->key_valid, 0, (size_t)((cnt[p] + 7) / 8 + 1));
+  }
+  for (int64_t i = 0; i < n; i++) {
+    int32_t a = b->key_off[i], e = b->key_off[i + 1];
+    own_batch* o = &subs[part[i]];
     int64_t m = o->n++;
     o->ts[m] = b->ts[i]; if (o->has_ts_valid && bit_get(b->ts_valid, i)) bit_set(o->ts_valid, m);
     o->val[m] = b->val[i]; if (o->has_val_valid && bit_get(b->val_valid, i)) bit_set(o->val_valid, m);
@@ -473,6 +479,7 @@ static void partition_batch(const orc_batch* b, int P, own_batch* subs /* [P] */
     if (o->has_occ) o->occurred_at[m] = b->occurred_at[i];
     if (o->has_bar) { int32_t c = b->barrier_off[i], d = b->barrier_off[i + 1]; int32_t bo = o->barrier_off[m]; memcpy(o->barrier_bytes + bo, b->barrier_bytes + c, (size_t)(d - c)); o->barrier_off[m + 1] = bo + (d - c); }
   }
+  free(part); free(cnt); free(kbytes); free(bbytes);
 }
 
 static void* mt_worker(void* vp) {
@@ -499,7 +506,7 @@ static void* mt_worker(void* vp) {
 }
 
 int64_t orc_mt_push_many(orc_mt* m, const orc_batch* batches, int64_t nb) {
-  int P = m->P; const int64_t CH = 16;   /* batches per chunk: bounds the partition scratch */
+  int P = m->P; const int64_t CH = P * 2 > 16 ? P * 2 : 16;   /* batches per chunk: bounds the partition scratch */
   own_batch* subs = xcalloc((size_t)(CH * P), sizeof(own_batch));
   int64_t* wmn = xcalloc(CH, 8); int64_t* wmx = xcalloc(CH, 8); int* wany = xcalloc(CH, sizeof(int));
   pthread_t* th = xcalloc(P, sizeof(pthread_t)); mt_arg* args = xcalloc(P, sizeof(mt_arg));
