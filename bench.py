@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--max-rows-per-launch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra DNZ_FLAG_* bits for the operator (experiments)")
     return ap.parse_args()
 
 
@@ -259,7 +260,7 @@ def main():
 
     def new_window(flags=0):
         return d.GpuStreamingWindow(d.canonical_schema(), "sensor_name", AGGS, wl["window_ms"], wl["slide_ms"], wl["filt"], device=local,
-                                    flags=flags, expected_groups=G, max_rows_per_launch=args.max_rows_per_launch,
+                                    flags=flags | args.flags, expected_groups=G, max_rows_per_launch=args.max_rows_per_launch,
                                     cuda_stream=stream.cuda_stream)
 
     def step_device(w):

@@ -161,14 +161,10 @@ __device__ __forceinline__ uint32_t dict_try_insert(const DictView& d, DictSlot*
   }
   uint32_t old = atomicCAS(&slot->state, SLOT_EMPTY, SLOT_LOCKED);
   if (old != SLOT_EMPTY) return 0xFFFFFFFFu;
-  // group id: never exceed gcap
-  uint32_t g = *(volatile uint32_t*)d.n_groups;
-  for (;;) {
-    if (g >= d.gcap) { st_release_u32(&slot->state, SLOT_EMPTY); return GID_DEFER_GROUPS; }
-    uint32_t prev = atomicCAS(d.n_groups, g, g + 1);
-    if (prev == g) break;
-    g = prev;
-  }
+  // group id: one atomicAdd (a CAS loop on this single counter serialises every inserter on the chip).  The counter may
+  // run past gcap; ids >= gcap are never used (the rows are deferred) and the host clamps the counter before it grows.
+  uint32_t g = atomicAdd(d.n_groups, 1u);
+  if (g >= d.gcap) { st_release_u32(&slot->state, SLOT_EMPTY); return GID_DEFER_GROUPS; }
   if (k.len > (uint32_t)INLINE_KEY) {
     for (uint32_t i = 0; i < k.len; i++) d.arena[arena_off + i] = ld_key_byte(k.ptr + i, key_shared);
     slot->k0 = k.k0; slot->k1 = arena_off; slot->k2 = 0;
@@ -218,13 +214,8 @@ __device__ __forceinline__ uint32_t dict_lookup_null(const DictView& d) {
     if (s == 0) {
       uint32_t old = atomicCAS(d.null_gid, 0u, SLOT_LOCKED);
       if (old != 0) continue;
-      uint32_t g = *(volatile uint32_t*)d.n_groups;
-      for (;;) {
-        if (g >= d.gcap) { st_release_u32(d.null_gid, 0u); return GID_DEFER_GROUPS; }
-        uint32_t prev = atomicCAS(d.n_groups, g, g + 1);
-        if (prev == g) break;
-        g = prev;
-      }
+      uint32_t g = atomicAdd(d.n_groups, 1u);
+      if (g >= d.gcap) { st_release_u32(d.null_gid, 0u); return GID_DEFER_GROUPS; }
       d.slot_of_gid[g] = 0xFFFFFFFFu;
       __threadfence();
       st_release_u32(d.null_gid, g + 1);
@@ -251,15 +242,15 @@ __device__ __forceinline__ uint32_t dict_lookup(const DictView& d, const KeyRef&
 __device__ __forceinline__ bool value_needs_fz(double v) { return v == 0.0; }
 
 __device__ __forceinline__ void state_update(GroupState* st, unsigned long long* fz, uint32_t gid, double v,
-                                             unsigned long long rowseq) {
+                                             unsigned long long rowseq, bool precheck) {
   GroupState* s = st + gid;
   unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   if (v == 0.0) {                      // both zeros order as +0.0; remember which one came first
     red_min_u64(fz + gid, (rowseq << 1) | (bits >> 63));
     bits = 0ull;
   }
-  unsigned long long curmn, curmx;
-  ld_minmax(s, curmn, curmx);
+  unsigned long long curmn = 0, curmx = 0;
+  if (precheck) ld_minmax(s, curmn, curmx);   // saves ~90 % of the min/max reductions but adds a dependent L2 round trip
   red_add_u64(&s->cnt, 1ull);
   red_add_f64(&s->sum, v);
   unsigned long long o = ord_bits(bits);

@@ -99,8 +99,9 @@ __device__ __forceinline__ bool apply_row(const AggParams& P, uint32_t tile, uin
     fm = m ? P.panes.fz_main[pi] : nullptr; fl = l ? P.panes.fz_late[pi] : nullptr;
     if ((m && !fm) || (l && !fl)) { defer_row(P.defer, tile, row, DEFER_NEED_FZ); return false; }
   }
-  if (m) state_update(m, fm, gid, v, rowseq);
-  if (l) state_update(l, fl, gid, v, rowseq);
+  const bool pre = P.flags & AGG_MINMAX_PRECHECK;
+  if (m) state_update(m, fm, gid, v, rowseq, pre);
+  if (l) state_update(l, fl, gid, v, rowseq, pre);
   return true;
 }
 

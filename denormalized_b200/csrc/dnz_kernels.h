@@ -52,7 +52,7 @@ struct __align__(32) DictSlot {
 constexpr uint32_t SLOT_EMPTY = 0u, SLOT_LOCKED = 0xFFFFFFFFu;
 
 struct DictView {
-  DictSlot* slots; uint32_t mask;     // capacity - 1 (power of two, >= 2 * gcap)
+  DictSlot* slots; uint32_t mask;     // capacity - 1 (power of two, 4 * gcap)
   uint32_t gcap;                      // group ids must stay < gcap (capacity of the per-pane state arrays)
   uint32_t* n_groups;                 // device counter
   uint32_t* null_gid;                 // 0 = unassigned, 0xFFFFFFFF locked, else gid + 1 (group of the NULL key)
@@ -86,7 +86,9 @@ enum : uint32_t { DEFER_GROUPS_FULL = 1, DEFER_ARENA_FULL = 2, DEFER_NEED_FZ = 4
 struct AggParams {
   const BatchDesc* batches; const TileDesc* tiles; int64_t tile_begin, tile_end;
   DictView dict; PaneTable panes; DeferList defer;
+  uint32_t flags;
 };
+enum : uint32_t { AGG_MINMAX_PRECHECK = 1 };
 
 // ------------------------------------------------------------------------------------------------
 // Emission: combine the panes of one window, evaluate the predicate, compact into Arrow-shaped columns.

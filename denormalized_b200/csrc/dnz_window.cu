@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -126,9 +127,15 @@ struct dnz_window {
   int64_t max_rows = 16ll << 20;
 
   // dictionary
-  DevBuf slots, slot_of_gid, arena, counters;   // counters: [0] n_groups(u32) [1] null_gid(u32) [2..3] arena_used(u64) [4..5] key_bytes_total(u64)
+  DevBuf slots, slot_of_gid, arena;
+  // one 256 B device control block so that a single D2H copy fetches everything the host needs after a launch:
+  //   +0   n_groups(u32) null_gid(u32) arena_used(u64) key_bytes_total(u64)
+  //   +64  deferred-row count(u64) flags(u32)
+  //   +128 result cursor(u64: rows<<32|bytes) overflow(u32)
+  DevBuf d_ctl;
+  char* ctl(size_t off) const { return d_ctl.as<char>() + off; }
   uint32_t dict_cap = 0, gcap = 0; uint64_t arena_cap = 0;
-  uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0;
+  uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0; uint64_t defer_count_host = 0; uint32_t defer_flags_host = 0;
 
   // panes
   std::map<int64_t, std::unique_ptr<Pane>> panes;
@@ -142,9 +149,9 @@ struct dnz_window {
   Arena in_arena; bool copies_in_flight = false;
 
   // scratch
-  DevBuf d_batches, d_tiles, d_minmax, d_ptrs, d_defer[2], d_defer_ctl, d_cursor;
+  DevBuf d_batches, d_tiles, d_minmax, d_ptrs, d_defer[2];
   PinnedBuf h_stage, h_minmax, h_tiles, h_small;
-  ResultSet res; bool res_consumed = false;
+  ResultSet res; bool res_consumed = false; bool ctl_fresh = false;
 
   // multi-GPU
   int rank = 0, world = 1;
@@ -158,7 +165,7 @@ struct dnz_window {
   void dict_alloc(uint32_t new_gcap);
   void dict_grow();
   void arena_grow();
-  void sync_counters();
+  void fetch_ctl();
   Pane* get_pane(int64_t id, bool create);
   std::unique_ptr<Pane> new_pane(int64_t id);
   void ensure_side_arrays(Pane* p);
@@ -172,7 +179,6 @@ struct dnz_window {
   void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
   void emit_normal(int64_t wm_new);
   void ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes);
-  void sync_cursor();
   void reset_results();
   void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output);
   void fill_schema(ArrowSchema* schema);
@@ -182,17 +188,37 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 // Arrow C-Data export plumbing
+// Page-locked blocks for exported results are recycled: cudaMallocHost costs milliseconds, a poll must not.
+struct PinnedPool {
+  std::mutex m; std::multimap<size_t, void*> free_blocks;
+  void* get(size_t n, size_t& cap) {
+    {
+      std::lock_guard<std::mutex> g(m);
+      auto it = free_blocks.lower_bound(n);
+      if (it != free_blocks.end() && it->first <= 4 * n + (1 << 20)) { void* p = it->second; cap = it->first; free_blocks.erase(it); return p; }
+    }
+    void* p = nullptr; cap = round_up(n + n / 4, 1 << 16);
+    CK(cudaMallocHost(&p, cap));
+    return p;
+  }
+  void put(void* p, size_t cap) {
+    std::lock_guard<std::mutex> g(m);
+    if (free_blocks.size() >= 8) { auto it = free_blocks.begin(); cudaFreeHost(it->second); free_blocks.erase(it); }
+    free_blocks.emplace(cap, p);
+  }
+};
+PinnedPool g_pinned_pool;
+
 struct ExportPrivate {
-  std::vector<void*> pinned;               // cudaMallocHost allocations
+  void* block = nullptr; size_t block_cap = 0;   // one pooled page-locked block holds every exported buffer
+  ~ExportPrivate() { if (block) g_pinned_pool.put(block, block_cap); }
   std::vector<std::unique_ptr<ArrowArray>> children; std::vector<ArrowArray*> child_ptrs;
   std::vector<std::vector<const void*>> buffers;
 };
 void release_array(ArrowArray* a) {
   if (!a || !a->release) return;
   if (a->private_data) {
-    auto* p = static_cast<ExportPrivate*>(a->private_data);
-    for (void* q : p->pinned) cudaFreeHost(q);
-    delete p;
+    delete static_cast<ExportPrivate*>(a->private_data);
   }
   a->release = nullptr;
 }
@@ -290,12 +316,10 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(agg_kernel_setup());
 
-  counters.alloc(64); CK(cudaMemsetAsync(counters.p, 0, 64, stream));
-  d_defer_ctl.alloc(64); d_cursor.alloc(64);
-  CK(cudaMemsetAsync(d_cursor.p, 0, 64, stream));
+  d_ctl.alloc(256); CK(cudaMemsetAsync(d_ctl.p, 0, 256, stream));
   uint64_t eg = c->expected_groups > 0 ? (uint64_t)c->expected_groups : (1ull << 16);
   uint64_t g0 = 1024; while (g0 < eg + eg / 8) g0 <<= 1;
-  if (g0 > (1ull << 30)) fail(DNZ_ERR_INVALID, "expected_groups too large");
+  if (g0 > (1ull << 29)) fail(DNZ_ERR_INVALID, "expected_groups too large");
   dict_alloc((uint32_t)g0);
   arena_cap = 1 << 20; arena.alloc(arena_cap);
   CK(cudaStreamSynchronize(stream));
@@ -304,7 +328,7 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
 DictView dnz_window::dict_view() const {
   DictView d;
   d.slots = slots.as<DictSlot>(); d.mask = dict_cap - 1; d.gcap = gcap;
-  uint32_t* c32 = counters.as<uint32_t>();
+  uint32_t* c32 = reinterpret_cast<uint32_t*>(ctl(0));
   d.n_groups = c32; d.null_gid = c32 + 1;
   d.arena_used = reinterpret_cast<unsigned long long*>(c32 + 2);
   d.key_bytes_total = reinterpret_cast<unsigned long long*>(c32 + 4);
@@ -315,7 +339,7 @@ DictView dnz_window::dict_view() const {
 
 // (re)allocate dictionary + per-pane state arrays for `new_gcap` groups, preserving contents
 void dnz_window::dict_alloc(uint32_t new_gcap) {
-  uint32_t new_cap = new_gcap * 2;
+  uint32_t new_cap = new_gcap * 4;     // load factor <= 25 %: the probe length of the slowest lane paces a warp
   DevBuf ns, ng;
   ns.alloc((size_t)new_cap * sizeof(DictSlot)); CK(cudaMemsetAsync(ns.p, 0, ns.bytes, stream));
   ng.alloc((size_t)new_gcap * 4); CK(cudaMemsetAsync(ng.p, 0xFF, ng.bytes, stream));
@@ -340,7 +364,7 @@ void dnz_window::dict_alloc(uint32_t new_gcap) {
   dict_cap = new_cap; gcap = new_gcap;
 }
 void dnz_window::dict_grow() {
-  if (gcap >= (1u << 30)) fail(DNZ_ERR_NOMEM, "more than 2^30 groups");
+  if (gcap >= (1u << 29)) fail(DNZ_ERR_NOMEM, "more than 2^29 groups");
   dict_alloc(gcap * 2);
 }
 void dnz_window::arena_grow() {
@@ -349,12 +373,19 @@ void dnz_window::arena_grow() {
   CK(cudaStreamSynchronize(stream));
   arena = std::move(na); arena_cap *= 2;
 }
-void dnz_window::sync_counters() {
-  h_small.reserve(64);
-  CK(cudaMemcpyAsync(h_small.p, counters.p, 32, cudaMemcpyDeviceToHost, stream));
+// one small D2H + sync: group count, key bytes, deferred rows, result cursor
+void dnz_window::fetch_ctl() {
+  h_small.reserve(256);
+  CK(cudaMemcpyAsync(h_small.p, d_ctl.p, 192, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
-  n_groups_host = h_small.as<uint32_t>()[0];
-  key_bytes_total_host = reinterpret_cast<uint64_t*>(h_small.as<uint32_t>() + 4)[0];
+  const char* h = h_small.as<char>();
+  n_groups_host = std::min(*reinterpret_cast<const uint32_t*>(h), gcap);
+  key_bytes_total_host = *reinterpret_cast<const uint64_t*>(h + 16);
+  defer_count_host = *reinterpret_cast<const uint64_t*>(h + 64);
+  defer_flags_host = *reinterpret_cast<const uint32_t*>(h + 72);
+  uint64_t c = *reinterpret_cast<const uint64_t*>(h + 128);
+  res.rows = c >> 32; res.bytes = c & 0xFFFFFFFFull;
+  if (*reinterpret_cast<const uint32_t*>(h + 136)) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
   stats.groups = n_groups_host;
 }
 
@@ -613,10 +644,11 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
         hp[4 * np + k] = m ? m->fz.p : nullptr; hp[5 * np + k] = l ? l->fz.p : nullptr;
       }
       CK(cudaMemcpyAsync(d_ptrs.p, hp, 6 * pb, cudaMemcpyHostToDevice, stream));
-      CK(cudaMemsetAsync(d_defer_ctl.p, 0, 16, stream));
+      CK(cudaMemsetAsync(ctl(64), 0, 16, stream));
       AggParams P;
       P.batches = d_batches.as<BatchDesc>(); P.tiles = d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
       P.dict = dict_view();
+      P.flags = (cfg.flags & DNZ_FLAG_MINMAX_PRECHECK) ? AGG_MINMAX_PRECHECK : 0;
       char* dp = d_ptrs.as<char>();
       P.panes.pane0 = pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
       P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
@@ -625,8 +657,8 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
       const int out_list = iter == 0 ? 0 : (in_list ^ 1);
       d_defer[out_list].reserve(defer_cap * sizeof(DeferEntry));
       P.defer.entries = d_defer[out_list].as<DeferEntry>();
-      P.defer.count = d_defer_ctl.as<unsigned long long>(); P.defer.cap = defer_cap;
-      P.defer.flags = d_defer_ctl.as<uint32_t>() + 2;
+      P.defer.count = reinterpret_cast<unsigned long long*>(ctl(64)); P.defer.cap = defer_cap;
+      P.defer.flags = reinterpret_cast<uint32_t*>(ctl(72));
       const bool timing = iter == 0 && (cfg.flags & DNZ_FLAG_KERNEL_TIMING);
       if (iter == 0) {
         if (timing) CK(cudaEventRecord(ev0, stream));
@@ -638,18 +670,21 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
         CK(launch_deferred(P, d_defer[in_list].as<DeferEntry>(), n_in, stream));   // replays the rows of the previous pass
         stats.total_launches++;
       }
-      h_small.reserve(64);
-      CK(cudaMemcpyAsync(h_small.p, d_defer_ctl.p, 16, cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
+      fetch_ctl();
       if (timing) {
         float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += alg_bytes;
       }
-      uint64_t cnt = h_small.as<uint64_t>()[0]; uint32_t flags = h_small.as<uint32_t>()[2];
-      if (cnt == 0) break;
+      uint64_t cnt = defer_count_host; uint32_t flags = defer_flags_host;
+      if (cnt == 0) { ctl_fresh = true; break; }
       if (flags & DEFER_LIST_OVERFLOW) fail(DNZ_ERR_NOMEM, "deferred-row list overflow");
       stats.deferred_rows += (int64_t)cnt;
-      if (flags & DEFER_GROUPS_FULL) dict_grow();
+      if (flags & DEFER_GROUPS_FULL) {
+        uint32_t clamp = gcap;       // the device counter ran past gcap; ids >= gcap were never handed out
+        CK(cudaMemcpyAsync(ctl(0), &clamp, 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        dict_grow();
+      }
       if (flags & DEFER_ARENA_FULL) arena_grow();
       if (flags & DEFER_NEED_FZ) need_fz = true;
       if (flags & DEFER_NEED_NULLROWS) need_nullrows = true;
@@ -692,15 +727,6 @@ void dnz_window::emit_normal(int64_t wm_new) {
   retire_panes();
 }
 
-void dnz_window::sync_cursor() {
-  h_small.reserve(64);
-  CK(cudaMemcpyAsync(h_small.p, d_cursor.p, 16, cudaMemcpyDeviceToHost, stream));
-  CK(cudaStreamSynchronize(stream));
-  uint64_t c = h_small.as<uint64_t>()[0];
-  res.rows = c >> 32; res.bytes = c & 0xFFFFFFFFull;
-  if (h_small.as<uint32_t>()[2]) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
-}
-
 void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
   uint64_t need_rows = res.rows + add_rows, need_bytes = res.bytes + add_bytes;
   if (need_bytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes between polls (Utf8 offsets are 32-bit); poll more often");
@@ -726,16 +752,16 @@ void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
 }
 
 void dnz_window::reset_results() {
-  CK(cudaMemsetAsync(d_cursor.p, 0, 16, stream));
+  CK(cudaMemsetAsync(ctl(128), 0, 16, stream));
   res.rows = 0; res.bytes = 0; res_consumed = false;
 }
 
 // One k_emit launch per window: combine its panes, apply the fused FilterExec predicate, compact.
 void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src) {
   if (starts.empty()) return;
-  sync_counters();
+  if (!ctl_fresh) fetch_ctl();        // group count + result cursor (already fetched after an aggregate launch)
+  ctl_fresh = false;
   if (n_groups_host == 0) return;
-  sync_cursor();
   ensure_result_capacity((uint64_t)starts.size() * n_groups_host, (uint64_t)starts.size() * key_bytes_total_host);
   for (int64_t s : starts) {
     EmitParams E; memset(&E, 0, sizeof E);
@@ -756,11 +782,12 @@ void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map
     E.out.key_off = res.key_off.as<int32_t>(); E.out.key_bytes = res.key_bytes.as<uint8_t>(); E.out.key_valid = res.key_valid.as<uint8_t>();
     E.out.count = res.count.as<int64_t>(); E.out.mn = res.mn.as<double>(); E.out.mx = res.mx.as<double>(); E.out.avg = res.avg.as<double>();
     E.out.sum = res.sum.as<double>(); E.out.agg_valid = res.agg_valid.as<uint8_t>(); E.out.wstart = res.wstart.as<int64_t>(); E.out.wend = res.wend.as<int64_t>();
-    E.out.cursor = d_cursor.as<unsigned long long>(); E.out.row_cap = res.row_cap; E.out.byte_cap = res.byte_cap;
-    E.out.overflow = d_cursor.as<uint32_t>() + 2;
+    E.out.cursor = reinterpret_cast<unsigned long long*>(ctl(128)); E.out.row_cap = res.row_cap; E.out.byte_cap = res.byte_cap;
+    E.out.overflow = reinterpret_cast<uint32_t*>(ctl(136));
     CK(launch_emit(E, stream));
     stats.total_launches++; stats.windows_emitted++;
   }
+  ctl_fresh = false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -786,11 +813,15 @@ void dnz_window::fill_schema(ArrowSchema* schema) {
 }
 
 void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output) {
-  sync_cursor();
+  fetch_ctl(); ctl_fresh = false;
   const uint64_t n = res.rows, nbytes = res.bytes;
   auto* ep = new ExportPrivate();
   std::unique_ptr<ExportPrivate> guard(ep);
-  auto pinned = [&](size_t bytes) -> void* { void* p = nullptr; CK(cudaMallocHost(&p, std::max<size_t>(bytes, 64))); ep->pinned.push_back(p); return p; };
+  const size_t total = round_up((n + 1) * 4, 64) + round_up(nbytes, 64) + 2 * round_up(n, 64) + 7 * round_up(n * 8, 64) +
+                       2 * round_up((n + 7) / 8 + 8, 64) + 1024;
+  ep->block = g_pinned_pool.get(total, ep->block_cap);
+  size_t used = 0;
+  auto pinned = [&](size_t bytes) -> void* { void* p = (char*)ep->block + used; used += round_up(std::max<size_t>(bytes, 8), 64); return p; };
   auto fetch = [&](const DevBuf& b, size_t bytes) -> void* {
     void* h = pinned(bytes);
     if (bytes) { CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (int64_t)bytes; }
@@ -917,7 +948,7 @@ int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out) {
   if (!out) fail(DNZ_ERR_INVALID, "null out");
   w->process_pending();
   if (w->res_consumed) w->reset_results();
-  w->sync_cursor();
+  w->fetch_ctl(); w->ctl_fresh = false;
   out->n_rows = (int64_t)w->res.rows; out->key_bytes_len = (int64_t)w->res.bytes;
   out->key_off = w->res.key_off.as<int32_t>(); out->key_bytes = w->res.key_bytes.as<uint8_t>(); out->key_valid = w->res.key_valid.as<uint8_t>();
   out->count = w->res.count.as<int64_t>(); out->min = w->res.mn.as<double>(); out->max = w->res.mx.as<double>();

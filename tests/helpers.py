@@ -74,15 +74,16 @@ def assert_rows_equal(got, want, rel=1e-9, check_seq=False):
 
 
 def random_stream(rng, n_batches, rows_per_batch, n_keys, t0=1_700_000_000_000, span_ms=400, jitter_ms=0,
-                  null_frac=0.0, special_vals=False, ragged=False):
+                  null_frac=0.0, special_vals=False, ragged=False, late_every=0, late_shift_ms=0):
     """Mostly in-order batches of (ts,val,key) rows; jitter_ms>0 makes batches overlap / arrive late."""
     batches = []
     t = t0
-    for _ in range(n_batches):
+    for bi in range(n_batches):
         n = int(rng.integers(0, rows_per_batch + 1)) if ragged else rows_per_batch
         rows = []
+        back = late_shift_ms if (late_every and bi % late_every == late_every - 1) else 0   # a whole batch arrives late
         for _ in range(n):
-            ts = t + int(rng.integers(0, span_ms)) - (int(rng.integers(0, jitter_ms)) if jitter_ms else 0)
+            ts = t - back + int(rng.integers(0, span_ms)) - (int(rng.integers(0, jitter_ms)) if jitter_ms else 0)
             k = int(rng.integers(0, n_keys))
             key = b"sensor_%d" % k if k % 7 else b"k" * (k % 40)   # some long / empty keys
             val = float(rng.random() * 115.0)

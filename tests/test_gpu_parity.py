@@ -18,7 +18,7 @@ def sentinel(ts):
 
 
 @pytest.mark.parametrize("L,S", [(1000, 0), (2000, 0), (5000, 1000), (10_000, 1000), (4000, 2000)])
-@pytest.mark.parametrize("flags", [0, 2])
+@pytest.mark.parametrize("flags", [0, 2, 4])
 def test_in_order_stream_per_batch(L, S, flags):
     rng = np.random.default_rng(L + S)
     batches = [rows_to_batch(r) for r in random_stream(rng, 30, 200, 17, span_ms=350, ragged=True)]
@@ -33,9 +33,14 @@ def test_in_order_stream_per_batch(L, S, flags):
 @pytest.mark.parametrize("L,S", [(1000, 0), (3000, 1000), (6000, 2000)])
 def test_late_rows_reopen_windows_exactly(L, S):
     rng = np.random.default_rng(99 + L)
-    batches = [rows_to_batch(r) for r in random_stream(rng, 40, 60, 9, span_ms=350, jitter_ms=2500, ragged=True)]
+    batches = [rows_to_batch(r) for r in random_stream(rng, 40, 60, 9, span_ms=350, jitter_ms=700, ragged=True,
+                                                       late_every=5, late_shift_ms=4200)]
     batches.append(sentinel(T0 + 40 * 350 + 3 * L))
     want = run_oracle_batches(batches, L, S)
+    seen = {}
+    for r in want:                      # the stream really re-opens windows: some (window, key) is emitted more than once
+        seen[(r[0], r[2])] = seen.get((r[0], r[2]), 0) + 1
+    assert max(seen.values()) > 1
     got, st = run_gpu(batches, L, S)
     assert st["late_batches"] > 0
     assert_rows_equal(got, want, check_seq=True)

@@ -52,7 +52,8 @@ def test_window_enumeration_tumbling_and_sliding():
 @pytest.mark.parametrize("jitter", [0, 1500])
 def test_oracle_matches_python_model(L, S, jitter):
     rng = np.random.default_rng(L * 7 + S + jitter)
-    batches = random_stream(rng, 30, 40, 9, span_ms=350, jitter_ms=jitter, ragged=True)
+    batches = random_stream(rng, 30, 40, 9, span_ms=350, jitter_ms=jitter, ragged=True, late_every=6 if jitter else 0,
+                            late_shift_ms=3 * jitter)
     batches.append([(T0 + 30 * 350 + 3 * L, 1.0, b"sentinel")])
     assert_rows_equal(run_oracle(batches, L, S), run_model(batches, L, S), rel=0.0, check_seq=True)
 
