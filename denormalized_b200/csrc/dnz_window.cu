@@ -105,6 +105,12 @@ struct PendingBatch {
   ArrowArray moved{};
 };
 
+// Batches queued for one aggregate pass (<= max_rows_per_launch rows).  Host batches are copied into the superbatch's
+// arena while the PREVIOUS superbatch is being aggregated, so PCIe transfers overlap kernels and host-side planning.
+struct Superbatch {
+  std::vector<PendingBatch> batches; int64_t rows = 0; int arena = 0; bool copies = false;
+};
+
 struct ResultSet {             // device columns of the rows emitted since the last poll
   DevBuf key_off, key_bytes, key_valid, count, mn, mx, avg, sum, agg_valid, wstart, wend;
   uint64_t row_cap = 0, byte_cap = 0;
@@ -122,7 +128,7 @@ struct dnz_window {
   int key_col = -1, val_col = -1, meta_col = -1, ts_child = -1, n_input_cols = 0;
   int dev = 0; int sm_count = 148;
   cudaStream_t stream = nullptr; bool own_stream = false;
-  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t L = 0, S = 0, pane_ms = 0; int panes_per_window = 1;
   int64_t max_rows = 16ll << 20;
 
@@ -145,8 +151,9 @@ struct dnz_window {
   int64_t emitted_upto = INT64_MIN;
 
   // pending input
-  std::vector<PendingBatch> pending; int64_t pending_rows = 0; int64_t next_seq = 0;
-  Arena in_arena; bool copies_in_flight = false;
+  Superbatch cur, sealed; bool has_sealed = false; int64_t next_seq = 0;
+  std::vector<PendingBatch>* active = nullptr;    // batches of the superbatch being aggregated
+  Arena in_arena[2]; cudaEvent_t copy_done[2] = {nullptr, nullptr};
 
   // scratch
   DevBuf d_batches, d_tiles, d_minmax, d_ptrs, d_defer[2];
@@ -173,6 +180,9 @@ struct dnz_window {
   void push_host(ArrowArray* batch);
   void push_dev(const dnz_device_batch* b, int64_t n);
   void process_pending();
+  void seal_current();
+  void process_superbatch(Superbatch& sb);
+  void prealloc();
   void process_chunk(size_t b0, size_t b1);
   void execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0, size_t rb1,
                    bool dirty, int64_t horizon, int64_t wm_after);
@@ -241,10 +251,11 @@ const char* agg_format(int kind) { return kind == DNZ_AGG_COUNT ? "l" : "g"; }
 // =================================================================================================
 dnz_window::~dnz_window() {
   cudaSetDevice(dev);
-  for (auto& pb : pending) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+  if (copy_stream) cudaStreamSynchronize(copy_stream);
+  for (Superbatch* sb : {&cur, &sealed}) for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
   if (stream) cudaStreamSynchronize(stream);
-  if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
-  if (copy_done) cudaEventDestroy(copy_done);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (auto& e : copy_done) if (e) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (own_stream && stream) cudaStreamDestroy(stream);
@@ -312,7 +323,7 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   if (c->cuda_stream) { stream = (cudaStream_t)c->cuda_stream; own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
   CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
+  for (auto& e : copy_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(agg_kernel_setup());
 
@@ -322,6 +333,7 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   if (g0 > (1ull << 29)) fail(DNZ_ERR_INVALID, "expected_groups too large");
   dict_alloc((uint32_t)g0);
   arena_cap = 1 << 20; arena.alloc(arena_cap);
+  prealloc();
   CK(cudaStreamSynchronize(stream));
 }
 
@@ -431,7 +443,8 @@ void dnz_window::push_host(ArrowArray* batch) {
   if (batch->n_children != n_input_cols) fail(DNZ_ERR_INVALID, "batch has %lld columns, schema has %d", (long long)batch->n_children, n_input_cols);
   int64_t n = batch->length;
   if (n >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
-  if (pending_rows > 0 && pending_rows + n > max_rows) process_pending();
+  if (cur.rows > 0 && cur.rows + n > max_rows) seal_current();
+  Arena& arena_in = in_arena[cur.arena];
   PendingBatch pb;
   pb.d.n_rows = n; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
   if (n > 0) {
@@ -442,7 +455,7 @@ void dnz_window::push_host(ArrowArray* batch) {
     const ArrowArray* ts = meta->children[ts_child];
     if (key->length < po + n || val->length < po + n || ts->length < po + meta->offset + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
     auto copy_in = [&](const void* src, size_t bytes) -> void* {
-      void* d = in_arena.alloc(bytes);
+      void* d = arena_in.alloc(bytes);
       CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream));
       stats.h2d_bytes += (int64_t)bytes;
       return d;
@@ -472,15 +485,15 @@ void dnz_window::push_host(ArrowArray* batch) {
     int64_t a0 = o0 & ~(int64_t)15;
     pb.key_bytes = o1 - o0;
     const uint8_t* hb = (const uint8_t*)buf_at(key, 2);
-    uint8_t* db = (uint8_t*)in_arena.alloc((size_t)(o1 - a0) + 16);
+    uint8_t* db = (uint8_t*)arena_in.alloc((size_t)(o1 - a0) + 16);
     if (o1 > a0) { CK(cudaMemcpyAsync(db, hb + a0, (size_t)(o1 - a0), cudaMemcpyHostToDevice, copy_stream)); stats.h2d_bytes += o1 - a0; }
     pb.d.bytes = db - a0;     // only [o0, o1) is ever dereferenced
     copy_bitmap(key, ko, pb.d.key_valid, pb.d.key_vbit);
-    copies_in_flight = true;
+    cur.copies = true;
   }
   pb.has_moved = true; pb.moved = *batch; batch->release = nullptr;   // moved
-  pending.push_back(pb);
-  pending_rows += n;
+  cur.batches.push_back(pb);
+  cur.rows += n;
   stats.batches_in++; stats.rows_in += n;
 }
 
@@ -488,31 +501,50 @@ void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
   for (int64_t i = 0; i < nb; i++) {
     const dnz_device_batch& s = b[i];
     if (s.n_rows >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
-    if (pending_rows > 0 && pending_rows + s.n_rows > max_rows) process_pending();
+    if (cur.rows > 0 && cur.rows + s.n_rows > max_rows) seal_current();
     PendingBatch pb;
     pb.d.ts = s.ts; pb.d.val = s.val; pb.d.off = s.key_off; pb.d.bytes = s.key_bytes;
     pb.d.ts_valid = s.ts_valid; pb.d.val_valid = s.val_valid; pb.d.key_valid = s.key_valid;
     pb.d.n_rows = s.n_rows; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
     pb.key_bytes = -1;
-    pending.push_back(pb);
-    pending_rows += s.n_rows;
+    cur.batches.push_back(pb);
+    cur.rows += s.n_rows;
     stats.batches_in++; stats.rows_in += s.n_rows;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// The current superbatch is full: aggregate the previously sealed one (its successor's copies are already in flight on the
+// copy stream, so they overlap this work), then seal the current one and start filling the other arena.
+void dnz_window::seal_current() {
+  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
+  if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+  std::swap(sealed, cur); has_sealed = true;
+  cur.batches.clear(); cur.rows = 0; cur.copies = false; cur.arena = sealed.arena ^ 1;
+}
+
 void dnz_window::process_pending() {
-  if (pending.empty()) return;
+  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
+  if (!cur.batches.empty()) {
+    if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+    process_superbatch(cur);
+  }
+}
+
+void dnz_window::process_superbatch(Superbatch& sb) {
+  if (sb.batches.empty()) return;
   if (res_consumed) reset_results();
-  if (copies_in_flight) { CK(cudaEventRecord(copy_done, copy_stream)); CK(cudaStreamWaitEvent(stream, copy_done, 0)); }
+  if (sb.copies) CK(cudaStreamWaitEvent(stream, copy_done[sb.arena], 0));
   struct Cleanup {
-    dnz_window* w;
+    dnz_window* w; Superbatch* sb;
     ~Cleanup() {
-      if (w->copies_in_flight) cudaStreamSynchronize(w->copy_stream);
-      for (auto& pb : w->pending) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
-      w->pending.clear(); w->pending_rows = 0; w->in_arena.reset(); w->copies_in_flight = false;
+      if (sb->copies) cudaEventSynchronize(w->copy_done[sb->arena]);
+      for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+      sb->batches.clear(); sb->rows = 0; sb->copies = false; w->in_arena[sb->arena].reset(); w->active = nullptr;
     }
-  } cleanup{this};
+  } cleanup{this, &sb};
+  active = &sb.batches;
+  std::vector<PendingBatch>& pending = sb.batches;
   // chunks of <= max_rows rows (a single batch larger than that forms its own chunk)
   size_t b0 = 0;
   while (b0 < pending.size()) {
@@ -523,12 +555,24 @@ void dnz_window::process_pending() {
   }
 }
 
+// Everything a steady-state pass needs is allocated when the operator is created (cudaMalloc / cudaMallocHost cost
+// milliseconds and must stay out of the per-batch path).
+void dnz_window::prealloc() {
+  const size_t nb_max = 16384 + (size_t)(max_rows / 4096), nt_max = (size_t)(max_rows / TILE) + nb_max;
+  d_batches.reserve(nb_max * sizeof(BatchDesc)); d_tiles.reserve(nt_max * sizeof(TileDesc)); d_minmax.reserve(nb_max * sizeof(BatchMinMax));
+  d_ptrs.reserve(6 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
+  h_stage.reserve(std::max(nb_max * sizeof(BatchDesc), (size_t)6 * 1024 * sizeof(void*)));
+  h_minmax.reserve(nb_max * sizeof(BatchMinMax)); h_tiles.reserve(nt_max * sizeof(TileDesc)); h_small.reserve(256);
+  for (int i = 0; i < panes_per_window + 2 && i < 8; i++) pane_pool.push_back(new_pane(0));
+  ensure_result_capacity((uint64_t)gcap * (panes_per_window > 1 ? 2 : 4), (uint64_t)gcap * 16 * (panes_per_window > 1 ? 2 : 4));
+}
+
 void dnz_window::process_chunk(size_t b0, size_t b1) {
   const size_t nb = b1 - b0;
   // ---- batch descriptors + tile scan (RecordBatchWatermark per batch)
   std::vector<BatchDesc> bds(nb);
   int64_t n_tiles = 0;
-  for (size_t i = 0; i < nb; i++) { bds[i] = pending[b0 + i].d; bds[i].tile0 = n_tiles; n_tiles += (bds[i].n_rows + TILE - 1) / TILE; }
+  for (size_t i = 0; i < nb; i++) { bds[i] = (*active)[b0 + i].d; bds[i].tile0 = n_tiles; n_tiles += (bds[i].n_rows + TILE - 1) / TILE; }
   if (n_tiles == 0) return;                 // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
   // empty batches own no tile; give them the tile0 of their successor so that the binary search never selects them
   d_batches.reserve(nb * sizeof(BatchDesc)); d_tiles.reserve((size_t)n_tiles * sizeof(TileDesc)); d_minmax.reserve(nb * sizeof(BatchMinMax));
@@ -586,7 +630,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
   {
     int64_t acc = 0;
     for (size_t i = 0; i < rb1; i++) {
-      int64_t nt = (pending[chunk_b0 + i].d.n_rows + TILE - 1) / TILE;
+      int64_t nt = ((*active)[chunk_b0 + i].d.n_rows + TILE - 1) / TILE;
       if (i == rb0) t0 = acc;
       acc += nt;
     }
@@ -608,7 +652,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
     int64_t np = pmax - pmin + 1;
     if (np > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one launch spans %lld panes (timestamps too sparse); limit 65536", (long long)np);
     bool val_nulls = false;
-    for (size_t i = rb0; i < rb1; i++) if (pending[chunk_b0 + i].d.val_valid) val_nulls = true;
+    for (size_t i = rb0; i < rb1; i++) if ((*active)[chunk_b0 + i].d.val_valid) val_nulls = true;
     if (val_nulls && !need_nullrows) { need_nullrows = true; for (auto& kv : panes) ensure_side_arrays(kv.second.get()); }
     std::vector<uint8_t> touched((size_t)np, 0);
     for (int64_t t = t0; t < t1; t++) {

@@ -416,34 +416,47 @@ int64_t orc_push(orc_window* w, const orc_batch* b) {
 /* multi-threaded hash-partition mode (timed CPU baseline)                                     */
 
 struct orc_mt {
-  orc_config cfg; int P;
+  orc_config cfg; int P; int64_t CH;
   orc_window** parts;
-  /* per (partition) scratch batch for the current input batch: filled by the partitioning pass */
-  own_batch* sub;
+  /* persistent worker pool + scratch: [CH][P] sub-batches produced by the partitioning phase of the current chunk */
+  pthread_t* th; struct mt_arg* args;
+  pthread_barrier_t bar_start, bar_mid, bar_end;
+  own_batch* subs; int64_t* wm_min; int64_t* wm_max; int* wm_any;
+  const orc_batch* batches; int64_t c0, c1; int stop;
   char err[256];
 };
+
+typedef struct mt_arg { orc_mt* m; int tid; int64_t emitted; int err; } mt_arg;
+
+static void* mt_worker(void* vp);
 
 orc_mt* orc_mt_create(const orc_config* cfg, int partitions) {
   orc_mt* m = xcalloc(1, sizeof(orc_mt));
   m->cfg = *cfg; m->P = partitions < 1 ? 1 : partitions;
-  m->parts = xcalloc(m->P, sizeof(orc_window*));
-  for (int p = 0; p < m->P; p++) m->parts[p] = orc_create(cfg);
+  int P = m->P;
+  m->CH = P * 2 > 16 ? P * 2 : 16;                 /* batches per chunk: bounds the partition scratch */
+  m->parts = xcalloc(P, sizeof(orc_window*));
+  for (int p = 0; p < P; p++) m->parts[p] = orc_create(cfg);
+  m->subs = xcalloc((size_t)(m->CH * P), sizeof(own_batch));
+  m->wm_min = xcalloc(m->CH, 8); m->wm_max = xcalloc(m->CH, 8); m->wm_any = xcalloc(m->CH, sizeof(int));
+  pthread_barrier_init(&m->bar_start, NULL, (unsigned)P + 1);
+  pthread_barrier_init(&m->bar_mid, NULL, (unsigned)P);
+  pthread_barrier_init(&m->bar_end, NULL, (unsigned)P + 1);
+  m->th = xcalloc(P, sizeof(pthread_t)); m->args = xcalloc(P, sizeof(mt_arg));
+  for (int t = 0; t < P; t++) { m->args[t].m = m; m->args[t].tid = t; pthread_create(&m->th[t], NULL, mt_worker, &m->args[t]); }
   return m;
 }
 void orc_mt_destroy(orc_mt* m) {
   if (!m) return;
+  m->stop = 1;
+  pthread_barrier_wait(&m->bar_start);
+  for (int t = 0; t < m->P; t++) pthread_join(m->th[t], NULL);
+  pthread_barrier_destroy(&m->bar_start); pthread_barrier_destroy(&m->bar_mid); pthread_barrier_destroy(&m->bar_end);
+  for (int64_t i = 0; i < m->CH * m->P; i++) own_batch_free(&m->subs[i]);
+  free(m->subs); free(m->wm_min); free(m->wm_max); free(m->wm_any); free(m->th); free(m->args);
   for (int p = 0; p < m->P; p++) orc_destroy(m->parts[p]);
   free(m->parts); free(m);
 }
-
-typedef struct {
-  orc_mt* m; const orc_batch* batches; int64_t nb; int tid;
-  own_batch* subs;          /* [nb_chunk][P] sub-batches, produced in phase 1 */
-  int64_t* wm_min; int64_t* wm_max; int* wm_any;
-  int64_t c0, c1;           /* chunk range */
-  pthread_barrier_t* bar;
-  int64_t emitted; int err;
-} mt_arg;
 
 /* RepartitionExec(Hash): hash the key of every row (create_hashes), build the row-index list of each output
  * partition, then `take` the rows of each partition (all columns are copied once more). */
@@ -484,45 +497,42 @@ static void partition_batch(const orc_batch* b, int P, own_batch* subs /* [P] */
 
 static void* mt_worker(void* vp) {
   mt_arg* a = (mt_arg*)vp; orc_mt* m = a->m; int P = m->P;
-  /* phase 1: threads split the chunk's batches and hash-partition them */
-  for (int64_t i = a->c0 + a->tid; i < a->c1; i += P) {
-    const orc_batch* b = &a->batches[i];
-    a->wm_any[i - a->c0] = batch_watermark(b, &a->wm_min[i - a->c0], &a->wm_max[i - a->c0]);
-    partition_batch(b, P, a->subs + (i - a->c0) * P);
+  for (;;) {
+    pthread_barrier_wait(&m->bar_start);
+    if (m->stop) return NULL;
+    /* phase 1: threads split the chunk's batches and hash-partition them */
+    for (int64_t i = m->c0 + a->tid; i < m->c1; i += P) {
+      const orc_batch* b = &m->batches[i];
+      m->wm_any[i - m->c0] = batch_watermark(b, &m->wm_min[i - m->c0], &m->wm_max[i - m->c0]);
+      partition_batch(b, P, m->subs + (i - m->c0) * P);
+    }
+    pthread_barrier_wait(&m->bar_mid);
+    /* phase 2: thread p runs partition p's stream over its sub-batches in batch order */
+    orc_window* w = m->parts[a->tid];
+    for (int64_t i = m->c0; i < m->c1 && !a->err; i++) {
+      if (m->batches[i].n == 0) { w->seq++; continue; }
+      if (!m->wm_any[i - m->c0]) { a->err = -1; break; }
+      orc_batch v = own_as_view(&m->subs[(i - m->c0) * P + a->tid]);
+      int64_t r = stream_push(w, &v, 1, m->wm_min[i - m->c0], m->wm_max[i - m->c0], v.n > 0);
+      w->seq++;
+      if (r < 0) { a->err = (int)r; break; }
+      a->emitted += r;
+    }
+    pthread_barrier_wait(&m->bar_end);
   }
-  pthread_barrier_wait(a->bar);
-  /* phase 2: thread p runs partition p's stream over its sub-batches in batch order */
-  orc_window* w = m->parts[a->tid];
-  for (int64_t i = a->c0; i < a->c1; i++) {
-    if (a->batches[i].n == 0) { w->seq++; continue; }
-    if (!a->wm_any[i - a->c0]) { a->err = -1; break; }
-    orc_batch v = own_as_view(&a->subs[(i - a->c0) * P + a->tid]);
-    int64_t r = stream_push(w, &v, 1, a->wm_min[i - a->c0], a->wm_max[i - a->c0], v.n > 0);
-    w->seq++;
-    if (r < 0) { a->err = (int)r; break; }
-    a->emitted += r;
-  }
-  return NULL;
 }
 
 int64_t orc_mt_push_many(orc_mt* m, const orc_batch* batches, int64_t nb) {
-  int P = m->P; const int64_t CH = P * 2 > 16 ? P * 2 : 16;   /* batches per chunk: bounds the partition scratch */
-  own_batch* subs = xcalloc((size_t)(CH * P), sizeof(own_batch));
-  int64_t* wmn = xcalloc(CH, 8); int64_t* wmx = xcalloc(CH, 8); int* wany = xcalloc(CH, sizeof(int));
-  pthread_t* th = xcalloc(P, sizeof(pthread_t)); mt_arg* args = xcalloc(P, sizeof(mt_arg));
-  int64_t total = 0; int err = 0;
-  for (int64_t c0 = 0; c0 < nb && !err; c0 += CH) {
-    int64_t c1 = c0 + CH < nb ? c0 + CH : nb;
-    pthread_barrier_t bar; pthread_barrier_init(&bar, NULL, (unsigned)P);
-    for (int t = 0; t < P; t++) {
-      args[t] = (mt_arg){m, batches, nb, t, subs, wmn, wmx, wany, c0, c1, &bar, 0, 0};
-      pthread_create(&th[t], NULL, mt_worker, &args[t]);
-    }
-    for (int t = 0; t < P; t++) { pthread_join(th[t], NULL); total += args[t].emitted; if (args[t].err) err = args[t].err; }
-    pthread_barrier_destroy(&bar);
+  int P = m->P; int64_t total = 0; int err = 0;
+  for (int t = 0; t < P; t++) { m->args[t].emitted = 0; m->args[t].err = 0; }
+  m->batches = batches;
+  for (int64_t c0 = 0; c0 < nb && !err; c0 += m->CH) {
+    m->c0 = c0; m->c1 = c0 + m->CH < nb ? c0 + m->CH : nb;
+    pthread_barrier_wait(&m->bar_start);
+    pthread_barrier_wait(&m->bar_end);
+    for (int t = 0; t < P; t++) if (m->args[t].err) err = m->args[t].err;
   }
-  for (int64_t i = 0; i < CH * P; i++) own_batch_free(&subs[i]);
-  free(subs); free(wmn); free(wmx); free(wany); free(th); free(args);
+  for (int t = 0; t < P; t++) total += m->args[t].emitted;
   return err ? err : total;
 }
 int64_t orc_mt_num_results(const orc_mt* m) { int64_t n = 0; for (int p = 0; p < m->P; p++) n += m->parts[p]->res.n; return n; }
