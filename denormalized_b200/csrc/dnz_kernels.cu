@@ -22,9 +22,11 @@ __global__ void k_init_minmax(BatchMinMax* mm, int64_t n) {
   if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].pad = 0; }
 }
 
+// one warp per tile, 8 tiles per CTA; aligned tiles are read with 128-bit loads, 16 in flight per lane
 __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__ batches, int64_t n_batches, int64_t n_tiles,
                                                     int64_t pane_ms, TileDesc* __restrict__ tiles, BatchMinMax* mm, int allow_fast) {
-  int64_t t = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= n_tiles) return;
   // batch that owns tile t: last b with tile0 <= t
   int64_t lo = 0, hi = n_batches - 1;
@@ -33,20 +35,25 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
   int64_t row0 = (t - bd.tile0) * TILE;
   int n = (int)min((int64_t)TILE, bd.n_rows - row0);
   long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    bool ok = bd.ts_valid == nullptr || bit_at(bd.ts_valid, bd.ts_vbit + row0 + r);
-    if (ok) { long long v = bd.ts[row0 + r]; mn = min(mn, v); mx = max(mx, v); cnt++; }
+  const long long* ts = reinterpret_cast<const long long*>(bd.ts) + row0;
+  if (!bd.ts_valid && (reinterpret_cast<uintptr_t>(ts) & 15u) == 0) {
+    const longlong2* p = reinterpret_cast<const longlong2*>(ts);
+    const int np = n >> 1;
+#pragma unroll 4
+    for (int i = lane; i < np; i += 32) { longlong2 v = __ldg(p + i); mn = min(mn, min(v.x, v.y)); mx = max(mx, max(v.x, v.y)); }
+    if ((n & 1) && lane == 0) { long long v = ts[n - 1]; mn = min(mn, v); mx = max(mx, v); }
+    cnt = (lane == 0) ? n : 0;
+  } else {
+    for (int r = lane; r < n; r += 32) {
+      bool ok = bd.ts_valid == nullptr || bit_at(bd.ts_valid, bd.ts_vbit + row0 + r);
+      if (ok) { long long v = ts[r]; mn = min(mn, v); mx = max(mx, v); cnt++; }
+    }
   }
   for (int o = 16; o; o >>= 1) {
     mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  __shared__ long long smn[8], smx[8]; __shared__ int scnt[8];
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { smn[w] = mn; smx[w] = mx; scnt[w] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); i++) { mn = min(mn, smn[i]); mx = max(mx, smx[i]); cnt += scnt[i]; }
+  if (lane == 0) {
     TileDesc td;
     td.batch = (int32_t)lo; td.row0 = (int32_t)row0; td.n_rows = n; td.flags = 0;
     int32_t o0 = bd.off[row0], o1 = bd.off[row0 + n];
@@ -72,7 +79,7 @@ cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_
                              BatchMinMax* minmax, bool allow_fast, cudaStream_t s) {
   if (n_batches <= 0 || n_tiles <= 0) return cudaSuccess;
   k_init_minmax<<<(unsigned)((n_batches + 255) / 256), 256, 0, s>>>(minmax, n_batches);
-  k_tile_scan<<<(unsigned)n_tiles, 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
+  k_tile_scan<<<(unsigned)((n_tiles + 7) / 8), 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -130,7 +130,7 @@ struct dnz_window {
   cudaStream_t stream = nullptr; bool own_stream = false;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t L = 0, S = 0, pane_ms = 0; int panes_per_window = 1;
-  int64_t max_rows = 16ll << 20;
+  int64_t max_rows = 64ll << 20;
 
   // dictionary
   DevBuf slots, slot_of_gid, arena;
@@ -156,8 +156,13 @@ struct dnz_window {
   Arena in_arena[2]; cudaEvent_t copy_done[2] = {nullptr, nullptr};
 
   // scratch
-  DevBuf d_batches, d_tiles, d_minmax, d_ptrs, d_defer[2];
-  PinnedBuf h_stage, h_minmax, h_tiles, h_small;
+  struct Scan {
+    DevBuf d_batches, d_tiles, d_minmax; PinnedBuf h_batches, h_minmax, h_tiles; cudaEvent_t done = nullptr;
+    std::vector<BatchDesc> bds; int64_t n_tiles = 0; bool launched = false;
+  } scan[2];
+  Scan* cur_scan = nullptr;
+  DevBuf d_ptrs, d_defer[2];
+  PinnedBuf h_stage, h_small;
   ResultSet res; bool res_consumed = false; bool ctl_fresh = false;
 
   // multi-GPU
@@ -183,7 +188,8 @@ struct dnz_window {
   void seal_current();
   void process_superbatch(Superbatch& sb);
   void prealloc();
-  void process_chunk(size_t b0, size_t b1);
+  void process_chunk(Superbatch& sb);
+  void launch_scan(Superbatch& sb);
   void execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0, size_t rb1,
                    bool dirty, int64_t horizon, int64_t wm_after);
   void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
@@ -256,6 +262,7 @@ dnz_window::~dnz_window() {
   if (stream) cudaStreamSynchronize(stream);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+  for (auto& sc : scan) if (sc.done) cudaEventDestroy(sc.done);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (own_stream && stream) cudaStreamDestroy(stream);
@@ -517,8 +524,9 @@ void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
 // The current superbatch is full: aggregate the previously sealed one (its successor's copies are already in flight on the
 // copy stream, so they overlap this work), then seal the current one and start filling the other arena.
 void dnz_window::seal_current() {
-  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
   if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+  launch_scan(cur);                                   // tile scan of the new superbatch is queued before ...
+  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }   // ... the previous one is aggregated
   std::swap(sealed, cur); has_sealed = true;
   cur.batches.clear(); cur.rows = 0; cur.copies = false; cur.arena = sealed.arena ^ 1;
 }
@@ -527,70 +535,77 @@ void dnz_window::process_pending() {
   if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
   if (!cur.batches.empty()) {
     if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+    launch_scan(cur);
     process_superbatch(cur);
   }
+}
+
+// Batch descriptors + tile scan (RecordBatchWatermark::try_from per batch, byte ranges per tile), asynchronously: the
+// results land in this arena's pinned buffers and `done` fires when they are readable.
+void dnz_window::launch_scan(Superbatch& sb) {
+  Scan& sc = scan[sb.arena];
+  const size_t nb = sb.batches.size();
+  sc.bds.resize(nb); sc.n_tiles = 0; sc.launched = true;
+  for (size_t i = 0; i < nb; i++) { sc.bds[i] = sb.batches[i].d; sc.bds[i].tile0 = sc.n_tiles; sc.n_tiles += (sc.bds[i].n_rows + TILE - 1) / TILE; }
+  if (sc.n_tiles == 0) return;            // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
+  // the scan picks the LAST batch with tile0 <= t: empty batches in the middle share their successor's tile0 and are
+  // never chosen; trailing empties get a tile0 past the end
+  for (size_t i = nb; i-- > 0;) { if (sc.bds[i].n_rows == 0) sc.bds[i].tile0 = sc.n_tiles + 1; else break; }
+  sc.d_batches.reserve(nb * sizeof(BatchDesc)); sc.d_tiles.reserve((size_t)sc.n_tiles * sizeof(TileDesc)); sc.d_minmax.reserve(nb * sizeof(BatchMinMax));
+  sc.h_batches.reserve(nb * sizeof(BatchDesc)); sc.h_minmax.reserve(nb * sizeof(BatchMinMax)); sc.h_tiles.reserve((size_t)sc.n_tiles * sizeof(TileDesc));
+  memcpy(sc.h_batches.p, sc.bds.data(), nb * sizeof(BatchDesc));
+  if (sb.copies) CK(cudaStreamWaitEvent(stream, copy_done[sb.arena], 0));
+  CK(cudaMemcpyAsync(sc.d_batches.p, sc.h_batches.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
+  bool allow_fast = !(cfg.flags & DNZ_FLAG_FORCE_GENERIC);
+  CK(launch_tile_scan(sc.d_batches.as<BatchDesc>(), (int64_t)nb, sc.n_tiles, pane_ms, sc.d_tiles.as<TileDesc>(), sc.d_minmax.as<BatchMinMax>(), allow_fast, stream));
+  stats.total_launches += 2;
+  CK(cudaMemcpyAsync(sc.h_minmax.p, sc.d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(sc.h_tiles.p, sc.d_tiles.p, (size_t)sc.n_tiles * sizeof(TileDesc), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(sc.done, stream));
 }
 
 void dnz_window::process_superbatch(Superbatch& sb) {
   if (sb.batches.empty()) return;
   if (res_consumed) reset_results();
-  if (sb.copies) CK(cudaStreamWaitEvent(stream, copy_done[sb.arena], 0));
   struct Cleanup {
     dnz_window* w; Superbatch* sb;
     ~Cleanup() {
       if (sb->copies) cudaEventSynchronize(w->copy_done[sb->arena]);
       for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
       sb->batches.clear(); sb->rows = 0; sb->copies = false; w->in_arena[sb->arena].reset(); w->active = nullptr;
+      w->scan[sb->arena].launched = false;
     }
   } cleanup{this, &sb};
   active = &sb.batches;
-  std::vector<PendingBatch>& pending = sb.batches;
-  // chunks of <= max_rows rows (a single batch larger than that forms its own chunk)
-  size_t b0 = 0;
-  while (b0 < pending.size()) {
-    size_t b1 = b0; int64_t rows = 0;
-    while (b1 < pending.size() && (b1 == b0 || rows + pending[b1].d.n_rows <= max_rows)) { rows += pending[b1].d.n_rows; b1++; }
-    process_chunk(b0, b1);
-    b0 = b1;
-  }
+  if (!scan[sb.arena].launched) launch_scan(sb);
+  process_chunk(sb);
 }
 
 // Everything a steady-state pass needs is allocated when the operator is created (cudaMalloc / cudaMallocHost cost
 // milliseconds and must stay out of the per-batch path).
 void dnz_window::prealloc() {
-  const size_t nb_max = 16384 + (size_t)(max_rows / 4096), nt_max = (size_t)(max_rows / TILE) + nb_max;
-  d_batches.reserve(nb_max * sizeof(BatchDesc)); d_tiles.reserve(nt_max * sizeof(TileDesc)); d_minmax.reserve(nb_max * sizeof(BatchMinMax));
+  const size_t nb_max = 4096 + (size_t)(max_rows / 8192), nt_max = (size_t)(max_rows / TILE) + nb_max;
+  for (Scan& sc : scan) {
+    CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
+    sc.d_batches.reserve(nb_max * sizeof(BatchDesc)); sc.d_tiles.reserve(nt_max * sizeof(TileDesc)); sc.d_minmax.reserve(nb_max * sizeof(BatchMinMax));
+    sc.h_batches.reserve(nb_max * sizeof(BatchDesc)); sc.h_minmax.reserve(nb_max * sizeof(BatchMinMax)); sc.h_tiles.reserve(nt_max * sizeof(TileDesc));
+  }
   d_ptrs.reserve(6 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
-  h_stage.reserve(std::max(nb_max * sizeof(BatchDesc), (size_t)6 * 1024 * sizeof(void*)));
-  h_minmax.reserve(nb_max * sizeof(BatchMinMax)); h_tiles.reserve(nt_max * sizeof(TileDesc)); h_small.reserve(256);
+  h_stage.reserve((size_t)6 * 1024 * sizeof(void*)); h_small.reserve(256);
   for (int i = 0; i < panes_per_window + 2 && i < 8; i++) pane_pool.push_back(new_pane(0));
   ensure_result_capacity((uint64_t)gcap * (panes_per_window > 1 ? 2 : 4), (uint64_t)gcap * 16 * (panes_per_window > 1 ? 2 : 4));
 }
 
-void dnz_window::process_chunk(size_t b0, size_t b1) {
-  const size_t nb = b1 - b0;
-  // ---- batch descriptors + tile scan (RecordBatchWatermark per batch)
-  std::vector<BatchDesc> bds(nb);
-  int64_t n_tiles = 0;
-  for (size_t i = 0; i < nb; i++) { bds[i] = (*active)[b0 + i].d; bds[i].tile0 = n_tiles; n_tiles += (bds[i].n_rows + TILE - 1) / TILE; }
-  if (n_tiles == 0) return;                 // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
-  // empty batches own no tile; give them the tile0 of their successor so that the binary search never selects them
-  d_batches.reserve(nb * sizeof(BatchDesc)); d_tiles.reserve((size_t)n_tiles * sizeof(TileDesc)); d_minmax.reserve(nb * sizeof(BatchMinMax));
-  h_stage.reserve(nb * sizeof(BatchDesc));
-  // the scan picks the LAST batch with tile0 <= t, so empty batches (same tile0 as their successor) are never chosen
-  // unless they are at the end; move trailing empties' tile0 past the end.
-  for (size_t i = nb; i-- > 0;) { if (bds[i].n_rows == 0) bds[i].tile0 = n_tiles + 1; else break; }
-  memcpy(h_stage.p, bds.data(), nb * sizeof(BatchDesc));
-  CK(cudaMemcpyAsync(d_batches.p, h_stage.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
-  bool allow_fast = !(cfg.flags & DNZ_FLAG_FORCE_GENERIC);
-  CK(launch_tile_scan(d_batches.as<BatchDesc>(), (int64_t)nb, n_tiles, pane_ms, d_tiles.as<TileDesc>(), d_minmax.as<BatchMinMax>(), allow_fast, stream));
-  stats.total_launches += 2;
-  h_minmax.reserve(nb * sizeof(BatchMinMax)); h_tiles.reserve((size_t)n_tiles * sizeof(TileDesc));
-  CK(cudaMemcpyAsync(h_minmax.p, d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
-  CK(cudaMemcpyAsync(h_tiles.p, d_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyDeviceToHost, stream));
-  CK(cudaStreamSynchronize(stream));
-  std::vector<BatchMinMax> mm(h_minmax.as<BatchMinMax>(), h_minmax.as<BatchMinMax>() + nb);
-  std::vector<TileDesc> tiles(h_tiles.as<TileDesc>(), h_tiles.as<TileDesc>() + n_tiles);
+void dnz_window::process_chunk(Superbatch& sb) {
+  Scan& sc = scan[sb.arena];
+  cur_scan = &sc;
+  const size_t nb = sb.batches.size(); const size_t b0 = 0;
+  const int64_t n_tiles = sc.n_tiles;
+  if (n_tiles == 0) return;
+  CK(cudaEventSynchronize(sc.done));
+  const std::vector<BatchDesc>& bds = sc.bds;
+  std::vector<BatchMinMax> mm(sc.h_minmax.as<BatchMinMax>(), sc.h_minmax.as<BatchMinMax>() + nb);
+  std::vector<TileDesc> tiles(sc.h_tiles.as<TileDesc>(), sc.h_tiles.as<TileDesc>() + n_tiles);
 
   // ---- validation: inputs the reference panics on
   for (size_t i = 0; i < nb; i++) {
@@ -690,7 +705,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
       CK(cudaMemcpyAsync(d_ptrs.p, hp, 6 * pb, cudaMemcpyHostToDevice, stream));
       CK(cudaMemsetAsync(ctl(64), 0, 16, stream));
       AggParams P;
-      P.batches = d_batches.as<BatchDesc>(); P.tiles = d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
+      P.batches = cur_scan->d_batches.as<BatchDesc>(); P.tiles = cur_scan->d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
       P.dict = dict_view();
       P.flags = (cfg.flags & DNZ_FLAG_MINMAX_PRECHECK) ? AGG_MINMAX_PRECHECK : 0;
       char* dp = d_ptrs.as<char>();

@@ -63,7 +63,7 @@ typedef struct {
   uint32_t flags;
   double filter_literal;     /* literal already coerced to Float64 (lit(113) -> 113.0)              */
   int64_t expected_groups;   /* capacity hint (0 = default); tables grow on demand                  */
-  int64_t max_rows_per_launch; /* rows aggregated per kernel launch (0 = default 16 Mi)             */
+  int64_t max_rows_per_launch; /* rows aggregated per kernel launch (0 = default 64 Mi)             */
   void* cuda_stream;         /* optional caller-owned cudaStream_t for all work (NULL = own stream) */
 } dnz_window_config;
 
