@@ -284,10 +284,16 @@ def main():
                                     flags=flags | args.flags, expected_groups=G, max_rows_per_launch=args.max_rows_per_launch,
                                     cuda_stream=stream.cuda_stream)
 
+    GROUP = 1024       # batches (64 Mi rows) pushed between polls: emitted windows are consumed as the stream advances
+
     def step_device(w):
-        w.push_device(dev)
+        n_out = 0
+        for g0 in range(0, dev.n_batches, GROUP):
+            n = min(GROUP, dev.n_batches - g0)
+            w.push_device(array=C.cast(C.byref(dev.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
+            n_out += w.poll_device().n_rows
         w.flush(close_wm)
-        return w.poll_device()
+        return n_out + w.poll_device().n_rows
 
     def barrier():
         if world > 1:
@@ -300,7 +306,7 @@ def main():
     log(f"device input ready: {rows} rows, {dev.n_batches} batches, {dev.algorithmic_bytes / 1e9:.2f} GB algorithmic")
     out_rows = 0
     for _ in range(args.warmup):
-        w = new_window(); r = step_device(w); out_rows = r.n_rows; w.close()
+        w = new_window(); out_rows = step_device(w); w.close()
     wins = [new_window(d.capi.FLAG_KERNEL_TIMING) for _ in range(args.steps)]
     sampler = ClockSampler(local); sampler.start()
     barrier()
@@ -356,15 +362,18 @@ def main():
         def step_host(i):
             h = e_wins[i]._h
             arr = exported[i]
+            n_out = 0
             for k in range(len(hb)):
                 rc = push(h, C.byref(arr[k]))
                 if rc:
                     raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
-            rc = flush(h, e_close) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))
-            if rc:
-                raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
-            n_out = ca.length
-            rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
+                last = k == len(hb) - 1
+                if last or (k + 1) % GROUP == 0:      # consume emitted windows as the stream advances
+                    rc = (flush(h, e_close) if last else 0) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))
+                    if rc:
+                        raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
+                    n_out += ca.length
+                    rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
             return n_out
         log(f"e2e host batches ready: {e2e_rows} rows")
         for i in range(args.warmup):

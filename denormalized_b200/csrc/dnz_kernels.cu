@@ -427,6 +427,51 @@ cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long lon
   return cudaGetLastError();
 }
 
+// Host-pinned -> device gather copy.  CTAs claim 256 KiB pieces of the descriptor list dynamically; every thread keeps
+// eight 16 B loads from system memory in flight (PCIe reads need ~100 KB outstanding to reach line rate).
+__global__ void __launch_bounds__(256) k_gather_copy(const CopyDesc* __restrict__ descs, uint32_t n, unsigned int* cursor) {
+  constexpr uint64_t PIECE = COPY_PIECE;
+  __shared__ unsigned int s_desc; __shared__ unsigned long long s_skip;
+  const uint64_t total = descs[n - 1].first_piece + (descs[n - 1].bytes + PIECE - 1) / PIECE;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      unsigned int piece = atomicAdd(cursor, 1u);
+      uint32_t lo = 0, hi = n - 1;                       // last descriptor whose first_piece <= piece
+      if (piece >= total) lo = n;
+      else while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (descs[mid].first_piece <= piece) lo = mid; else hi = mid - 1; }
+      s_desc = lo; s_skip = lo < n ? piece - descs[lo].first_piece : 0;
+    }
+    __syncthreads();
+    const uint32_t d = s_desc; const uint64_t skip = s_skip;
+    __syncthreads();
+    if (d >= n) return;
+    const CopyDesc cd = descs[d];
+    uint64_t off = skip * PIECE, end = min(cd.bytes, off + PIECE);
+    const char* src = (const char*)cd.src; char* dst = (char*)cd.dst;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+      uint64_t nvec = (end - off) >> 4;
+      const int4* s4 = reinterpret_cast<const int4*>(src + off); int4* d4 = reinterpret_cast<int4*>(dst + off);
+      uint64_t i = threadIdx.x;
+      for (; i + 7 * 256 < nvec; i += 8 * 256) {
+        int4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldcs(s4 + i + k * 256);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d4[i + k * 256] = v[k];
+      }
+      for (; i < nvec; i += 256) d4[i] = __ldcs(s4 + i);
+      for (uint64_t b = off + (nvec << 4) + threadIdx.x; b < end; b += 256) dst[b] = src[b];
+    } else {
+      for (uint64_t b = off + threadIdx.x; b < end; b += 256) dst[b] = src[b];
+    }
+  }
+}
+cudaError_t launch_gather_copy(const CopyDesc* descs, uint32_t n, unsigned int* cursor, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_gather_copy<<<64, 256, 0, s>>>(descs, n, cursor);
+  return cudaGetLastError();
+}
+
 // re-insert every occupied slot of the old table into the (zeroed) new one; group ids are preserved
 __global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {

@@ -142,6 +142,12 @@ cudaError_t launch_pack_partials(const EmitParams& p, PartialEntry* entries, uin
 cudaError_t launch_merge_partials(const PartialEntry* entries, int64_t n, const uint8_t* key_bytes, DictView dict,
                                   PaneTable panes, int64_t window_ms, DeferList defer, cudaStream_t s);
 
+// Arrow<->device buffer manager: one launch pulls every pinned host buffer of a superbatch over PCIe with 128-bit loads
+// (hundreds of 0.5 MiB cudaMemcpyAsync calls reach only ~25 GB/s on this platform; see profiles/h2d_probe.py)
+struct CopyDesc { const void* src; void* dst; uint64_t bytes; uint64_t first_piece; };   // pieces of 256 KiB, prefix over the list
+constexpr uint64_t COPY_PIECE = 256 * 1024;
+cudaError_t launch_gather_copy(const CopyDesc* descs, uint32_t n, unsigned int* cursor, cudaStream_t s);
+
 // synthetic generator (dnz_synth.cu)
 cudaError_t launch_synth(int64_t row0, int64_t n_rows, int64_t batch_rows, uint64_t seed, int64_t groups,
                          int64_t rows_per_ms, int64_t t0_ms, int uuid_keys, int64_t key_mul, int64_t key_add, int64_t* ts, double* val, int32_t* off,

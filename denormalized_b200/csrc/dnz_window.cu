@@ -109,6 +109,7 @@ struct PendingBatch {
 // arena while the PREVIOUS superbatch is being aggregated, so PCIe transfers overlap kernels and host-side planning.
 struct Superbatch {
   std::vector<PendingBatch> batches; int64_t rows = 0; int arena = 0; bool copies = false;
+  std::vector<CopyDesc> gather;       // pinned host buffers pulled by one k_gather_copy launch when the superbatch is sealed
 };
 
 struct ResultSet {             // device columns of the rows emitted since the last poll
@@ -190,6 +191,8 @@ struct dnz_window {
   void prealloc();
   void process_chunk(Superbatch& sb);
   void launch_scan(Superbatch& sb);
+  void finish_copies(Superbatch& sb);
+  DevBuf d_copy_descs[2]; PinnedBuf h_copy_descs[2]; DevBuf d_copy_cursor;
   void execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0, size_t rb1,
                    bool dirty, int64_t horizon, int64_t wm_after);
   void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
@@ -461,10 +464,23 @@ void dnz_window::push_host(ArrowArray* batch) {
     const ArrowArray* meta = batch->children[meta_col];
     const ArrowArray* ts = meta->children[ts_child];
     if (key->length < po + n || val->length < po + n || ts->length < po + meta->offset + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
+    // page-locked sources (dnz_host_alloc / cudaHostRegister) are device-readable: queue them for the gather kernel;
+    // pageable sources go through cudaMemcpyAsync (staged by the driver)
+    auto enqueue_copy = [&](void* d, const void* src, size_t bytes) {
+      if (!bytes) return;
+      cudaPointerAttributes at{};
+      bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer;
+      if (!pinned) cudaGetLastError();
+      if (pinned && bytes >= 4096) {
+        uint64_t fp = cur.gather.empty() ? 0 : cur.gather.back().first_piece + (cur.gather.back().bytes + COPY_PIECE - 1) / COPY_PIECE;
+        cur.gather.push_back(CopyDesc{at.devicePointer, d, (uint64_t)bytes, fp});
+      }
+      else CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream));
+      stats.h2d_bytes += (int64_t)bytes;
+    };
     auto copy_in = [&](const void* src, size_t bytes) -> void* {
       void* d = arena_in.alloc(bytes);
-      CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream));
-      stats.h2d_bytes += (int64_t)bytes;
+      enqueue_copy(d, src, bytes);
       return d;
     };
     auto copy_bitmap = [&](const ArrowArray* a, int64_t eff_off, const uint8_t*& dptr, int32_t& vbit) {
@@ -493,7 +509,7 @@ void dnz_window::push_host(ArrowArray* batch) {
     pb.key_bytes = o1 - o0;
     const uint8_t* hb = (const uint8_t*)buf_at(key, 2);
     uint8_t* db = (uint8_t*)arena_in.alloc((size_t)(o1 - a0) + 16);
-    if (o1 > a0) { CK(cudaMemcpyAsync(db, hb + a0, (size_t)(o1 - a0), cudaMemcpyHostToDevice, copy_stream)); stats.h2d_bytes += o1 - a0; }
+    if (o1 > a0) enqueue_copy(db, hb + a0, (size_t)(o1 - a0));
     pb.d.bytes = db - a0;     // only [o0, o1) is ever dereferenced
     copy_bitmap(key, ko, pb.d.key_valid, pb.d.key_vbit);
     cur.copies = true;
@@ -523,8 +539,24 @@ void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
 // ------------------------------------------------------------------------------------------------
 // The current superbatch is full: aggregate the previously sealed one (its successor's copies are already in flight on the
 // copy stream, so they overlap this work), then seal the current one and start filling the other arena.
+// launch the gather copy of a superbatch's pinned sources and mark the point where all its bytes are on the device
+void dnz_window::finish_copies(Superbatch& sb) {
+  if (!sb.copies) return;
+  if (!sb.gather.empty()) {
+    size_t nbytes = sb.gather.size() * sizeof(CopyDesc);
+    h_copy_descs[sb.arena].reserve(nbytes); d_copy_descs[sb.arena].reserve(nbytes);
+    memcpy(h_copy_descs[sb.arena].p, sb.gather.data(), nbytes);
+    CK(cudaMemcpyAsync(d_copy_descs[sb.arena].p, h_copy_descs[sb.arena].p, nbytes, cudaMemcpyHostToDevice, copy_stream));
+    CK(cudaMemsetAsync(d_copy_cursor.p, 0, 4, copy_stream));
+    CK(launch_gather_copy(d_copy_descs[sb.arena].as<CopyDesc>(), (uint32_t)sb.gather.size(), d_copy_cursor.as<unsigned int>(), copy_stream));
+    stats.total_launches++;
+    sb.gather.clear();
+  }
+  CK(cudaEventRecord(copy_done[sb.arena], copy_stream));
+}
+
 void dnz_window::seal_current() {
-  if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+  finish_copies(cur);
   launch_scan(cur);                                   // tile scan of the new superbatch is queued before ...
   if (has_sealed) { process_superbatch(sealed); has_sealed = false; }   // ... the previous one is aggregated
   std::swap(sealed, cur); has_sealed = true;
@@ -534,7 +566,7 @@ void dnz_window::seal_current() {
 void dnz_window::process_pending() {
   if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
   if (!cur.batches.empty()) {
-    if (cur.copies) CK(cudaEventRecord(copy_done[cur.arena], copy_stream));
+    finish_copies(cur);
     launch_scan(cur);
     process_superbatch(cur);
   }
@@ -572,7 +604,7 @@ void dnz_window::process_superbatch(Superbatch& sb) {
     ~Cleanup() {
       if (sb->copies) cudaEventSynchronize(w->copy_done[sb->arena]);
       for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
-      sb->batches.clear(); sb->rows = 0; sb->copies = false; w->in_arena[sb->arena].reset(); w->active = nullptr;
+      sb->batches.clear(); sb->gather.clear(); sb->rows = 0; sb->copies = false; w->in_arena[sb->arena].reset(); w->active = nullptr;
       w->scan[sb->arena].launched = false;
     }
   } cleanup{this, &sb};
@@ -590,6 +622,8 @@ void dnz_window::prealloc() {
     sc.d_batches.reserve(nb_max * sizeof(BatchDesc)); sc.d_tiles.reserve(nt_max * sizeof(TileDesc)); sc.d_minmax.reserve(nb_max * sizeof(BatchMinMax));
     sc.h_batches.reserve(nb_max * sizeof(BatchDesc)); sc.h_minmax.reserve(nb_max * sizeof(BatchMinMax)); sc.h_tiles.reserve(nt_max * sizeof(TileDesc));
   }
+  d_copy_cursor.alloc(64);
+  for (int i = 0; i < 2; i++) { d_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); h_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); }
   d_ptrs.reserve(6 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
   h_stage.reserve((size_t)6 * 1024 * sizeof(void*)); h_small.reserve(256);
   for (int i = 0; i < panes_per_window + 2 && i < 8; i++) pane_pool.push_back(new_pane(0));
