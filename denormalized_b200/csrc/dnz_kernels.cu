@@ -19,7 +19,7 @@ namespace dnz {
 // =================================================================================================
 __global__ void k_init_minmax(BatchMinMax* mm, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].pad = 0; }
+  if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].key_bytes = 0; mm[i].n_fast = 0; mm[i].n_tiles = 0; }
 }
 
 // one warp per tile, 8 tiles per CTA; aligned tiles are read with 128-bit loads, 16 in flight per lane
@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
         td.byte_len <= BCAP && cnt > 0)
       td.flags |= TILE_FAST;
     tiles[t] = td;
+    atomicAdd((unsigned long long*)&mm[lo].key_bytes, (unsigned long long)td.byte_len);
+    atomicAdd((unsigned long long*)&mm[lo].n_tiles, 1ull);
+    if (td.flags & TILE_FAST) atomicAdd((unsigned long long*)&mm[lo].n_fast, 1ull);
   }
 }
 

@@ -40,7 +40,7 @@ struct TileDesc {
   int64_t pane_lo;      // floor(ts_min / pane_ms)
 };
 
-struct BatchMinMax { int64_t ts_min, ts_max, n_valid; int64_t pad; };
+struct BatchMinMax { int64_t ts_min, ts_max, n_valid, key_bytes, n_fast, n_tiles; };   // per RecordBatch, filled by k_tile_scan
 
 // ------------------------------------------------------------------------------------------------
 // Key dictionary: open addressing, one 32 B sector per slot, keys <= 24 B inline.

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +43,21 @@ struct DnzError {
   } while (0)
 
 thread_local std::string g_last_error;
+
+// DNZ_TRACE=1: host-side phase timings per superbatch on stderr (debugging aid)
+const bool g_trace = getenv("DNZ_TRACE") != nullptr;
+struct Trace {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  std::string line;
+  void mark(const char* what) {
+    if (!g_trace) return;
+    auto t1 = std::chrono::steady_clock::now();
+    char buf[64]; snprintf(buf, sizeof buf, " %s=%.3fms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    line += buf; t0 = t1;
+  }
+  void flush(const char* tag) { if (g_trace) fprintf(stderr, "[dnz] %s:%s\n", tag, line.c_str()); line.clear(); }
+};
+Trace g_tr;
 
 inline int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -193,7 +209,7 @@ struct dnz_window {
   void launch_scan(Superbatch& sb);
   void finish_copies(Superbatch& sb);
   DevBuf d_copy_descs[2]; PinnedBuf h_copy_descs[2]; DevBuf d_copy_cursor;
-  void execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0, size_t rb1,
+  void execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0, size_t rb0, size_t rb1,
                    bool dirty, int64_t horizon, int64_t wm_after);
   void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
   void emit_normal(int64_t wm_new);
@@ -584,7 +600,7 @@ void dnz_window::launch_scan(Superbatch& sb) {
   // never chosen; trailing empties get a tile0 past the end
   for (size_t i = nb; i-- > 0;) { if (sc.bds[i].n_rows == 0) sc.bds[i].tile0 = sc.n_tiles + 1; else break; }
   sc.d_batches.reserve(nb * sizeof(BatchDesc)); sc.d_tiles.reserve((size_t)sc.n_tiles * sizeof(TileDesc)); sc.d_minmax.reserve(nb * sizeof(BatchMinMax));
-  sc.h_batches.reserve(nb * sizeof(BatchDesc)); sc.h_minmax.reserve(nb * sizeof(BatchMinMax)); sc.h_tiles.reserve((size_t)sc.n_tiles * sizeof(TileDesc));
+  sc.h_batches.reserve(nb * sizeof(BatchDesc)); sc.h_minmax.reserve(nb * sizeof(BatchMinMax));
   memcpy(sc.h_batches.p, sc.bds.data(), nb * sizeof(BatchDesc));
   if (sb.copies) CK(cudaStreamWaitEvent(stream, copy_done[sb.arena], 0));
   CK(cudaMemcpyAsync(sc.d_batches.p, sc.h_batches.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
@@ -592,7 +608,6 @@ void dnz_window::launch_scan(Superbatch& sb) {
   CK(launch_tile_scan(sc.d_batches.as<BatchDesc>(), (int64_t)nb, sc.n_tiles, pane_ms, sc.d_tiles.as<TileDesc>(), sc.d_minmax.as<BatchMinMax>(), allow_fast, stream));
   stats.total_launches += 2;
   CK(cudaMemcpyAsync(sc.h_minmax.p, sc.d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
-  CK(cudaMemcpyAsync(sc.h_tiles.p, sc.d_tiles.p, (size_t)sc.n_tiles * sizeof(TileDesc), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventRecord(sc.done, stream));
 }
 
@@ -620,7 +635,7 @@ void dnz_window::prealloc() {
   for (Scan& sc : scan) {
     CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
     sc.d_batches.reserve(nb_max * sizeof(BatchDesc)); sc.d_tiles.reserve(nt_max * sizeof(TileDesc)); sc.d_minmax.reserve(nb_max * sizeof(BatchMinMax));
-    sc.h_batches.reserve(nb_max * sizeof(BatchDesc)); sc.h_minmax.reserve(nb_max * sizeof(BatchMinMax)); sc.h_tiles.reserve(nt_max * sizeof(TileDesc));
+    sc.h_batches.reserve(nb_max * sizeof(BatchDesc)); sc.h_minmax.reserve(nb_max * sizeof(BatchMinMax));
   }
   d_copy_cursor.alloc(64);
   for (int i = 0; i < 2; i++) { d_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); h_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); }
@@ -636,10 +651,11 @@ void dnz_window::process_chunk(Superbatch& sb) {
   const size_t nb = sb.batches.size(); const size_t b0 = 0;
   const int64_t n_tiles = sc.n_tiles;
   if (n_tiles == 0) return;
+  g_tr.mark("pre");
   CK(cudaEventSynchronize(sc.done));
+  g_tr.mark("scan_wait");
   const std::vector<BatchDesc>& bds = sc.bds;
   std::vector<BatchMinMax> mm(sc.h_minmax.as<BatchMinMax>(), sc.h_minmax.as<BatchMinMax>() + nb);
-  std::vector<TileDesc> tiles(sc.h_tiles.as<TileDesc>(), sc.h_tiles.as<TileDesc>() + n_tiles);
 
   // ---- validation: inputs the reference panics on
   for (size_t i = 0; i < nb; i++) {
@@ -659,8 +675,8 @@ void dnz_window::process_chunk(Superbatch& sb) {
     bool dirty = cur_has_wm && first_pane_end <= cur_wm;
     int64_t new_wm = (!cur_has_wm || cur_wm <= mn) ? mn : cur_wm;     // process_watermark (:255-266)
     if (dirty) {
-      if (run_start != nb) { execute_run(mm, tiles, b0, run_start, i, false, 0, run_wm_after); run_start = nb; }
-      execute_run(mm, tiles, b0, i, i + 1, true, cur_wm, new_wm);
+      if (run_start != nb) { execute_run(mm, b0, run_start, i, false, 0, run_wm_after); run_start = nb; }
+      execute_run(mm, b0, i, i + 1, true, cur_wm, new_wm);
       stats.late_batches++;
     } else {
       if (run_start == nb) run_start = i;
@@ -668,11 +684,12 @@ void dnz_window::process_chunk(Superbatch& sb) {
     }
     cur_has_wm = true; cur_wm = new_wm;
   }
-  if (run_start != nb) execute_run(mm, tiles, b0, run_start, nb, false, 0, run_wm_after);
+  if (run_start != nb) execute_run(mm, b0, run_start, nb, false, 0, run_wm_after);
+  g_tr.flush("superbatch");
 }
 
 // Aggregates batches [rb0, rb1) of the chunk (indices relative to the chunk) and triggers.
-void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vector<TileDesc>& tiles, size_t chunk_b0, size_t rb0,
+void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0, size_t rb0,
                              size_t rb1, bool dirty, int64_t horizon, int64_t wm_after) {
   // tile range of the run
   int64_t t0 = -1, t1 = -1; int64_t rows = 0; double alg_bytes = 0;
@@ -686,14 +703,16 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
     t1 = acc;
   }
   if (t1 <= t0) { return; }
-  // ---- panes touched by the run
+  // ---- panes touched by the run (from the per-batch timestamp ranges of the tile scan)
   int64_t pmin = INT64_MAX, pmax = INT64_MIN; int64_t fast = 0, generic = 0;
-  for (int64_t t = t0; t < t1; t++) {
-    const TileDesc& td = tiles[t];
-    rows += td.n_rows; alg_bytes += 20.0 * td.n_rows + td.byte_len;
-    if (td.flags & TILE_EMPTY) continue;
-    if (td.flags & TILE_FAST) fast++; else generic++;
-    pmin = std::min(pmin, td.pane_lo); pmax = std::max(pmax, floor_div(td.ts_max, pane_ms));
+  for (size_t i = rb0; i < rb1; i++) {
+    const BatchMinMax& b = mm[i];
+    const int64_t nr = (*active)[chunk_b0 + i].d.n_rows;
+    if (nr == 0) continue;
+    rows += nr; alg_bytes += 20.0 * nr + (double)b.key_bytes;
+    fast += b.n_fast; generic += b.n_tiles - b.n_fast;
+    if (b.n_valid == 0) continue;
+    pmin = std::min(pmin, floor_div(b.ts_min, pane_ms)); pmax = std::max(pmax, floor_div(b.ts_max, pane_ms));
   }
   stats.fast_tiles += fast; stats.generic_tiles += generic;
   std::map<int64_t, std::unique_ptr<Pane>> late_panes;
@@ -704,10 +723,10 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
     for (size_t i = rb0; i < rb1; i++) if ((*active)[chunk_b0 + i].d.val_valid) val_nulls = true;
     if (val_nulls && !need_nullrows) { need_nullrows = true; for (auto& kv : panes) ensure_side_arrays(kv.second.get()); }
     std::vector<uint8_t> touched((size_t)np, 0);
-    for (int64_t t = t0; t < t1; t++) {
-      const TileDesc& td = tiles[t];
-      if (td.flags & TILE_EMPTY) continue;
-      for (int64_t p = td.pane_lo; p <= floor_div(td.ts_max, pane_ms); p++) touched[(size_t)(p - pmin)] = 1;
+    for (size_t i = rb0; i < rb1; i++) {
+      const BatchMinMax& b = mm[i];
+      if ((*active)[chunk_b0 + i].d.n_rows == 0 || b.n_valid == 0) continue;
+      for (int64_t p = floor_div(b.ts_min, pane_ms); p <= floor_div(b.ts_max, pane_ms); p++) touched[(size_t)(p - pmin)] = 1;
     }
     for (int64_t p = pmin; p <= pmax; p++) {
       if (!touched[(size_t)(p - pmin)]) continue;
@@ -716,6 +735,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
       if (need_main) get_pane(p, true);
       if (need_late) late_panes[p] = new_pane(p);
     }
+    g_tr.mark("panes");
     // ---- aggregate, replaying deferred rows until every table is large enough
     const size_t defer_cap = (size_t)std::max<int64_t>(rows, 1);
     d_defer[0].reserve(defer_cap * sizeof(DeferEntry));
@@ -763,7 +783,9 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
         CK(launch_deferred(P, d_defer[in_list].as<DeferEntry>(), n_in, stream));   // replays the rows of the previous pass
         stats.total_launches++;
       }
+      g_tr.mark("agg_launch");
       fetch_ctl();
+      g_tr.mark("agg_wait");
       if (timing) {
         float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += alg_bytes;
@@ -785,6 +807,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
       in_list = out_list; n_in = cnt;
     }
   }
+  g_tr.mark("post_agg");
   // ---- process_watermark + trigger_windows
   if (dirty) {
     // windows that were already emitted (end <= horizon) and received rows from this batch are re-opened and emitted
@@ -803,6 +826,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, const std::vect
     late_panes.clear();
   }
   emit_normal(wm_after);
+  g_tr.mark("emit");
 }
 
 void dnz_window::emit_normal(int64_t wm_new) {
