@@ -63,7 +63,44 @@ inline int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % 
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
-// device memory helpers
+// device memory helpers.  All device buffers come from the CUDA stream-ordered allocator with an unbounded release
+// threshold: blocks freed by one operator stay cached in the process and are handed to the next one without a driver
+// call (plain cudaMalloc/cudaFree cost milliseconds to seconds once tens of GB are mapped, and cudaFree synchronises
+// the whole device).
+struct AllocCtx { cudaStream_t s = nullptr; bool async_ok = false; };
+AllocCtx& alloc_ctx() {
+  static thread_local int cached_dev = -1; static thread_local AllocCtx* cur = nullptr;
+  static std::mutex m; static std::map<int, AllocCtx> ctxs;
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev == cached_dev && cur) return *cur;
+  std::lock_guard<std::mutex> g(m);
+  AllocCtx& c = ctxs[dev];
+  if (!c.s) {
+    int supported = 0; cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) c.s = nullptr;
+    cudaMemPool_t pool;
+    if (supported && c.s && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      c.async_ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess;
+    }
+    cudaGetLastError();
+  }
+  cached_dev = dev; cur = &c;
+  return c;
+}
+void* dev_alloc(size_t n) {
+  AllocCtx& c = alloc_ctx();
+  void* p = nullptr;
+  if (c.async_ok) { CK(cudaMallocAsync(&p, n, c.s)); CK(cudaStreamSynchronize(c.s)); }
+  else CK(cudaMalloc(&p, n));
+  return p;
+}
+void dev_free(void* p) {          // callers free only after the work that used the block has completed
+  if (!p) return;
+  AllocCtx& c = alloc_ctx();
+  if (c.async_ok) cudaFreeAsync(p, c.s); else cudaFree(p);
+}
+
 struct DevBuf {
   void* p = nullptr; size_t bytes = 0;
   DevBuf() = default;
@@ -71,8 +108,8 @@ struct DevBuf {
   DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-  void alloc(size_t n) { release(); if (n == 0) n = 256; CK(cudaMalloc(&p, n)); bytes = n; }
+  void release() { if (p) dev_free(p); p = nullptr; bytes = 0; }
+  void alloc(size_t n) { release(); if (n == 0) n = 256; p = dev_alloc(n); bytes = n; }
   // grow without preserving contents
   void reserve(size_t n) { if (n > bytes) alloc(std::max(n, bytes + bytes / 2)); }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -455,7 +492,7 @@ Pane* dnz_window::get_pane(int64_t id, bool create) {
 void dnz_window::retire_panes() {
   if (!has_wm) return;
   for (auto it = panes.begin(); it != panes.end();) {
-    if (it->first * pane_ms + L <= wm) { if (pane_pool.size() < 8) pane_pool.push_back(std::move(it->second)); it = panes.erase(it); }
+    if (it->first * pane_ms + L <= wm) { if (pane_pool.size() < 16) pane_pool.push_back(std::move(it->second)); it = panes.erase(it); }
     else ++it;
   }
 }
@@ -641,8 +678,8 @@ void dnz_window::prealloc() {
   for (int i = 0; i < 2; i++) { d_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); h_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); }
   d_ptrs.reserve(6 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
   h_stage.reserve((size_t)6 * 1024 * sizeof(void*)); h_small.reserve(256);
-  for (int i = 0; i < panes_per_window + 2 && i < 8; i++) pane_pool.push_back(new_pane(0));
-  ensure_result_capacity((uint64_t)gcap * (panes_per_window > 1 ? 2 : 4), (uint64_t)gcap * 16 * (panes_per_window > 1 ? 2 : 4));
+  for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
+  ensure_result_capacity((uint64_t)gcap * 8, (uint64_t)gcap * 16 * 8);
 }
 
 void dnz_window::process_chunk(Superbatch& sb) {
@@ -822,7 +859,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
     for (auto& kv : late_panes) src[kv.first] = kv.second.get();
     emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src);
     CK(cudaStreamSynchronize(stream));
-    for (auto& kv : late_panes) if (pane_pool.size() < 8) pane_pool.push_back(std::move(kv.second));
+    for (auto& kv : late_panes) if (pane_pool.size() < 16) pane_pool.push_back(std::move(kv.second));
     late_panes.clear();
   }
   emit_normal(wm_after);
