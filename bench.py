@@ -347,7 +347,9 @@ def main():
             free_gb = psutil.virtual_memory().available / 2**30
         except Exception:
             pass
-        e2e_rows = args.e2e_rows or int(min(rows, 268_435_456, max(BATCH_ROWS, (free_gb / 4 / world) * 2**30 / 40)))
+        # the whole stream when the host has the memory for it (40 B/row pinned), else its first 256 Mi rows
+        cap = rows if free_gb / world > 6 * rows * 40 / 2**30 else 268_435_456
+        e2e_rows = args.e2e_rows or int(min(rows, cap, max(BATCH_ROWS, (free_gb / 4 / world) * 2**30 / 40)))
         e2e_rows = max(BATCH_ROWS, e2e_rows // BATCH_ROWS * BATCH_ROWS)
         hb, in_bytes, base = pinned_host_batches(d, wl, e2e_rows, rank, world)
         e_last = T0 + (e2e_rows - 1) // wl["rows_per_ms"]
@@ -356,7 +358,7 @@ def main():
         exported = [export_all(d, hb) for _ in range(n_e2e_steps)]
         e_wins = [new_window() for _ in range(n_e2e_steps)]
         ca, cs, has = d.capi.ArrowArrayC(), d.capi.ArrowSchemaC(), C.c_int32(0)
-        push, poll, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_flush
+        push, poll, poll_ready, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_poll_ready, L.dnz_window_flush
         rel = C.CFUNCTYPE(None, C.c_void_p)
 
         def step_host(i):
@@ -369,7 +371,10 @@ def main():
                     raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
                 last = k == len(hb) - 1
                 if last or (k + 1) % GROUP == 0:      # consume emitted windows as the stream advances
-                    rc = (flush(h, e_close) if last else 0) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))
+                    if last:
+                        rc = flush(h, e_close) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))
+                    else:       # hand over what has been emitted so far; queued batches keep streaming
+                        rc = poll_ready(h, C.byref(ca), C.byref(cs), C.byref(has))
                     if rc:
                         raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
                     n_out += ca.length

@@ -81,7 +81,8 @@ class StatsC(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_device",
+EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_ready",
+           "dnz_window_poll_device",
            "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
            "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
@@ -110,6 +111,8 @@ def lib():
         L.dnz_window_push_device.argtypes = [C.c_void_p, C.POINTER(DeviceBatchC), C.c_int64]
         L.dnz_window_poll.restype = C.c_int32
         L.dnz_window_poll.argtypes = [C.c_void_p, C.POINTER(ArrowArrayC), C.POINTER(ArrowSchemaC), C.POINTER(C.c_int32)]
+        L.dnz_window_poll_ready.restype = C.c_int32
+        L.dnz_window_poll_ready.argtypes = [C.c_void_p, C.POINTER(ArrowArrayC), C.POINTER(ArrowSchemaC), C.POINTER(C.c_int32)]
         L.dnz_window_poll_device.restype = C.c_int32
         L.dnz_window_poll_device.argtypes = [C.c_void_p, C.POINTER(DeviceResultC)]
         L.dnz_window_flush.restype = C.c_int32
@@ -251,6 +254,11 @@ class GpuStreamingWindow:
     def poll(self) -> pa.RecordBatch:
         ca, cs, has = ArrowArrayC(), ArrowSchemaC(), C.c_int32(0)
         self._check(self._L.dnz_window_poll(self._h, C.byref(ca), C.byref(cs), C.byref(has)))
+        return pa.RecordBatch._import_from_c(C.addressof(ca), C.addressof(cs))
+
+    def poll_ready(self) -> pa.RecordBatch:
+        ca, cs, has = ArrowArrayC(), ArrowSchemaC(), C.c_int32(0)
+        self._check(self._L.dnz_window_poll_ready(self._h, C.byref(ca), C.byref(cs), C.byref(has)))
         return pa.RecordBatch._import_from_c(C.addressof(ca), C.addressof(cs))
 
     def poll_device(self) -> DeviceResultC:

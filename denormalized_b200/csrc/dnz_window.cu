@@ -609,9 +609,9 @@ void dnz_window::finish_copies(Superbatch& sb) {
 }
 
 void dnz_window::seal_current() {
-  finish_copies(cur);
-  launch_scan(cur);                                   // tile scan of the new superbatch is queued before ...
-  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }   // ... the previous one is aggregated
+  finish_copies(cur);                                 // this superbatch's host->device transfer starts now ...
+  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }   // ... and overlaps the aggregation of the previous one
+  launch_scan(cur);                                   // queued behind that aggregation; waits for the transfer on the device
   std::swap(sealed, cur); has_sealed = true;
   cur.batches.clear(); cur.rows = 0; cur.copies = false; cur.arena = sealed.arena ^ 1;
 }
@@ -1092,6 +1092,14 @@ int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchem
   DNZ_TRY(w)
   if (!out) fail(DNZ_ERR_INVALID, "null out");
   w->process_pending();
+  if (w->res_consumed) w->reset_results();
+  w->export_arrow(out, out_schema, has_output);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_poll_ready(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output) {
+  DNZ_TRY(w)
+  if (!out) fail(DNZ_ERR_INVALID, "null out");
   if (w->res_consumed) w->reset_results();
   w->export_arrow(out, out_schema, has_output);
   DNZ_CATCH(w)

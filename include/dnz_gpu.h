@@ -129,6 +129,11 @@ int32_t dnz_window_push_device(dnz_window* w, const dnz_device_batch* batches, i
  * empty batch when nothing closed (the reference returns an empty batch, :343-348). */
 int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output);
 
+/* Non-forcing variant: returns the rows emitted so far WITHOUT aggregating batches that are still queued or in flight
+ * (what a poll_next would hand downstream while upstream keeps producing).  Keeps host->device transfers, kernels and
+ * result hand-off overlapped; rows of queued batches appear at a later poll. */
+int32_t dnz_window_poll_ready(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output);
+
 /* As dnz_window_poll but leaves the emitted rows on the device. */
 int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out);
 
