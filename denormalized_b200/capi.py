@@ -266,8 +266,8 @@ class GpuStreamingWindow:
         self._check(self._L.dnz_window_poll_device(self._h, C.byref(r)))
         return r
 
-    def fetch_device_result(self, r: DeviceResultC) -> pa.RecordBatch | None:
-        """Copy a device-resident result to host arrays (test helper)."""
+    def fetch_device_result(self, r: DeviceResultC, max_keys=None) -> dict:
+        """Copy a device-resident result to host arrays (test helper); keys are materialised for the first max_keys rows."""
         n = r.n_rows
 
         def get(ptr, dt, m):
@@ -281,7 +281,8 @@ class GpuStreamingWindow:
         kb = get(r.key_bytes, np.uint8, r.key_bytes_len).tobytes()
         kv = get(r.key_valid, np.uint8, n)
         av = get(r.agg_valid, np.uint8, n)
-        return {"key": [kb[off[i]:off[i + 1]] if kv[i] else None for i in range(n)],
+        nk = n if max_keys is None else min(n, max_keys)
+        return {"key": [kb[off[i]:off[i + 1]] if kv[i] else None for i in range(nk)], "key_off": off,
                 "count": get(r.count, np.int64, n), "min": get(r.min, np.float64, n), "max": get(r.max, np.float64, n),
                 "avg": get(r.avg, np.float64, n), "sum": get(r.sum, np.float64, n), "agg_valid": av,
                 "window_start": get(r.window_start_ms, np.int64, n), "window_end": get(r.window_end_ms, np.int64, n)}

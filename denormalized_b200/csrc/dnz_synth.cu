@@ -1,6 +1,6 @@
 // dnz_synth.cu -- counter-based synthetic sensor stream generated directly in device memory
 // (value distribution of examples/examples/emit_measurements.rs:30-33,45).  Bit-identical to the
-// host generator orc_synth_fill in oracle/dnz_oracle.c; bench/test infrastructure, not part of the hot path.
+// the host generator used by the tests (orc_synth_fill); bench/test infrastructure, not part of the hot path.
 #include "dnz_kernels.h"
 
 namespace dnz {

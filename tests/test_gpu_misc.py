@@ -1,0 +1,68 @@
+"""GPU: the C++ mirror of the reference API, and size-independent properties at BASELINE.json's full cfg-2 size."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.helpers import assert_rows_equal, rows_to_batch, run_oracle_batches
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T0 = 1_700_000_000_000
+
+
+@pytest.mark.parametrize("L,S,filt", [(1000, 0, None), (3000, 1000, 113.0)])
+def test_cpp_mirror_simple_aggregation(L, S, filt):
+    """denormalized_b200/cpp/simple_aggregation (DataStream::window().filter() -> StreamingWindowExec::execute ->
+    poll_next per batch, as examples/simple_aggregation.rs) against the oracle on the same synthetic batches."""
+    from oracle import synth_batch
+    exe = os.path.join(ROOT, "denormalized_b200", "cpp", "simple_aggregation")
+    nb, n, G, rpm = 12, 4096, 200, 4
+    args = [exe, str(nb), str(n), str(G), str(rpm), str(L), str(S)] + ([str(filt)] if filt else [])
+    out = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = []
+    for line in out.stdout.splitlines():
+        ws, we, key, cnt, mn, mx, av = line.split(",")
+        got.append((int(ws), int(we), key.encode(), int(cnt), float.fromhex(mn), float.fromhex(mx), float.fromhex(av), 0))
+    batches = [synth_batch(b * n, n, groups=G, rows_per_ms=rpm) for b in range(nb)]
+    batches.append(synth_batch(nb * n + 100 * (L + 1000) * rpm, 1, groups=G, rows_per_ms=rpm))
+    want = run_oracle_batches(batches, L, S, ("max", ">", filt) if filt else None)
+    assert len(want) > 100
+    assert_rows_equal(got, want)
+
+
+def test_full_size_cfg2_properties():
+    """1e9 rows, 100K groups, 64Ki-row batches, tumbling 1 s (BASELINE.json configs[1]) on one B200: the oracle cannot run
+    this size in seconds, so check properties that do not depend on it: every row is counted exactly once, every window
+    holds every group, per-window counts add up to the rows of that second, min <= avg <= max within [0,115), and the
+    filtered run keeps exactly the rows whose max exceeds the literal."""
+    from denormalized_b200 import DeviceBatches
+    from tests.helpers import gpu_window
+    n, G, rpm = 1_000_000_000, 100_000, 10_000
+    dev = DeviceBatches(n, 65536, groups=G, rows_per_ms=rpm)
+    close = T0 + n // rpm + 3000
+    totals = {}
+    for filt in (None, ("max", ">", 113)):
+        w = gpu_window(1000, 0, filt, expected_groups=G)
+        w.push_device(dev)
+        w.flush(close)
+        r = w.fetch_device_result(w.poll_device(), max_keys=G)
+        cnt, mn, mx, av, ws = r["count"], r["min"], r["max"], r["avg"], r["window_start"]
+        assert r["agg_valid"].all()
+        assert np.all(mn >= 0.0) and np.all(mx < 115.0) and np.all(mn <= av) and np.all(av <= mx)
+        if filt is None:
+            assert len(cnt) == 100 * G                      # 100 windows x every group (100 rows per group and window on average)
+            assert int(cnt.sum()) == n
+            per_window = np.bincount(((ws - T0) // 1000).astype(np.int64), weights=cnt.astype(np.float64))
+            assert np.all(per_window == rpm * 1000)
+            assert len(set(r["key"][:G])) == G
+            totals["all_max_gt"] = int((mx > 113.0).sum())
+            totals["sum_check"] = float(np.sum(r["sum"]))
+            assert abs(float(np.sum(av * cnt)) - totals["sum_check"]) <= 1e-9 * totals["sum_check"]
+        else:
+            assert np.all(mx > 113.0) and len(cnt) == totals["all_max_gt"]
+            assert 0.80 < len(cnt) / (100 * G) < 0.85     # P(pass) = 1 - (113/115)^100 = 0.826
+        w.close()
+    dev.free()
