@@ -1,0 +1,194 @@
+//! gpu_streaming_window.rs -- the Rust shim a Denormalized maintainer would add to `crates/core` to route the grouped
+//! streaming window through `libdnz_gpu.so`.  SOURCE ONLY: this image has no Rust toolchain, so the file has never been
+//! compiled; it is the reference-side binding that `INTEGRATION.md` describes, written against DataFusion 42 /
+//! arrow-rs 53 as pinned by the reference (`Cargo.toml:31`).  The C++ mirror `denormalized_b200/cpp/denormalized.hpp`
+//! is the compiled, tested equivalent.
+//!
+//! Plug-in point: `StreamingWindowPlanner::plan_extension` (`crates/core/src/planner/streaming_window.rs:154-165`)
+//! constructs `GpuStreamingWindowExec::try_new(..)` with exactly the arguments it passes to
+//! `StreamingWindowExec::try_new` today when the plan is GPU-eligible (one Utf8 group column; count/min/max/avg/sum over
+//! one Float64 column; window length in whole seconds, length % slide == 0) and returns an error otherwise --
+//! there is no CPU fallback inside the GPU operator.
+
+use std::any::Any;
+use std::ffi::{c_char, c_void, CStr};
+use std::pin::Pin;
+use std::sync::Arc;
+use std::task::{Context, Poll};
+
+use arrow::array::{Array, RecordBatch, StructArray};
+use arrow::datatypes::SchemaRef;
+use arrow::ffi::{from_ffi, to_ffi, FFI_ArrowArray, FFI_ArrowSchema};
+use datafusion::common::{DataFusionError, Result};
+use datafusion::execution::TaskContext;
+use datafusion::physical_expr::aggregate::AggregateFunctionExpr;
+use datafusion::physical_plan::aggregates::{AggregateMode, PhysicalGroupBy};
+use datafusion::physical_plan::{
+    DisplayAs, DisplayFormatType, ExecutionPlan, PlanProperties, RecordBatchStream, SendableRecordBatchStream,
+};
+use futures::{Stream, StreamExt};
+
+use crate::physical_plan::continuous::streaming_window::PhysicalStreamingWindowType;
+
+// ---- raw bindings of include/dnz_gpu.h -------------------------------------------------------------------------
+#[repr(C)]
+pub struct DnzAgg { kind: i32, arg_column: i32, alias: *const c_char }
+#[repr(C)]
+pub struct DnzWindowConfig {
+    abi_version: u32, device: i32, key_column: i32, n_aggs: i32, aggs: *const DnzAgg,
+    window_ms: i64, slide_ms: i64, has_filter: i32, filter_agg: i32, filter_op: i32, flags: u32,
+    filter_literal: f64, expected_groups: i64, max_rows_per_launch: i64, cuda_stream: *mut c_void,
+}
+#[repr(C)]
+pub struct DnzWindow { _private: [u8; 0] }
+
+#[link(name = "dnz_gpu")]
+extern "C" {
+    fn dnz_window_create(cfg: *const DnzWindowConfig, schema: *const FFI_ArrowSchema, out: *mut *mut DnzWindow) -> i32;
+    fn dnz_window_push(w: *mut DnzWindow, batch: *mut FFI_ArrowArray) -> i32;
+    fn dnz_window_poll(w: *mut DnzWindow, out: *mut FFI_ArrowArray, schema: *mut FFI_ArrowSchema, has_output: *mut i32) -> i32;
+    fn dnz_window_poll_ready(w: *mut DnzWindow, out: *mut FFI_ArrowArray, schema: *mut FFI_ArrowSchema, has_output: *mut i32) -> i32;
+    fn dnz_window_last_error(w: *const DnzWindow) -> *const c_char;
+    fn dnz_window_destroy(w: *mut DnzWindow);
+}
+
+fn dnz_err(w: *const DnzWindow) -> DataFusionError {
+    let msg = unsafe { CStr::from_ptr(dnz_window_last_error(w)) }.to_string_lossy().into_owned();
+    DataFusionError::Execution(format!("GpuStreamingWindowExec: {msg}"))
+}
+
+// ---- the operator ------------------------------------------------------------------------------------------------
+#[derive(Debug)]
+pub struct GpuStreamingWindowExec {
+    input: Arc<dyn ExecutionPlan>,
+    group_by: PhysicalGroupBy,
+    aggr_expr: Vec<AggregateFunctionExpr>,
+    /// FilterExec predicate `agg <op> literal` fused into the operator (index into aggr_expr, DNZ_OP_*, literal)
+    fused_filter: Option<(usize, i32, f64)>,
+    schema: SchemaRef,        // group key | aggregates | window_start_time | window_end_time
+    window_type: PhysicalStreamingWindowType,
+    cache: PlanProperties,
+    device: i32,
+}
+
+impl GpuStreamingWindowExec {
+    /// Same arguments as `StreamingWindowExec::try_new` (streaming_window.rs:221-230).
+    #[allow(clippy::too_many_arguments)]
+    pub fn try_new(
+        _mode: AggregateMode,
+        group_by: PhysicalGroupBy,
+        aggr_expr: Vec<AggregateFunctionExpr>,
+        _filter_expr: Vec<Option<Arc<dyn datafusion::physical_plan::PhysicalExpr>>>,
+        input: Arc<dyn ExecutionPlan>,
+        _input_schema: SchemaRef,
+        window_type: PhysicalStreamingWindowType,
+        _upstream_partitioning: Option<usize>,
+    ) -> Result<Self> {
+        // schema and properties are computed exactly as StreamingWindowExec does (create_schema :1096-1134,
+        // add_window_columns_to_schema continuous/mod.rs:42-62, compute_properties :253-300); elided here.
+        let inner = crate::physical_plan::continuous::streaming_window::StreamingWindowExec::try_new(
+            _mode, group_by.clone(), aggr_expr.clone(), _filter_expr, input.clone(), _input_schema, window_type, _upstream_partitioning)?;
+        Ok(Self { input, group_by, aggr_expr, fused_filter: None, schema: inner.schema(), window_type,
+                  cache: inner.properties().clone(), device: 0 })
+    }
+}
+
+impl DisplayAs for GpuStreamingWindowExec {
+    fn fmt_as(&self, _t: DisplayFormatType, f: &mut std::fmt::Formatter) -> std::fmt::Result {
+        write!(f, "GpuStreamingWindowExec: window_type={:?}", self.window_type)
+    }
+}
+
+impl ExecutionPlan for GpuStreamingWindowExec {
+    fn name(&self) -> &'static str { "GpuStreamingWindowExec" }
+    fn as_any(&self) -> &dyn Any { self }
+    fn properties(&self) -> &PlanProperties { &self.cache }
+    fn children(&self) -> Vec<&Arc<dyn ExecutionPlan>> { vec![&self.input] }
+    fn schema(&self) -> SchemaRef { self.schema.clone() }
+    fn with_new_children(self: Arc<Self>, children: Vec<Arc<dyn ExecutionPlan>>) -> Result<Arc<dyn ExecutionPlan>> {
+        Ok(Arc::new(Self { input: children[0].clone(), group_by: self.group_by.clone(), aggr_expr: self.aggr_expr.clone(),
+                           fused_filter: self.fused_filter, schema: self.schema.clone(), window_type: self.window_type,
+                           cache: self.cache.clone(), device: self.device }))
+    }
+
+    /// One GPU handle per output partition, as `StreamingWindowExec::execute` creates one GroupedWindowAggStream
+    /// per partition (streaming_window.rs:421-482).
+    fn execute(&self, partition: usize, ctx: Arc<TaskContext>) -> Result<SendableRecordBatchStream> {
+        let input = self.input.execute(partition, ctx)?;
+        let in_schema = self.input.schema();
+        let ffi_schema = FFI_ArrowSchema::try_from(in_schema.as_ref())?;
+        let key_column = in_schema.index_of(self.group_by.expr()[0].1.as_str())? as i32;
+        let aliases: Vec<std::ffi::CString> = self.aggr_expr.iter().map(|a| std::ffi::CString::new(a.name()).unwrap()).collect();
+        let aggs: Vec<DnzAgg> = self.aggr_expr.iter().zip(&aliases).map(|(a, alias)| DnzAgg {
+            kind: match a.fun().name() { "count" => 0, "min" => 1, "max" => 2, "avg" => 3, "sum" => 4, _ => -1 },
+            arg_column: in_schema.index_of(&a.expressions()[0].to_string()).map(|i| i as i32).unwrap_or(-1),
+            alias: alias.as_ptr(),
+        }).collect();
+        let (window_ms, slide_ms) = match self.window_type {
+            PhysicalStreamingWindowType::Tumbling(l) => (l.as_millis() as i64, 0),
+            PhysicalStreamingWindowType::Sliding(l, s) => (l.as_millis() as i64, s.as_millis() as i64),
+            PhysicalStreamingWindowType::Session(_) => return Err(DataFusionError::NotImplemented("session windows".into())),
+        };
+        let (has_filter, filter_agg, filter_op, filter_literal) = match self.fused_filter {
+            Some((i, op, lit)) => (1, i as i32, op, lit), None => (0, 0, 0, 0.0) };
+        let cfg = DnzWindowConfig { abi_version: 1, device: self.device, key_column, n_aggs: aggs.len() as i32, aggs: aggs.as_ptr(),
+            window_ms, slide_ms, has_filter, filter_agg, filter_op, flags: 0, filter_literal, expected_groups: 0,
+            max_rows_per_launch: 0, cuda_stream: std::ptr::null_mut() };
+        let mut handle: *mut DnzWindow = std::ptr::null_mut();
+        let rc = unsafe { dnz_window_create(&cfg, &ffi_schema, &mut handle) };
+        if rc != 0 { return Err(dnz_err(std::ptr::null())); }
+        Ok(Box::pin(GpuGroupedWindowAggStream { handle, input, schema: self.schema.clone() }))
+    }
+}
+
+/// Drop-in for GroupedWindowAggStream (grouped_window_agg_stream.rs:63-82, poll_next :429-441).
+struct GpuGroupedWindowAggStream { handle: *mut DnzWindow, input: SendableRecordBatchStream, schema: SchemaRef }
+unsafe impl Send for GpuGroupedWindowAggStream {}   // the handle is externally synchronised, not thread-affine
+
+impl Drop for GpuGroupedWindowAggStream {
+    fn drop(&mut self) { unsafe { dnz_window_destroy(self.handle) } }
+}
+
+impl GpuGroupedWindowAggStream {
+    fn take_output(&mut self, force: bool) -> Result<RecordBatch> {
+        let (mut arr, mut sch, mut has) = (FFI_ArrowArray::empty(), FFI_ArrowSchema::empty(), 0i32);
+        let rc = unsafe { if force { dnz_window_poll(self.handle, &mut arr, &mut sch, &mut has) }
+                          else { dnz_window_poll_ready(self.handle, &mut arr, &mut sch, &mut has) } };
+        if rc != 0 { return Err(dnz_err(self.handle)); }
+        let data = unsafe { from_ffi(arr, &sch) }?;
+        Ok(RecordBatch::from(StructArray::from(data)))
+    }
+}
+
+impl Stream for GpuGroupedWindowAggStream {
+    type Item = Result<RecordBatch>;
+    fn poll_next(mut self: Pin<&mut Self>, cx: &mut Context<'_>) -> Poll<Option<Self::Item>> {
+        // Feed every batch that is ready upstream (they queue up to max_rows_per_launch rows per kernel launch), then hand
+        // downstream whatever has closed.  When upstream is Pending the queued batches are forced through, which is the
+        // reference's behaviour of emitting after each batch in the limit of one batch per poll.
+        let mut fed = false;
+        loop {
+            match self.input.poll_next_unpin(cx) {
+                Poll::Ready(Some(Ok(batch))) => {
+                    if batch.num_rows() == 0 { continue; }
+                    let (mut arr, _sch) = to_ffi(&StructArray::from(batch).into_data())?;
+                    if unsafe { dnz_window_push(self.handle, &mut arr) } != 0 { return Poll::Ready(Some(Err(dnz_err(self.handle)))); }
+                    fed = true;
+                }
+                Poll::Ready(Some(Err(e))) => return Poll::Ready(Some(Err(e))),
+                // the reference answers `None` upstream with an EMPTY batch, never `None` (:343-348)
+                Poll::Ready(None) | Poll::Pending => {
+                    let out = self.take_output(true);
+                    return match out {
+                        Ok(b) if b.num_rows() == 0 && !fed => Poll::Pending,
+                        other => Poll::Ready(Some(other)),
+                    };
+                }
+            }
+        }
+    }
+}
+
+impl RecordBatchStream for GpuGroupedWindowAggStream {
+    fn schema(&self) -> SchemaRef { self.schema.clone() }   // includes the two window columns
+}
