@@ -20,7 +20,7 @@ AGG_KINDS = {"count": 0, "min": 1, "max": 2, "avg": 3, "average": 3, "sum": 4}
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 FLAG_KERNEL_TIMING = 1
 FLAG_FORCE_GENERIC = 2
-FLAG_MINMAX_PRECHECK = 4
+FLAG_NO_HINTS = 4
 INTERNAL_METADATA_COLUMN = "_streaming_internal_metadata"   # crates/common/src/lib.rs:5
 
 

@@ -48,10 +48,8 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// L2-coherent 16 B read of (minkey, maxkey): a stale value can only be LESS extreme than the truth, which
-// at worst costs one redundant reduction (never a missed one).
-__device__ __forceinline__ void ld_minmax(const GroupState* s, unsigned long long& mn, unsigned long long& mx) {
-  asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(mn), "=l"(mx) : "l"(&s->minkey) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -84,20 +82,29 @@ __host__ __device__ __forceinline__ long long total_key(unsigned long long b) {
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; return x;
 }
-__host__ __device__ __forceinline__ uint64_t hash_inline(uint64_t k0, uint64_t k1, uint64_t k2, uint32_t len) {
-  uint64_t h = (k0 + 0x9E3779B97F4A7C15ull * (len + 1));
-  h = mix64(h) ^ k1; h = h * 0xBF58476D1CE4E5B9ull + k2; return mix64(h);
+// inline keys (<= 16 B, four zero-padded 32-bit words): 32-bit multiply-xorshift chain -- the slot index needs < 30 bits and
+// 64-bit multiplies cost 3-4 IMADs each on the hot path
+__host__ __device__ __forceinline__ uint32_t hash_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t len) {
+  uint32_t h = (w0 ^ (len * 0x9E3779B1u)) * 0x85EBCA6Bu; h ^= h >> 15;
+  h = (h ^ w1) * 0xC2B2AE35u; h ^= h >> 13;
+  h = (h ^ w2) * 0x27D4EB2Fu; h ^= h >> 16;
+  h = (h ^ w3) * 0x165667B1u; h ^= h >> 15;
+  h *= 0x85EBCA6Bu; h ^= h >> 13;
+  return h;
+}
+__host__ __device__ __forceinline__ uint64_t hash_inline(uint64_t k0, uint64_t k1, uint32_t len) {
+  return hash_words((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32), len);
 }
 
 // A key as the dictionary sees it.
 struct KeyRef {
-  uint64_t k0, k1, k2;   // inline words (long keys: k0 = hash of all bytes)
+  uint64_t k0, k1;       // inline words (long keys: k0 = hash of all bytes)
   uint64_t hash;
   uint32_t len;
   const uint8_t* ptr;    // original bytes (needed only for long keys)
 };
 
-// Load up to 24 key bytes from an arbitrarily aligned address using aligned 32-bit loads.
+// Load up to 16 key bytes from an arbitrarily aligned address using aligned 32-bit loads.
 // Reading the aligned words that contain the first / last key byte never leaves their 4 B word, so it is
 // safe for both shared and global memory.
 template <bool SHARED>
@@ -111,23 +118,22 @@ __device__ __forceinline__ void load_key(const uint8_t* p, uint32_t len, KeyRef&
   if (len <= (uint32_t)INLINE_KEY) {
     uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
     const uint8_t* q = p - mis;
-    uint32_t nw = (mis + len + 3u) >> 2;            // aligned words holding the key (<= 7)
-    uint32_t a[8];
+    uint32_t nw = (mis + len + 3u) >> 2;            // aligned words holding the key (<= 5)
+    uint32_t a[5];
 #pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = (uint32_t)i < nw ? ld_word<SHARED>(q + 4 * i) : 0u;
-    uint32_t w[6];
+    for (int i = 0; i < 5; i++) a[i] = (uint32_t)i < nw ? ld_word<SHARED>(q + 4 * i) : 0u;
+    uint32_t w[4];
     uint32_t sh = mis * 8u;
 #pragma unroll
-    for (int i = 0; i < 6; i++) w[i] = __funnelshift_r(a[i], a[i + 1], sh);
+    for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(a[i], i < 4 ? a[i + 1] : 0u, sh);
 #pragma unroll
-    for (int i = 0; i < 6; i++) {                    // zero the bytes past len
+    for (int i = 0; i < 4; i++) {                    // zero the bytes past len
       uint32_t lo = 4u * i;
       uint32_t keep = len <= lo ? 0u : (len - lo >= 4u ? 0xFFFFFFFFu : ((1u << ((len - lo) * 8u)) - 1u));
       w[i] &= keep;
     }
     k.k0 = (uint64_t)w[0] | ((uint64_t)w[1] << 32); k.k1 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
-    k.k2 = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
-    k.hash = hash_inline(k.k0, k.k1, k.k2, len);
+    k.hash = hash_inline(k.k0, k.k1, len);
   } else {
     uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)len * 0xff51afd7ed558ccdull);
     for (uint32_t i = 0; i < len; i++) {
@@ -137,7 +143,7 @@ __device__ __forceinline__ void load_key(const uint8_t* p, uint32_t len, KeyRef&
       h = (h ^ c) * 0x100000001B3ull; h ^= h >> 29;
     }
     h = mix64(h);
-    k.k0 = h; k.k1 = 0; k.k2 = 0; k.hash = h;
+    k.k0 = h; k.k1 = 0; k.hash = h;
   }
 }
 
@@ -167,10 +173,10 @@ __device__ __forceinline__ uint32_t dict_try_insert(const DictView& d, DictSlot*
   if (g >= d.gcap) { st_release_u32(&slot->state, SLOT_EMPTY); return GID_DEFER_GROUPS; }
   if (k.len > (uint32_t)INLINE_KEY) {
     for (uint32_t i = 0; i < k.len; i++) d.arena[arena_off + i] = ld_key_byte(k.ptr + i, key_shared);
-    slot->k0 = k.k0; slot->k1 = arena_off; slot->k2 = 0;
+    slot->k0 = k.k0; slot->k1 = arena_off;
   } else {
-    slot->k0 = k.k0; slot->k1 = k.k1; slot->k2 = k.k2;
-  }
+    slot->k0 = k.k0; slot->k1 = k.k1;
+  }                                                  // slot->hint stays 0 (= no hint) from the zero fill
   slot->len = k.len;
   d.slot_of_gid[g] = slot_idx;
   atomicAdd(d.key_bytes_total, (unsigned long long)k.len);
@@ -190,8 +196,8 @@ __device__ __forceinline__ bool dict_long_equal(const DictView& d, uint64_t aren
 // `advance` is set when the probe must move to the next slot (occupied by a different key).
 __device__ __forceinline__ uint32_t dict_step(const DictView& d, uint32_t idx, const KeyRef& k, bool key_shared, bool& advance) {
   DictSlot* slot = d.slots + idx;
-  uint64_t a, b, c, w3;
-  ld_slot(slot, a, b, c, w3);
+  uint64_t a, b, hint, w3;
+  ld_slot(slot, a, b, hint, w3);
   uint32_t len = (uint32_t)w3, state = (uint32_t)(w3 >> 32);
   advance = false;
   if (state == SLOT_EMPTY) {
@@ -200,7 +206,7 @@ __device__ __forceinline__ uint32_t dict_step(const DictView& d, uint32_t idx, c
   }
   if (state == SLOT_LOCKED) return 0xFFFFFFFFu;  // insert in flight -> re-read
   bool eq;
-  if (k.len <= (uint32_t)INLINE_KEY) eq = (len == k.len) && a == k.k0 && b == k.k1 && c == k.k2;
+  if (k.len <= (uint32_t)INLINE_KEY) eq = (len == k.len) && a == k.k0 && b == k.k1;
   else eq = (len == k.len) && a == k.k0 && dict_long_equal(d, b, k, key_shared);
   if (eq) return state - 1;
   advance = true;
@@ -224,13 +230,13 @@ __device__ __forceinline__ uint32_t dict_lookup_null(const DictView& d) {
   }
 }
 
-// full lookup (used by the generic / deferred / merge paths; the staged kernel interleaves two probes by hand)
-__device__ __forceinline__ uint32_t dict_lookup(const DictView& d, const KeyRef& k, bool key_shared) {
+// full lookup (used by the generic / deferred / merge paths and by the staged kernel's slow path)
+__device__ __forceinline__ uint32_t dict_lookup(const DictView& d, const KeyRef& k, bool key_shared, uint32_t* slot_out = nullptr) {
   uint32_t idx = (uint32_t)k.hash & d.mask;
   for (;;) {
     bool adv;
     uint32_t g = dict_step(d, idx, k, key_shared, adv);
-    if (g != 0xFFFFFFFFu) return g;
+    if (g != 0xFFFFFFFFu) { if (slot_out) *slot_out = idx; return g; }
     if (adv) idx = (idx + 1) & d.mask;
   }
 }
@@ -242,26 +248,18 @@ __device__ __forceinline__ uint32_t dict_lookup(const DictView& d, const KeyRef&
 __device__ __forceinline__ bool value_needs_fz(double v) { return v == 0.0; }
 
 __device__ __forceinline__ void state_update(GroupState* st, unsigned long long* fz, uint32_t gid, double v,
-                                             unsigned long long rowseq, bool precheck) {
+                                             unsigned long long rowseq) {
   GroupState* s = st + gid;
   unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   if (v == 0.0) {                      // both zeros order as +0.0; remember which one came first
     red_min_u64(fz + gid, (rowseq << 1) | (bits >> 63));
     bits = 0ull;
   }
-  unsigned long long curmn = 0, curmx = 0;
-  if (precheck) ld_minmax(s, curmn, curmx);   // saves ~90 % of the min/max reductions but adds a dependent L2 round trip
-  red_add_u64(&s->cnt, 1ull);
+  red_add_f64(&s->cnt, 1.0);
   red_add_f64(&s->sum, v);
   unsigned long long o = ord_bits(bits);
-  if (v <= 1.7976931348623157e308) {   // false for NaN and +inf
-    unsigned long long k = ORD_F64_MAX - o;
-    if (k > curmn) red_max_u64(&s->minkey, k);
-  }
-  if (v >= -1.7976931348623157e308) {  // false for NaN and -inf
-    unsigned long long k = o - ORD_F64_MIN;
-    if (k > curmx) red_max_u64(&s->maxkey, k);
-  }
+  if (v <= 1.7976931348623157e308) red_max_u64(&s->minkey, ORD_F64_MAX - o);    // false for NaN and +inf
+  if (v >= -1.7976931348623157e308) red_max_u64(&s->maxkey, o - ORD_F64_MIN);   // false for NaN and -inf
 }
 
 __device__ __forceinline__ void defer_row(const DeferList& dl, uint32_t tile, uint32_t row, uint32_t why) {

@@ -109,9 +109,8 @@ __device__ __forceinline__ bool apply_row(const AggParams& P, uint32_t tile, uin
     fm = m ? P.panes.fz_main[pi] : nullptr; fl = l ? P.panes.fz_late[pi] : nullptr;
     if ((m && !fm) || (l && !fl)) { defer_row(P.defer, tile, row, DEFER_NEED_FZ); return false; }
   }
-  const bool pre = P.flags & AGG_MINMAX_PRECHECK;
-  if (m) state_update(m, fm, gid, v, rowseq, pre);
-  if (l) state_update(l, fl, gid, v, rowseq, pre);
+  if (m) state_update(m, fm, gid, v, rowseq);
+  if (l) state_update(l, fl, gid, v, rowseq);
   return true;
 }
 
@@ -156,24 +155,64 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 }
 
 // =================================================================================================
-// k_aggregate: persistent, warp-specialised.  Warp 16 (one elected lane) is the TMA producer: for every tile it
-// issues four 1-D bulk copies (timestamps, values, key offsets, key bytes) into a 4-deep shared-memory ring and
-// arms the stage's `full` mbarrier with the byte count.  Warps 0-15 consume: two rows per thread, both dictionary
-// probes and both accumulator pre-reads kept in flight together, reductions fire-and-forget to L2.
+// k_aggregate: persistent (one CTA per SM), warp-specialised.
+//
+// Warp 16 is the TMA producer.  Its 32 lanes fetch the descriptors of the CTA's next 32 tiles in parallel (TileDesc ->
+// BatchDesc -> pane table: three dependent global loads that would otherwise serialise per tile), then take turns: wait
+// for the ring slot, write the tile header (row count, key byte base, resolved pane state array + hint tag) into shared
+// memory and issue four 1-D bulk copies (timestamps, values, key offsets, key bytes; SASS UBLKCP) that complete on the
+// slot's `full` mbarrier.
+//
+// Warps 0-15 consume, two adjacent rows per thread.  Hot path per row: 3 LDS for value/offsets, 5 LDS.32 + funnel shifts
+// + one LDS.128 mask for the <= 16 B key, a 32-bit hash, ONE 32 B dictionary-slot load (LDG.E.256; both rows' loads in
+// flight together) that also carries the group's min/max hint, then reductions issued by lane PAIRS: lanes 2j / 2j+1 update
+// {cnt, sum} with one red.add.f64 and {minkey, maxkey} with one red.max.u64 of the same row, so an instruction touches
+// 16 sectors instead of 32, and the min/max pair is skipped for rows that cannot beat the hint.  Everything rare (empty
+// or locked slot -> insert, keys > 16 B, +-0.0, tiles spanning panes, late panes) is outlined into __noinline__ helpers
+// so that the hot loop stays ~300 SASS instructions per 64 rows (profiles/README.md).
 // =================================================================================================
+struct __align__(16) StageHdr {
+  GroupState* mbase;            // main state array of the tile's pane when every row can take the paired path, else nullptr
+  long long pane_lo;
+  unsigned long long rowseq0;   // (batch arrival seq << 32) | first row of the tile inside its batch
+  int32_t n_rows, flags, a0, pad0;
+  uint32_t tag, tile_rel, pad1, pad2;
+};
+static_assert(sizeof(StageHdr) == 64, "header size");
 struct __align__(128) Stage {
   long long ts[TILE];
   double val[TILE];
   int32_t off[TILE + 4];
-  uint8_t bytes[BCAP + 32];
+  uint8_t bytes[BCAP + 48];     // a FAST tile stages <= BCAP + 15 bytes; the key loader may over-read 20 B past a key start
+  StageHdr hdr;
 };
 struct AggSmem {
   Stage st[STAGES];
+  uint4 keymask[INLINE_KEY + 1];     // keymask[len] = byte mask of a len-byte key in four 32-bit words
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
 };
 
 __device__ __forceinline__ uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+// ---- outlined slow paths ------------------------------------------------------------------------------------------------
+// Full dictionary lookup / insert for one staged row (any key length).  Returns the gid (or GID_DEFER_*).
+__device__ __noinline__ uint32_t agg_probe_slow(const AggParams& P, const uint8_t* key_smem, uint32_t len, uint32_t* slot_out) {
+  KeyRef k; load_key<true>(key_smem, len, k);
+  return dict_lookup(P.dict, k, true, slot_out);
+}
+// Accumulate one staged row through the general per-row path (pane from the timestamp, late panes, +-0.0, ...).
+__device__ __noinline__ void agg_apply_slow(const AggParams& P, const StageHdr& h, uint32_t r, long long ts, double v, uint32_t gid) {
+  long long pane = (h.flags & TILE_PANE_UNIFORM) ? h.pane_lo : ts / P.panes.pane_ms;
+  apply_row(P, h.tile_rel, r, pane, true, v, gid, h.rowseq0 + r);
+}
+__device__ __noinline__ void agg_tile_generic(const AggParams& P, uint32_t tile_rel, int tid) {
+  const TileDesc td = P.tiles[P.tile_begin + tile_rel];
+  if (td.flags & TILE_EMPTY) return;
+  const BatchDesc bd = P.batches[td.batch];
+  for (uint32_t r = tid; r < (uint32_t)td.n_rows; r += CONSUMER_WARPS * 32) process_row_generic(P, tile_rel, td, bd, r);
+}
 
 __global__ void __launch_bounds__(AGG_THREADS, 1) k_aggregate(const __grid_constant__ AggParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -183,93 +222,170 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) k_aggregate(const __grid_const
     for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
     mbar_fence_init();
   }
+  if (tid <= INLINE_KEY) {
+    uint32_t m[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int keep = tid - 4 * i; m[i] = keep <= 0 ? 0u : keep >= 4 ? 0xFFFFFFFFu : ((1u << (8 * keep)) - 1u); }
+    S.keymask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
+  }
   __syncthreads();
 
   if (warp == CONSUMER_WARPS) {
-    // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x, it++) {
-        const int s = it % STAGES;
-        mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
-        const TileDesc td = P.tiles[t];
+    // ------------------------------------------------------------ producer warp
+    uint32_t it = 0;
+    const int64_t stride = gridDim.x;
+    for (int64_t tb = P.tile_begin + blockIdx.x; tb < P.tile_end; tb += stride * 32) {
+      const int64_t t = tb + stride * lane;
+      TileDesc td; td.flags = 0; td.n_rows = 0;
+      const int64_t* gts = nullptr; const double* gval = nullptr; const int32_t* goff = nullptr; const uint8_t* gby = nullptr;
+      StageHdr h; h.mbase = nullptr; h.tag = 0; h.pane_lo = 0; h.rowseq0 = 0; h.n_rows = 0; h.flags = 0; h.a0 = 0; h.tile_rel = 0;
+      h.pad0 = 0; h.pad1 = h.pad2 = 0;
+      if (t < P.tile_end) {
+        td = P.tiles[t];
+        const BatchDesc& bd = P.batches[td.batch];
+        h.n_rows = td.n_rows; h.flags = td.flags; h.pane_lo = td.pane_lo; h.tile_rel = (uint32_t)(t - P.tile_begin);
+        h.a0 = (int32_t)(td.byte0 & ~(int64_t)15);
+        h.rowseq0 = ((unsigned long long)bd.seq << 32) | (unsigned long long)(uint32_t)td.row0;
         if (td.flags & TILE_FAST) {
-          const BatchDesc& bd = P.batches[td.batch];
-          const int64_t* gts = bd.ts + td.row0; const double* gval = bd.val + td.row0; const int32_t* goff = bd.off + td.row0;
-          uint32_t nts = round16((uint32_t)td.n_rows * 8u), noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
-          int64_t a0 = td.byte0 & ~(int64_t)15;
-          uint32_t nby = round16((uint32_t)(td.byte0 + td.byte_len - a0));
-          mbar_arrive_expect_tx(&S.full[s], nts * 2u + noff + nby);
-          bulk_g2s(S.st[s].ts, gts, nts, &S.full[s]);
-          bulk_g2s(S.st[s].val, gval, nts, &S.full[s]);
-          bulk_g2s(S.st[s].off, goff, noff, &S.full[s]);
-          if (nby) bulk_g2s(S.st[s].bytes, bd.bytes + a0, nby, &S.full[s]);
-        } else {
-          mbar_arrive(&S.full[s]);
+          gts = bd.ts + td.row0; gval = bd.val + td.row0; goff = bd.off + td.row0; gby = bd.bytes + h.a0;
+          if (td.flags & TILE_PANE_UNIFORM) {
+            int64_t pi = td.pane_lo - P.panes.pane0;
+            if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) { h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; }
+          }
         }
+      }
+      for (int j = 0; j < 32; j++) {
+        if (tb + stride * j >= P.tile_end) break;                   // warp-uniform
+        const int s = it % STAGES;
+        if (lane == j) {
+          mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
+          S.st[s].hdr = h;
+          if (td.flags & TILE_FAST) {
+            uint32_t nts = round16((uint32_t)td.n_rows * 8u), noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
+            uint32_t nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
+            mbar_arrive_expect_tx(&S.full[s], nts * 2u + noff + nby);
+            bulk_g2s(S.st[s].ts, gts, nts, &S.full[s]);
+            bulk_g2s(S.st[s].val, gval, nts, &S.full[s]);
+            bulk_g2s(S.st[s].off, goff, noff, &S.full[s]);
+            if (nby) bulk_g2s(S.st[s].bytes, gby, nby, &S.full[s]);
+          } else {
+            mbar_arrive(&S.full[s]);
+          }
+        }
+        it++;
+        __syncwarp();
       }
     }
     return;
   }
 
-  // -------------------------------------------------------------- consumers
-  const DictView& D = P.dict;
+  // -------------------------------------------------------------- consumer warps
+  const DictSlot* const slots = P.dict.slots;
+  const uint32_t dmask = P.dict.mask;
+  const bool use_hints = !(P.flags & AGG_NO_HINTS);
+  const int odd = lane & 1;
   uint32_t it = 0;
   for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x, it++) {
     const int s = it % STAGES;
-    const TileDesc td = P.tiles[t];
     mbar_wait(&S.full[s], (it / STAGES) & 1u);
-    const uint32_t tile_rel = (uint32_t)(t - P.tile_begin);
-    if (!(td.flags & TILE_FAST)) {
-      if (!(td.flags & TILE_EMPTY)) {
-        const BatchDesc bd = P.batches[td.batch];
-        for (uint32_t r = tid; r < (uint32_t)td.n_rows; r += CONSUMER_WARPS * 32) process_row_generic(P, tile_rel, td, bd, r);
-      }
+    const Stage& st = S.st[s];
+    const StageHdr& H = st.hdr;
+    const int32_t hflags = H.flags;
+    if (!(hflags & TILE_FAST)) {
+      agg_tile_generic(P, H.tile_rel, tid);
     } else {
-      const Stage& st = S.st[s];
-      const long long seq = P.batches[td.batch].seq;
-      const int32_t a0 = (int32_t)(td.byte0 & ~(int64_t)15);
-      KeyRef key[2]; uint32_t idx[2], gid[2]; bool active[2], live[2]; long long ts[2]; double v[2]; uint32_t rr[2];
+      const uint32_t n = (uint32_t)H.n_rows;
+      const uint32_t r0 = 2u * (uint32_t)tid;
+      GroupState* const mbase = H.mbase;
+      const uint32_t tag = H.tag;
+      const bool live[2] = {r0 < n, r0 + 1u < n};
+      const double2 vv = *reinterpret_cast<const double2*>(&st.val[r0]);
+      const int2 oo = *reinterpret_cast<const int2*>(&st.off[r0]);
+      const int32_t o2 = st.off[r0 + 2];
+      const double v[2] = {vv.x, vv.y};
+      const int32_t a0 = H.a0;
+      uint32_t klen[2], kb[2];
+      klen[0] = live[0] ? (uint32_t)(oo.y - oo.x) : 0u; kb[0] = live[0] ? (uint32_t)(oo.x - a0) : 0u;
+      klen[1] = live[1] ? (uint32_t)(o2 - oo.y) : 0u;   kb[1] = live[1] ? (uint32_t)(oo.y - a0) : 0u;
+      const uint32_t bytes_base = smem_u32(st.bytes);
+      uint32_t w[2][4], idx[2], gid[2]; uint64_t hint[2];
+      uint32_t todo = 0, slow = 0;
 #pragma unroll
       for (int i = 0; i < 2; i++) {
-        uint32_t r = (uint32_t)tid + (uint32_t)i * (CONSUMER_WARPS * 32);
-        rr[i] = r; live[i] = r < (uint32_t)td.n_rows; active[i] = live[i]; gid[i] = 0;
-        if (live[i]) {
-          ts[i] = st.ts[r]; v[i] = st.val[r];
-          int32_t o0 = st.off[r], o1 = st.off[r + 1];
-          load_key<true>(st.bytes + (o0 - a0), (uint32_t)(o1 - o0), key[i]);
-          idx[i] = (uint32_t)key[i].hash & D.mask;
-        } else { ts[i] = 0; v[i] = 0.0; idx[i] = 0; key[i].len = 0; key[i].k0 = key[i].k1 = key[i].k2 = key[i].hash = 0; key[i].ptr = nullptr; }
-      }
-      // interleaved dictionary probes: both 32 B slot reads are issued before either is examined
-      while (active[0] || active[1]) {
-        uint64_t a[2], b[2], c[2], w3[2];
+        const uint32_t addr = bytes_base + kb[i], q = addr & ~3u, sh = (addr & 3u) * 8u;
+        uint32_t a[5];
 #pragma unroll
-        for (int i = 0; i < 2; i++) if (active[i]) ld_slot(D.slots + idx[i], a[i], b[i], c[i], w3[i]);
+        for (int j = 0; j < 5; j++) a[j] = lds32(q + 4u * j);
+        const uint4 m = S.keymask[min(klen[i], (uint32_t)INLINE_KEY)];
+        w[i][0] = __funnelshift_r(a[0], a[1], sh) & m.x; w[i][1] = __funnelshift_r(a[1], a[2], sh) & m.y;
+        w[i][2] = __funnelshift_r(a[2], a[3], sh) & m.z; w[i][3] = __funnelshift_r(a[3], a[4], sh) & m.w;
+        idx[i] = hash_words(w[i][0], w[i][1], w[i][2], w[i][3], klen[i]) & dmask;
+        gid[i] = 0; hint[i] = 0;
+        if (live[i]) { if (klen[i] <= (uint32_t)INLINE_KEY) todo |= 1u << i; else slow |= 1u << i; }
+      }
+      // dictionary probes: both rows' 32 B slot reads are issued before either is examined
+      while (todo) {
+        uint64_t sa[2], sb[2], sc[2], sd[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) if (todo & (1u << i)) ld_slot(slots + idx[i], sa[i], sb[i], sc[i], sd[i]);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          if (!active[i]) continue;
-          uint32_t len = (uint32_t)w3[i], state = (uint32_t)(w3[i] >> 32);
-          if (state == SLOT_EMPTY) {
-            uint32_t g = dict_try_insert(D, D.slots + idx[i], idx[i], key[i], true);
-            if (g != 0xFFFFFFFFu) { gid[i] = g; active[i] = false; }
-          } else if (state != SLOT_LOCKED) {
-            bool eq;
-            if (key[i].len <= (uint32_t)INLINE_KEY) eq = len == key[i].len && a[i] == key[i].k0 && b[i] == key[i].k1 && c[i] == key[i].k2;
-            else eq = len == key[i].len && a[i] == key[i].k0 && dict_long_equal(D, b[i], key[i], true);
-            if (eq) { gid[i] = state - 1; active[i] = false; } else idx[i] = (idx[i] + 1) & D.mask;
-          }
+          if (!(todo & (1u << i))) continue;
+          const uint32_t state = (uint32_t)(sd[i] >> 32);
+          if (state - 1u < 0xFFFFFFFEu) {                 // occupied and published
+            const bool eq = (uint32_t)sd[i] == klen[i] && sa[i] == (((uint64_t)w[i][1] << 32) | w[i][0]) && sb[i] == (((uint64_t)w[i][3] << 32) | w[i][2]);
+            if (eq) { gid[i] = state - 1u; hint[i] = sc[i]; todo &= ~(1u << i); } else idx[i] = (idx[i] + 1u) & dmask;
+          } else { slow |= 1u << i; todo &= ~(1u << i); }   // empty (insert) or locked (insert in flight)
         }
       }
-      // accumulate
+      if (slow) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+          if (slow & (1u << i)) { gid[i] = agg_probe_slow(P, st.bytes + kb[i], klen[i], &idx[i]); hint[i] = 0; }
+      }
+      // hints + packing for the paired reductions
+      uint32_t pk[2];
 #pragma unroll
       for (int i = 0; i < 2; i++) {
+        pk[i] = 0;
         if (!live[i]) continue;
-        if (gid[i] == GID_DEFER_GROUPS) { defer_row(P.defer, tile_rel, rr[i], DEFER_GROUPS_FULL); continue; }
-        if (gid[i] == GID_DEFER_ARENA) { defer_row(P.defer, tile_rel, rr[i], DEFER_ARENA_FULL); continue; }
-        long long pane = (td.flags & TILE_PANE_UNIFORM) ? td.pane_lo : ts[i] / P.panes.pane_ms;
-        unsigned long long rowseq = ((unsigned long long)seq << 32) | (unsigned long long)(td.row0 + rr[i]);
-        apply_row(P, tile_rel, rr[i], pane, true, v[i], gid[i], rowseq);
+        if (gid[i] >= GID_DEFER_ARENA) { defer_row(P.defer, H.tile_rel, r0 + i, gid[i] == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL); continue; }
+        if (mbase != nullptr && v[i] != 0.0) {
+          const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v[i]));
+          const bool okmin = v[i] <= 1.7976931348623157e308, okmax = v[i] >= -1.7976931348623157e308;   // false for NaN, +inf / -inf
+          const uint32_t tmin = (uint32_t)((ORD_F64_MAX - o) >> 48), tmax = (uint32_t)((o - ORD_F64_MIN) >> 48);
+          uint32_t hmin = 0, hmax = 0;
+          if (use_hints && (uint32_t)(hint[i] >> 32) == tag) { hmin = (uint32_t)(hint[i] >> 16) & 0xFFFFu; hmax = (uint32_t)hint[i] & 0xFFFFu; }
+          const bool pmin = okmin && tmin >= hmin, pmax = okmax && tmax >= hmax;
+          if (use_hints && ((okmin && tmin > hmin) || (okmax && tmax > hmax))) {
+            const uint32_t nmin = okmin ? max(hmin, tmin) : hmin, nmax = okmax ? max(hmax, tmax) : hmax;
+            st_relaxed_u64(const_cast<uint64_t*>(&slots[idx[i]].hint), ((uint64_t)tag << 32) | ((uint64_t)nmin << 16) | (uint64_t)nmax);
+          }
+          pk[i] = gid[i] | (1u << 29) | (pmin ? 1u << 30 : 0u) | (pmax ? 1u << 31 : 0u);
+        } else {
+          agg_apply_slow(P, H, r0 + i, st.ts[r0 + i], v[i], gid[i]);
+        }
+      }
+      if (mbase != nullptr) {                       // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const uint32_t vlo = (uint32_t)__double2loint(v[i]), vhi = (uint32_t)__double2hiint(v[i]);
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int src = (lane >> 1) + 16 * half;
+            const uint32_t pk2 = __shfl_sync(0xffffffffu, pk[i], src);
+            const uint32_t lo2 = __shfl_sync(0xffffffffu, vlo, src), hi2 = __shfl_sync(0xffffffffu, vhi, src);
+            if (pk2 & (1u << 29)) {
+              const double v2 = __hiloint2double((int)hi2, (int)lo2);
+              GroupState* s2 = mbase + (pk2 & 0x1FFFFFFFu);
+              red_add_f64(&s2->cnt + odd, odd ? v2 : 1.0);
+              if (pk2 & (odd ? 1u << 31 : 1u << 30)) {
+                const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v2));
+                red_max_u64(&s2->minkey + odd, odd ? o - ORD_F64_MIN : ORD_F64_MAX - o);
+              }
+            }
+          }
+        }
       }
     }
     __syncwarp();
@@ -321,18 +437,18 @@ __device__ __forceinline__ uint64_t key_hash_of_gid(const DictView& d, uint32_t 
   if (si == 0xFFFFFFFFu) { len_out = 0; return 0; }            // NULL key hashes to 0 (owner = rank 0)
   const DictSlot& sl = d.slots[si];
   len_out = sl.len;
-  return sl.len <= (uint32_t)INLINE_KEY ? hash_inline(sl.k0, sl.k1, sl.k2, sl.len) : sl.k0;
+  return sl.len <= (uint32_t)INLINE_KEY ? hash_inline(sl.k0, sl.k1, sl.len) : sl.k0;
 }
 
-struct Combined { unsigned long long cnt, nullrows, mnk, mxk, fz; double sum; bool present; };
+struct Combined { unsigned long long cnt, nullrows, mnk, mxk, fz; double sum; bool present; };   // cnt: exact integer
 
 __device__ __forceinline__ Combined combine_panes(const EmitParams& P, uint32_t g) {
   Combined c; c.cnt = 0; c.nullrows = 0; c.mnk = 0; c.mxk = 0; c.fz = ~0ull; c.sum = 0.0;
   bool first = true;
   for (int p = 0; p < P.n_panes; p++) {
     const GroupState s = P.panes[p][g];
-    if (s.cnt) { c.sum = first ? s.sum : c.sum + s.sum; first = false; }   // no "+ 0.0" for absent panes: keeps -0.0 sums exact
-    c.cnt += s.cnt; c.mnk = max(c.mnk, s.minkey); c.mxk = max(c.mxk, s.maxkey);
+    if (s.cnt != 0.0) { c.sum = first ? s.sum : c.sum + s.sum; first = false; }   // no "+ 0.0" for absent panes: keeps -0.0 sums exact
+    c.cnt += (unsigned long long)s.cnt; c.mnk = max(c.mnk, s.minkey); c.mxk = max(c.mxk, s.maxkey);
     if (P.nullrows[p]) c.nullrows += P.nullrows[p][g];
     if (P.fz[p]) c.fz = min(c.fz, P.fz[p][g]);
   }
@@ -398,7 +514,7 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams
   if (slot != 0xFFFFFFFFu) {
     const DictSlot& sl = P.dict.slots[slot];
     if (klen <= (uint32_t)INLINE_KEY) {
-      uint64_t w[3] = {sl.k0, sl.k1, sl.k2};
+      uint64_t w[2] = {sl.k0, sl.k1};
       for (uint32_t i = 0; i < klen; i++) O.key_bytes[boff + i] = (uint8_t)(w[i >> 3] >> ((i & 7) * 8));
     } else {
       const uint8_t* src = P.dict.arena + sl.k1;
@@ -480,7 +596,7 @@ __global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictV
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
     DictSlot s = old_slots[i];
     if (s.state == SLOT_EMPTY || s.state == SLOT_LOCKED) continue;
-    uint64_t h = s.len <= (uint32_t)INLINE_KEY ? hash_inline(s.k0, s.k1, s.k2, s.len) : s.k0;
+    uint64_t h = s.len <= (uint32_t)INLINE_KEY ? hash_inline(s.k0, s.k1, s.len) : s.k0;
     uint32_t idx = (uint32_t)h & nd.mask;
     for (;;) {
       uint32_t old = atomicCAS(&nd.slots[idx].state, SLOT_EMPTY, SLOT_LOCKED);
@@ -488,7 +604,7 @@ __global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictV
       idx = (idx + 1) & nd.mask;
     }
     DictSlot* d = nd.slots + idx;
-    d->k0 = s.k0; d->k1 = s.k1; d->k2 = s.k2; d->len = s.len;
+    d->k0 = s.k0; d->k1 = s.k1; d->hint = s.hint; d->len = s.len;
     nd.slot_of_gid[s.state - 1] = idx;
     __threadfence();
     d->state = s.state;
@@ -497,6 +613,16 @@ __global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictV
 cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd, cudaStream_t s) {
   uint64_t gb = ((uint64_t)old_cap + 255) / 256; int grid = (int)(gb < 148 * 16 ? gb : 148 * 16);
   k_dict_rehash<<<grid, 256, 0, s>>>(old_slots, old_cap, nd);
+  return cudaGetLastError();
+}
+
+
+__global__ void k_clear_hints(DictSlot* slots, uint32_t cap) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) slots[i].hint = 0;
+}
+cudaError_t launch_clear_hints(DictSlot* slots, uint32_t cap, cudaStream_t s) {
+  uint64_t gb = ((uint64_t)cap + 255) / 256; int grid = (int)(gb < 148 * 16 ? gb : 148 * 16);
+  k_clear_hints<<<grid, 256, 0, s>>>(slots, cap);
   return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ constexpr int STAGES = 4;             // TMA ring depth per CTA
 constexpr int BCAP = 16384;           // staged key bytes per tile (16 B/row average); longer tiles take the generic path
 constexpr int CONSUMER_WARPS = 16;    // 512 consumer threads x 2 rows = TILE
 constexpr int AGG_THREADS = (CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
-constexpr int INLINE_KEY = 24;        // key bytes stored inline in a dictionary slot
+constexpr int INLINE_KEY = 16;        // key bytes stored inline in a dictionary slot
 
 enum : int32_t {
   TILE_FAST = 1,          // all four column slices can be staged with cp.async.bulk (16 B aligned, fits BCAP, no bitmaps)
@@ -43,12 +43,18 @@ struct TileDesc {
 struct BatchMinMax { int64_t ts_min, ts_max, n_valid, key_bytes, n_fast, n_tiles; };   // per RecordBatch, filled by k_tile_scan
 
 // ------------------------------------------------------------------------------------------------
-// Key dictionary: open addressing, one 32 B sector per slot, keys <= 24 B inline.
+// Key dictionary: open addressing, one 32 B sector per slot, keys <= 16 B inline.
 struct __align__(32) DictSlot {
-  uint64_t k0, k1, k2;   // inline: zero padded key bytes; long keys: k0 = hash64, k1 = arena offset
+  uint64_t k0, k1;       // inline: zero padded key bytes; long keys: k0 = hash64, k1 = arena offset
+  uint64_t hint;         // min/max reduction filter of this group (see below); rides along with every probe for free
   uint32_t len;          // key length in bytes
   uint32_t state;        // 0 empty, 0xFFFFFFFF locked (insert in flight), else gid + 1
 };
+// hint = tag:32 | hmin:16 | hmax:16.  `tag` names ONE zero-initialised pane state array (Pane::tag, never reused);
+// hmin / hmax are the top 16 bits of a minkey / maxkey that some thread HAS reduced (or is about to reduce) into that
+// array for this group.  A row whose key is smaller in its top 16 bits cannot change the state and skips the reduction.
+// Plain racy stores keep it conservative: every value ever stored is backed by a reduction, a mismatching tag reads
+// as "no hint".
 constexpr uint32_t SLOT_EMPTY = 0u, SLOT_LOCKED = 0xFFFFFFFFu;
 
 struct DictView {
@@ -63,7 +69,7 @@ struct DictView {
 
 // Per (pane, group) partial aggregate: exactly one 32 B sector.
 struct __align__(32) GroupState {
-  unsigned long long cnt;      // non-null values
+  double cnt;                  // non-null values, kept as f64 (exact below 2^53) so that {cnt, sum} is ONE red.add.f64 pair
   double sum;
   unsigned long long minkey;   // ORD(f64::MAX) - ord(v): 0 == f64::MAX (accumulator start), larger == smaller value
   unsigned long long maxkey;   // ord(v) - ORD(f64::MIN): 0 == f64::MIN
@@ -77,6 +83,7 @@ struct PaneTable {             // uploaded per launch
   GroupState* const* late;     // [n_panes] nullable: rows re-opening already emitted windows (exact late path)
   unsigned long long* const* nullrows_main; unsigned long long* const* nullrows_late;   // rows with NULL value, nullable
   unsigned long long* const* fz_main; unsigned long long* const* fz_late;               // first +-0.0 row (seq<<1|sign), nullable
+  const unsigned long long* tag_main;   // [n_panes] instance tag of main[i] (low 32 bits, never 0), see DictSlot::hint
 };
 
 struct DeferEntry { uint32_t tile, row; };
@@ -88,7 +95,7 @@ struct AggParams {
   DictView dict; PaneTable panes; DeferList defer;
   uint32_t flags;
 };
-enum : uint32_t { AGG_MINMAX_PRECHECK = 1 };
+enum : uint32_t { AGG_NO_HINTS = 1 };   // experiments: reduce min/max for every row
 
 // ------------------------------------------------------------------------------------------------
 // Emission: combine the panes of one window, evaluate the predicate, compact into Arrow-shaped columns.
@@ -133,6 +140,7 @@ cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n
 cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);
 cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd, cudaStream_t s);
+cudaError_t launch_clear_hints(DictSlot* slots, uint32_t cap, cudaStream_t s);
 cudaError_t agg_kernel_setup();
 
 // exchange (multi-GPU)

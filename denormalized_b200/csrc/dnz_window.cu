@@ -148,6 +148,7 @@ struct Arena {
 
 struct Pane {
   int64_t id = 0;
+  uint64_t tag = 0;        // names this zero-initialised instance of `st` (DictSlot::hint); never reused
   DevBuf st, nullrows, fz;
 };
 
@@ -201,6 +202,7 @@ struct dnz_window {
   std::map<int64_t, std::unique_ptr<Pane>> panes;
   std::vector<std::unique_ptr<Pane>> pane_pool;
   bool need_nullrows = false, need_fz = false;
+  uint64_t next_tag = 1;   // pane instance tags (low 32 bits are stored in the hints)
   bool has_wm = false; int64_t wm = 0;
   int64_t emitted_upto = INT64_MIN;
 
@@ -469,6 +471,11 @@ std::unique_ptr<Pane> dnz_window::new_pane(int64_t id) {
   if (!pane_pool.empty()) { p = std::move(pane_pool.back()); pane_pool.pop_back(); }
   else { p.reset(new Pane()); p->st.alloc((size_t)gcap * sizeof(GroupState)); }
   p->id = id;
+  if ((uint32_t)next_tag == 0) {      // 2^32 pane instances later the 32-bit tags would repeat: drop every hint first
+    CK(launch_clear_hints(slots.as<DictSlot>(), dict_cap, stream)); stats.total_launches++;
+    next_tag = 1;
+  }
+  p->tag = next_tag++;
   CK(cudaMemsetAsync(p->st.p, 0, (size_t)gcap * sizeof(GroupState), stream));
   ensure_side_arrays(p.get());
   if (p->nullrows.p) CK(cudaMemsetAsync(p->nullrows.p, 0, (size_t)gcap * 8, stream));
@@ -676,8 +683,8 @@ void dnz_window::prealloc() {
   }
   d_copy_cursor.alloc(64);
   for (int i = 0; i < 2; i++) { d_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); h_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); }
-  d_ptrs.reserve(6 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
-  h_stage.reserve((size_t)6 * 1024 * sizeof(void*)); h_small.reserve(256);
+  d_ptrs.reserve(7 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
+  h_stage.reserve((size_t)7 * 1024 * sizeof(void*)); h_small.reserve(256);
   for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
   ensure_result_capacity((uint64_t)gcap * 8, (uint64_t)gcap * 16 * 8);
 }
@@ -781,7 +788,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
       if (iter > 64) fail(DNZ_ERR_NOMEM, "deferred rows did not converge");
       // pane pointer table
       size_t pb = (size_t)np * sizeof(void*);
-      h_stage.reserve(6 * pb); d_ptrs.reserve(6 * pb);
+      h_stage.reserve(7 * pb); d_ptrs.reserve(7 * pb);
       void** hp = h_stage.as<void*>();
       for (int64_t p = pmin; p <= pmax; p++) {
         size_t k = (size_t)(p - pmin);
@@ -792,18 +799,20 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
         hp[0 * np + k] = m ? m->st.p : nullptr; hp[1 * np + k] = l ? l->st.p : nullptr;
         hp[2 * np + k] = m ? m->nullrows.p : nullptr; hp[3 * np + k] = l ? l->nullrows.p : nullptr;
         hp[4 * np + k] = m ? m->fz.p : nullptr; hp[5 * np + k] = l ? l->fz.p : nullptr;
+        hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m ? (m->tag & 0xFFFFFFFFull) : 0));
       }
-      CK(cudaMemcpyAsync(d_ptrs.p, hp, 6 * pb, cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(d_ptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
       CK(cudaMemsetAsync(ctl(64), 0, 16, stream));
       AggParams P;
       P.batches = cur_scan->d_batches.as<BatchDesc>(); P.tiles = cur_scan->d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
       P.dict = dict_view();
-      P.flags = (cfg.flags & DNZ_FLAG_MINMAX_PRECHECK) ? AGG_MINMAX_PRECHECK : 0;
+      P.flags = (cfg.flags & DNZ_FLAG_NO_HINTS) ? AGG_NO_HINTS : 0;
       char* dp = d_ptrs.as<char>();
       P.panes.pane0 = pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
       P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
       P.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); P.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
       P.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); P.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+      P.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
       const int out_list = iter == 0 ? 0 : (in_list ^ 1);
       d_defer[out_list].reserve(defer_cap * sizeof(DeferEntry));
       P.defer.entries = d_defer[out_list].as<DeferEntry>();

@@ -75,6 +75,44 @@ def test_min_max_quirks_and_filter_total_order():
     assert math.copysign(1, got[b"z1"][4]) == -1 and math.copysign(1, got[b"z2"][4]) == 1
 
 
+@pytest.mark.parametrize("L,S", [(1000, 0), (4000, 1000)])
+@pytest.mark.parametrize("late", [False, True])
+def test_minmax_hints_never_lose_an_extreme(L, S, late):
+    """Few keys x many rows per pane, fast (TMA-staged) tiles, one launch per batch: the per-group min/max reduction filter
+    (DictSlot::hint) is hit hard -- trends, sign changes, tiny/huge magnitudes, values equal in their top 16 key bits,
+    panes revisited by late batches (new pane instances => new hint tags)."""
+    rng = np.random.default_rng(1234 + L + S + late)
+    batches, t = [], T0
+    for b in range(36):
+        n = 2500
+        k = rng.integers(0, 12, n)
+        mode = b % 6
+        if mode == 0:
+            v = rng.random(n) * 115.0
+        elif mode == 1:
+            v = 100.0 + np.arange(n) * 1e-9 + rng.random(n) * 1e-7          # same top-16 bucket, creeping upwards
+        elif mode == 2:
+            v = -100.0 - np.arange(n) * 1e-9 - rng.random(n) * 1e-7         # creeping downwards
+        elif mode == 3:
+            v = (rng.random(n) - 0.5) * 10.0 ** rng.integers(-300, 300, n).astype(np.float64)
+        elif mode == 4:
+            v = np.where(rng.random(n) < 0.5, 113.99999, 114.00001) * np.where(rng.random(n) < 0.1, -1.0, 1.0)
+        else:
+            v = rng.standard_normal(n) * 1e-3
+        back = 2600 if (late and b % 7 == 6) else 0
+        ts = t - back + rng.integers(0, 300, n)
+        rows = [(int(ts[i]), float(v[i]), b"g%d" % k[i]) for i in range(n)]
+        batches.append(rows_to_batch(rows))
+        t += 300
+    batches.append(sentinel(t + 3 * L))
+    want = run_oracle_batches(batches, L, S)
+    got, st = run_gpu(batches, L, S)
+    assert st["fast_tiles"] > 30 and (st["late_batches"] > 0) == late
+    assert_rows_equal(got, want, check_seq=True)
+    got2, _ = run_gpu(batches, L, S, per_batch_poll=False)
+    assert_rows_equal(got2, want)
+
+
 def test_long_and_empty_keys_and_dictionary_growth():
     rng = np.random.default_rng(3)
     rows_all = []
