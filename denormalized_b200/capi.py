@@ -21,6 +21,7 @@ OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 FLAG_KERNEL_TIMING = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_NO_HINTS = 4
+FLAG_NO_QUEUE = 8
 INTERNAL_METADATA_COLUMN = "_streaming_internal_metadata"   # crates/common/src/lib.rs:5
 
 

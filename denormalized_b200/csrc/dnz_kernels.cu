@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 }
 
 // =================================================================================================
-// k_aggregate: persistent (one CTA per SM), warp-specialised.
+// k_aggregate: persistent (two CTAs of 17 warps per SM), warp-specialised.
 //
 // Warp 16 is the TMA producer.  Its 32 lanes fetch the descriptors of the CTA's next 32 tiles in parallel (TileDesc ->
 // BatchDesc -> pane table: three dependent global loads that would otherwise serialise per tile), then take turns: wait
@@ -163,9 +163,10 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 // memory and issue four 1-D bulk copies (timestamps, values, key offsets, key bytes; SASS UBLKCP) that complete on the
 // slot's `full` mbarrier.
 //
-// Warps 0-15 consume, two adjacent rows per thread.  Hot path per row: 3 LDS for value/offsets, 5 LDS.32 + funnel shifts
-// + one LDS.128 mask for the <= 16 B key, a 32-bit hash, ONE 32 B dictionary-slot load (LDG.E.256; both rows' loads in
-// flight together) that also carries the group's min/max hint, then reductions issued by lane PAIRS: lanes 2j / 2j+1 update
+// Warps 0-15 consume, one row per thread (8 consumer warps per scheduler across the two CTAs hide the L2 round trip of
+// the probe).  Hot path per row: 3 LDS for value/offsets, 5 LDS.32 + funnel shifts + one LDS.128 mask for the <= 16 B
+// key, a 32-bit hash, ONE 32 B dictionary-slot load (LDG.E.256) that also carries the group's min/max hint; a row whose
+// slot holds another key is parked in the warp's retry queue; then reductions issued by lane PAIRS: lanes 2j / 2j+1 update
 // {cnt, sum} with one red.add.f64 and {minkey, maxkey} with one red.max.u64 of the same row, so an instruction touches
 // 16 sectors instead of 32, and the min/max pair is skipped for rows that cannot beat the hint.  Everything rare (empty
 // or locked slot -> insert, keys > 16 B, +-0.0, tiles spanning panes, late panes) is outlined into __noinline__ helpers
@@ -186,8 +187,26 @@ struct __align__(128) Stage {
   uint8_t bytes[BCAP + 48];     // a FAST tile stages <= BCAP + 15 bytes; the key loader may over-read 20 B past a key start
   StageHdr hdr;
 };
+// Per-warp retry queue.  A row whose first probe hit a slot occupied by ANOTHER key does not make its warp loop (the
+// slowest of 64 rows would pace the warp: ~3 dependent L2 round trips per tile at 25 % load); it is parked here with its
+// next slot index and re-probed 32 rows at a time, so every round trip is a full-warp load.
+constexpr int QCAP = 64;             // < 32 carried over + 32 new rows
+struct WarpQueue {
+  uint4 key[QCAP];                   // inline key words
+  uint2 meta[QCAP];                  // x: next slot index, y: key length | pane index (relative to PaneTable::pane0) << 8
+  double val[QCAP];
+  uint32_t row[QCAP];                // tile (relative to the launch) << 10 | row inside the tile  (deferred-row bookkeeping)
+};
+static_assert(TILE <= 1024, "row packing");
+struct __align__(16) TileFetch {     // what the producer needs to hand one tile to the ring (staged in shared memory, 2 x 32)
+  StageHdr h;
+  const int64_t* gts; const double* gval; const int32_t* goff; const uint8_t* gby;
+  uint32_t nts, noff, nby, pad;
+};
 struct AggSmem {
   Stage st[STAGES];
+  WarpQueue q[CONSUMER_WARPS];
+  TileFetch fetch[2][32];
   uint4 keymask[INLINE_KEY + 1];     // keymask[len] = byte mask of a len-byte key in four 32-bit words
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -198,14 +217,24 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volat
 
 // ---- outlined slow paths ------------------------------------------------------------------------------------------------
 // Full dictionary lookup / insert for one staged row (any key length).  Returns the gid (or GID_DEFER_*).
-__device__ __noinline__ uint32_t agg_probe_slow(const AggParams& P, const uint8_t* key_smem, uint32_t len, uint32_t* slot_out) {
+// Out-parameters would live in local memory, and local loads queue behind the scattered traffic in the L1TEX FIFO:
+// the slot index comes back packed as (slot << 32) | gid.
+__device__ __noinline__ uint64_t agg_probe_slow(const AggParams& P, const uint8_t* key_smem, uint32_t len) {
   KeyRef k; load_key<true>(key_smem, len, k);
-  return dict_lookup(P.dict, k, true, slot_out);
+  uint32_t slot = 0; uint32_t g = dict_lookup(P.dict, k, true, &slot);
+  return ((uint64_t)slot << 32) | g;
 }
 // Accumulate one staged row through the general per-row path (pane from the timestamp, late panes, +-0.0, ...).
 __device__ __noinline__ void agg_apply_slow(const AggParams& P, const StageHdr& h, uint32_t r, long long ts, double v, uint32_t gid) {
   long long pane = (h.flags & TILE_PANE_UNIFORM) ? h.pane_lo : ts / P.panes.pane_ms;
   apply_row(P, h.tile_rel, r, pane, true, v, gid, h.rowseq0 + r);
+}
+// Lookup / insert of a parked row whose chain ended in an empty or locked slot (inline key rebuilt from its words).
+__device__ __noinline__ uint64_t agg_probe_words(const AggParams& P, uint4 kw, uint32_t len) {
+  KeyRef k; k.k0 = ((uint64_t)kw.y << 32) | kw.x; k.k1 = ((uint64_t)kw.w << 32) | kw.z; k.len = len; k.ptr = nullptr;
+  k.hash = hash_words(kw.x, kw.y, kw.z, kw.w, len);
+  uint32_t slot = 0; uint32_t g = dict_lookup(P.dict, k, false, &slot);
+  return ((uint64_t)slot << 32) | g;
 }
 __device__ __noinline__ void agg_tile_generic(const AggParams& P, uint32_t tile_rel, int tid) {
   const TileDesc td = P.tiles[P.tile_begin + tile_rel];
@@ -214,7 +243,56 @@ __device__ __noinline__ void agg_tile_generic(const AggParams& P, uint32_t tile_
   for (uint32_t r = tid; r < (uint32_t)td.n_rows; r += CONSUMER_WARPS * 32) process_row_generic(P, tile_rel, td, bd, r);
 }
 
-__global__ void __launch_bounds__(AGG_THREADS, 1) k_aggregate(const __grid_constant__ AggParams P) {
+// One full-warp probe round over the top (up to) 32 parked rows.  Rows that resolve are accumulated with scalar
+// reductions (count, sum, hint-gated min / max); rows that collide again are pushed back.  Returns the new queue length.
+__device__ __noinline__ uint32_t agg_queue_round(const AggParams& P, WarpQueue& Q, uint32_t qcount, int lane, bool use_hints) {
+  __syncwarp();
+  const uint32_t nb = min(qcount, 32u), base = qcount - nb;
+  const bool have = (uint32_t)lane < nb;
+  uint4 kw = make_uint4(0, 0, 0, 0); uint2 me = make_uint2(0, 0); uint32_t ro = 0; double v = 0.0;
+  bool again = false;
+  if (have) {
+    kw = Q.key[base + lane]; me = Q.meta[base + lane]; v = Q.val[base + lane]; ro = Q.row[base + lane];
+    const uint32_t len = me.y & 0xFFu, pi = me.y >> 8;
+    uint64_t sa, sb, sc, sd;
+    ld_slot(P.dict.slots + me.x, sa, sb, sc, sd);
+    const uint32_t state = (uint32_t)(sd >> 32);
+    uint32_t gid = 0, slot = me.x; uint64_t hint = 0; bool done = false;
+    if (state - 1u < 0xFFFFFFFEu) {
+      if ((uint32_t)sd == len && sa == (((uint64_t)kw.y << 32) | kw.x) && sb == (((uint64_t)kw.w << 32) | kw.z)) { gid = state - 1u; hint = sc; done = true; }
+      else { me.x = (me.x + 1u) & P.dict.mask; again = true; }
+    } else { const uint64_t gs = agg_probe_words(P, kw, len); gid = (uint32_t)gs; slot = (uint32_t)(gs >> 32); done = true; }
+    if (done) {
+      if (gid >= GID_DEFER_ARENA) defer_row(P.defer, ro >> 10, ro & 1023u, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
+      else {
+        GroupState* s = P.panes.main[pi] + gid;        // parked rows come from tiles with a plain main pane and v != +-0.0
+        const uint32_t tag = (uint32_t)P.panes.tag_main[pi];
+        const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v));
+        const bool okmin = v <= 1.7976931348623157e308, okmax = v >= -1.7976931348623157e308;
+        const uint32_t tmin = (uint32_t)((ORD_F64_MAX - o) >> 48), tmax = (uint32_t)((o - ORD_F64_MIN) >> 48);
+        uint32_t hmin = 0, hmax = 0;
+        const uint32_t htag = (uint32_t)(hint >> 32);
+        if (use_hints && htag == tag) { hmin = (uint32_t)(hint >> 16) & 0xFFFFu; hmax = (uint32_t)hint & 0xFFFFu; }
+        red_add_f64(&s->cnt, 1.0); red_add_f64(&s->sum, v);
+        if (okmin && tmin >= hmin) red_max_u64(&s->minkey, ORD_F64_MAX - o);
+        if (okmax && tmax >= hmax) red_max_u64(&s->maxkey, o - ORD_F64_MIN);
+        if (use_hints && (int32_t)(htag - tag) <= 0 && ((okmin && tmin > hmin) || (okmax && tmax > hmax))) {
+          const uint32_t nmin = okmin ? max(hmin, tmin) : hmin, nmax = okmax ? max(hmax, tmax) : hmax;
+          st_relaxed_u64(&P.dict.slots[slot].hint, ((uint64_t)tag << 32) | ((uint64_t)nmin << 16) | (uint64_t)nmax);
+        }
+      }
+    }
+  }
+  __syncwarp();                                        // every lane has read its entry before the survivors are re-packed
+  const uint32_t bal = __ballot_sync(0xffffffffu, again);
+  if (again) {
+    const uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
+    Q.key[pos] = kw; Q.meta[pos] = me; Q.val[pos] = v; Q.row[pos] = ro;
+  }
+  return base + __popc(bal);
+}
+
+__global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_constant__ AggParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   AggSmem& S = *reinterpret_cast<AggSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -232,165 +310,169 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) k_aggregate(const __grid_const
 
   if (warp == CONSUMER_WARPS) {
     // ------------------------------------------------------------ producer warp
-    uint32_t it = 0;
-    const int64_t stride = gridDim.x;
-    for (int64_t tb = P.tile_begin + blockIdx.x; tb < P.tile_end; tb += stride * 32) {
-      const int64_t t = tb + stride * lane;
-      TileDesc td; td.flags = 0; td.n_rows = 0;
-      const int64_t* gts = nullptr; const double* gval = nullptr; const int32_t* goff = nullptr; const uint8_t* gby = nullptr;
+    // Lane j owns tile (group * 32 + j) of this CTA's sequence.  The three dependent descriptor loads (TileDesc ->
+    // BatchDesc -> pane table) of the NEXT group are issued before the current group's copies are handed out, so their
+    // latency hides behind 32 tiles of work; the results wait in shared memory (no register pressure on the kernel).
+    auto fetch = [&](int64_t t, TileFetch& d) {
       StageHdr h; h.mbase = nullptr; h.tag = 0; h.pane_lo = 0; h.rowseq0 = 0; h.n_rows = 0; h.flags = 0; h.a0 = 0; h.tile_rel = 0;
       h.pad0 = 0; h.pad1 = h.pad2 = 0;
+      d.nts = d.noff = d.nby = 0;
       if (t < P.tile_end) {
-        td = P.tiles[t];
+        const TileDesc td = P.tiles[t];
         const BatchDesc& bd = P.batches[td.batch];
         h.n_rows = td.n_rows; h.flags = td.flags; h.pane_lo = td.pane_lo; h.tile_rel = (uint32_t)(t - P.tile_begin);
         h.a0 = (int32_t)(td.byte0 & ~(int64_t)15);
         h.rowseq0 = ((unsigned long long)bd.seq << 32) | (unsigned long long)(uint32_t)td.row0;
         if (td.flags & TILE_FAST) {
-          gts = bd.ts + td.row0; gval = bd.val + td.row0; goff = bd.off + td.row0; gby = bd.bytes + h.a0;
+          d.gts = bd.ts + td.row0; d.gval = bd.val + td.row0; d.goff = bd.off + td.row0; d.gby = bd.bytes + h.a0;
+          d.nts = round16((uint32_t)td.n_rows * 8u); d.noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
+          d.nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
           if (td.flags & TILE_PANE_UNIFORM) {
             int64_t pi = td.pane_lo - P.panes.pane0;
             if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) { h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; }
           }
         }
       }
-      for (int j = 0; j < 32; j++) {
-        if (tb + stride * j >= P.tile_end) break;                   // warp-uniform
-        const int s = it % STAGES;
-        if (lane == j) {
+      d.h = h;
+    };
+    uint32_t it = 0;
+    const int64_t stride = gridDim.x;
+    int buf = 0;
+    fetch(P.tile_begin + blockIdx.x + stride * lane, S.fetch[0][lane]);
+    for (int64_t tb = P.tile_begin + blockIdx.x; tb < P.tile_end; tb += stride * 32, buf ^= 1) {
+      fetch(tb + stride * (32 + lane), S.fetch[buf ^ 1][lane]);
+      __syncwarp();
+      if (lane == 0) {
+        for (int j = 0; j < 32 && tb + stride * j < P.tile_end; j++, it++) {
+          const int s = it % STAGES;
+          const TileFetch& f = S.fetch[buf][j];
           mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
-          S.st[s].hdr = h;
-          if (td.flags & TILE_FAST) {
-            uint32_t nts = round16((uint32_t)td.n_rows * 8u), noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
-            uint32_t nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
-            mbar_arrive_expect_tx(&S.full[s], nts * 2u + noff + nby);
-            bulk_g2s(S.st[s].ts, gts, nts, &S.full[s]);
-            bulk_g2s(S.st[s].val, gval, nts, &S.full[s]);
-            bulk_g2s(S.st[s].off, goff, noff, &S.full[s]);
-            if (nby) bulk_g2s(S.st[s].bytes, gby, nby, &S.full[s]);
+          S.st[s].hdr = f.h;
+          if (f.h.flags & TILE_FAST) {
+            mbar_arrive_expect_tx(&S.full[s], f.nts * 2u + f.noff + f.nby);
+            bulk_g2s(S.st[s].ts, f.gts, f.nts, &S.full[s]);
+            bulk_g2s(S.st[s].val, f.gval, f.nts, &S.full[s]);
+            bulk_g2s(S.st[s].off, f.goff, f.noff, &S.full[s]);
+            if (f.nby) bulk_g2s(S.st[s].bytes, f.gby, f.nby, &S.full[s]);
           } else {
             mbar_arrive(&S.full[s]);
           }
         }
-        it++;
-        __syncwarp();
       }
+      it = __shfl_sync(0xffffffffu, it, 0);
     }
     return;
   }
 
-  // -------------------------------------------------------------- consumer warps
+  // -------------------------------------------------------------- consumer warps: one row per thread
   const DictSlot* const slots = P.dict.slots;
   const uint32_t dmask = P.dict.mask;
-  const bool use_hints = !(P.flags & AGG_NO_HINTS);
-  const int odd = lane & 1;
-  uint32_t it = 0;
-  for (int64_t t = P.tile_begin + blockIdx.x; t < P.tile_end; t += gridDim.x, it++) {
+  const bool use_hints = !(P.flags & AGG_NO_HINTS), use_queue = !(P.flags & AGG_NO_QUEUE);
+  uint32_t qcount = 0;                 // warp-uniform
+  const uint32_t n_tiles = (uint32_t)(P.tile_end - P.tile_begin);
+  for (uint32_t it = 0; blockIdx.x + it * gridDim.x < n_tiles; it++) {
     const int s = it % STAGES;
     mbar_wait(&S.full[s], (it / STAGES) & 1u);
     const Stage& st = S.st[s];
     const StageHdr& H = st.hdr;
-    const int32_t hflags = H.flags;
-    if (!(hflags & TILE_FAST)) {
-      agg_tile_generic(P, H.tile_rel, tid);
+    // Everything derived from the thread index is recomputed per tile behind an opaque barrier: hoisted out of the loop
+    // these values (lane masks, shuffle sources, queue address) cost registers the 64-register budget does not have, and
+    // a spill is a local-memory access that queues behind the scattered traffic in the L1TEX FIFO.
+    uint32_t tix = (uint32_t)tid; asm volatile("" : "+r"(tix));
+    const int lane = (int)(tix & 31u), odd = (int)(tix & 1u);
+    WarpQueue& Q = S.q[tix >> 5];
+    if (!(H.flags & TILE_FAST)) {
+      agg_tile_generic(P, H.tile_rel, (int)tix);
     } else {
-      const uint32_t n = (uint32_t)H.n_rows;
-      const uint32_t r0 = 2u * (uint32_t)tid;
+      const uint32_t r = tix;
+      const bool live = r < (uint32_t)H.n_rows;
       GroupState* const mbase = H.mbase;
-      const uint32_t tag = H.tag;
-      const bool live[2] = {r0 < n, r0 + 1u < n};
-      const double2 vv = *reinterpret_cast<const double2*>(&st.val[r0]);
-      const int2 oo = *reinterpret_cast<const int2*>(&st.off[r0]);
-      const int32_t o2 = st.off[r0 + 2];
-      const double v[2] = {vv.x, vv.y};
-      const int32_t a0 = H.a0;
-      uint32_t klen[2], kb[2];
-      klen[0] = live[0] ? (uint32_t)(oo.y - oo.x) : 0u; kb[0] = live[0] ? (uint32_t)(oo.x - a0) : 0u;
-      klen[1] = live[1] ? (uint32_t)(o2 - oo.y) : 0u;   kb[1] = live[1] ? (uint32_t)(oo.y - a0) : 0u;
-      const uint32_t bytes_base = smem_u32(st.bytes);
-      uint32_t w[2][4], idx[2], gid[2]; uint64_t hint[2];
-      uint32_t todo = 0, slow = 0;
+      const double v = st.val[r];
+      const int32_t o0 = st.off[r], o1 = st.off[r + 1];
+      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - H.a0) : 0u;
+      const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, sh = (addr & 3u) * 8u;
+      uint32_t a[5];
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        const uint32_t addr = bytes_base + kb[i], q = addr & ~3u, sh = (addr & 3u) * 8u;
-        uint32_t a[5];
-#pragma unroll
-        for (int j = 0; j < 5; j++) a[j] = lds32(q + 4u * j);
-        const uint4 m = S.keymask[min(klen[i], (uint32_t)INLINE_KEY)];
-        w[i][0] = __funnelshift_r(a[0], a[1], sh) & m.x; w[i][1] = __funnelshift_r(a[1], a[2], sh) & m.y;
-        w[i][2] = __funnelshift_r(a[2], a[3], sh) & m.z; w[i][3] = __funnelshift_r(a[3], a[4], sh) & m.w;
-        idx[i] = hash_words(w[i][0], w[i][1], w[i][2], w[i][3], klen[i]) & dmask;
-        gid[i] = 0; hint[i] = 0;
-        if (live[i]) { if (klen[i] <= (uint32_t)INLINE_KEY) todo |= 1u << i; else slow |= 1u << i; }
+      for (int j = 0; j < 5; j++) a[j] = lds32(q + 4u * j);
+      const uint4 m = S.keymask[min(klen, (uint32_t)INLINE_KEY)];
+      const uint32_t w0 = __funnelshift_r(a[0], a[1], sh) & m.x, w1 = __funnelshift_r(a[1], a[2], sh) & m.y;
+      const uint32_t w2 = __funnelshift_r(a[2], a[3], sh) & m.z, w3 = __funnelshift_r(a[3], a[4], sh) & m.w;
+      uint32_t idx = hash_words(w0, w1, w2, w3, klen) & dmask;
+      // paired-path row: finite and not +-0.0 (everything else goes through the general per-row path)
+      const uint32_t bhi = (uint32_t)__double2hiint(v), blo = (uint32_t)__double2loint(v);
+      const bool plain = mbase != nullptr && (bhi & 0x7FF00000u) != 0x7FF00000u && ((bhi << 1) | blo) != 0u;
+      uint32_t gid = 0; uint64_t hint = 0;
+      bool need_slow = live && klen > (uint32_t)INLINE_KEY, park = false, hit = false;
+      // ONE dictionary probe (32 B sector, carries the group's min/max hint)
+      if (live && !need_slow) {
+        uint64_t sa, sb, sc, sd;
+        ld_slot(slots + idx, sa, sb, sc, sd);
+        const uint32_t state = (uint32_t)(sd >> 32);
+        if (state - 1u < 0xFFFFFFFEu) {                   // occupied and published
+          if ((uint32_t)sd == klen && (uint32_t)sa == w0 && (uint32_t)(sa >> 32) == w1 && (uint32_t)sb == w2 && (uint32_t)(sb >> 32) == w3) {
+            gid = state - 1u; hint = sc; hit = true;
+          } else if (use_queue && plain) { idx = (idx + 1u) & dmask; park = true; }   // chain continues: park, re-probe 32 at a time
+          else need_slow = true;
+        } else need_slow = true;                          // empty (insert) or locked (insert in flight)
       }
-      // dictionary probes: both rows' 32 B slot reads are issued before either is examined
-      while (todo) {
-        uint64_t sa[2], sb[2], sc[2], sd[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) if (todo & (1u << i)) ld_slot(slots + idx[i], sa[i], sb[i], sc[i], sd[i]);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          if (!(todo & (1u << i))) continue;
-          const uint32_t state = (uint32_t)(sd[i] >> 32);
-          if (state - 1u < 0xFFFFFFFEu) {                 // occupied and published
-            const bool eq = (uint32_t)sd[i] == klen[i] && sa[i] == (((uint64_t)w[i][1] << 32) | w[i][0]) && sb[i] == (((uint64_t)w[i][3] << 32) | w[i][2]);
-            if (eq) { gid[i] = state - 1u; hint[i] = sc[i]; todo &= ~(1u << i); } else idx[i] = (idx[i] + 1u) & dmask;
-          } else { slow |= 1u << i; todo &= ~(1u << i); }   // empty (insert) or locked (insert in flight)
+      const uint32_t bal = __ballot_sync(0xffffffffu, park);
+      if (bal) {
+        if (park) {
+          const uint32_t pos = qcount + __popc(bal & ((1u << lane) - 1u));
+          Q.key[pos] = make_uint4(w0, w1, w2, w3);
+          Q.meta[pos] = make_uint2(idx, klen | ((uint32_t)(H.pane_lo - P.panes.pane0) << 8));
+          Q.val[pos] = v;
+          Q.row[pos] = (H.tile_rel << 10) | r;
         }
+        qcount += __popc(bal);
       }
-      if (slow) {
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-          if (slow & (1u << i)) { gid[i] = agg_probe_slow(P, st.bytes + kb[i], klen[i], &idx[i]); hint[i] = 0; }
-      }
-      // hints + packing for the paired reductions
-      uint32_t pk[2];
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-        pk[i] = 0;
-        if (!live[i]) continue;
-        if (gid[i] >= GID_DEFER_ARENA) { defer_row(P.defer, H.tile_rel, r0 + i, gid[i] == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL); continue; }
-        if (mbase != nullptr && v[i] != 0.0) {
-          const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v[i]));
-          const bool okmin = v[i] <= 1.7976931348623157e308, okmax = v[i] >= -1.7976931348623157e308;   // false for NaN, +inf / -inf
-          const uint32_t tmin = (uint32_t)((ORD_F64_MAX - o) >> 48), tmax = (uint32_t)((o - ORD_F64_MIN) >> 48);
+      if (need_slow) { const uint64_t gs = agg_probe_slow(P, st.bytes + kb, klen); gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true; }
+      uint32_t pk = 0;
+      if (hit) {
+        if (gid >= GID_DEFER_ARENA) defer_row(P.defer, H.tile_rel, r, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
+        else if (plain) {
+          // hints: top 16 bits of minkey / maxkey follow from the high word of ord(v) alone (no borrow from the low word)
+          const uint32_t ohi = (bhi & 0x80000000u) ? ~bhi : (bhi | 0x80000000u);
+          const uint32_t tmin = (0xFFEFFFFFu - ohi) >> 16, tmax = (ohi - 0x00100000u) >> 16;
           uint32_t hmin = 0, hmax = 0;
-          if (use_hints && (uint32_t)(hint[i] >> 32) == tag) { hmin = (uint32_t)(hint[i] >> 16) & 0xFFFFu; hmax = (uint32_t)hint[i] & 0xFFFFu; }
-          const bool pmin = okmin && tmin >= hmin, pmax = okmax && tmax >= hmax;
-          if (use_hints && ((okmin && tmin > hmin) || (okmax && tmax > hmax))) {
-            const uint32_t nmin = okmin ? max(hmin, tmin) : hmin, nmax = okmax ? max(hmax, tmax) : hmax;
-            st_relaxed_u64(const_cast<uint64_t*>(&slots[idx[i]].hint), ((uint64_t)tag << 32) | ((uint64_t)nmin << 16) | (uint64_t)nmax);
-          }
-          pk[i] = gid[i] | (1u << 29) | (pmin ? 1u << 30 : 0u) | (pmax ? 1u << 31 : 0u);
+          const uint32_t tag = H.tag;
+          const uint32_t htag = (uint32_t)(hint >> 32);
+          if (use_hints && htag == tag) { hmin = (uint32_t)(hint >> 16) & 0xFFFFu; hmax = (uint32_t)hint & 0xFFFFu; }
+          // CTAs drift apart by up to a few million rows, so around a pane boundary two panes are in flight: a straggler of
+          // the OLDER pane (smaller tag; tags live in [1, 2^31)) never replaces the newer pane's hint -- it just reduces
+          if (use_hints && (int32_t)(htag - tag) <= 0 && (tmin > hmin || tmax > hmax))
+            st_relaxed_u64(const_cast<uint64_t*>(&slots[idx].hint), ((uint64_t)tag << 32) | ((uint64_t)max(hmin, tmin) << 16) | (uint64_t)max(hmax, tmax));
+          pk = gid | (1u << 29) | (tmin >= hmin ? 1u << 30 : 0u) | (tmax >= hmax ? 1u << 31 : 0u);
         } else {
-          agg_apply_slow(P, H, r0 + i, st.ts[r0 + i], v[i], gid[i]);
+          agg_apply_slow(P, H, r, st.ts[r], v, gid);
         }
       }
+      // reductions by lane pairs: lanes 2j / 2j+1 serve the row of lane j (+16): {cnt, sum} as one red.add.f64 pair,
+      // {minkey, maxkey} as one red.max.u64 pair -> 16 sectors per instruction
       if (mbase != nullptr) {                       // warp-uniform
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const uint32_t vlo = (uint32_t)__double2loint(v[i]), vhi = (uint32_t)__double2hiint(v[i]);
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-            const int src = (lane >> 1) + 16 * half;
-            const uint32_t pk2 = __shfl_sync(0xffffffffu, pk[i], src);
-            const uint32_t lo2 = __shfl_sync(0xffffffffu, vlo, src), hi2 = __shfl_sync(0xffffffffu, vhi, src);
-            if (pk2 & (1u << 29)) {
-              const double v2 = __hiloint2double((int)hi2, (int)lo2);
-              GroupState* s2 = mbase + (pk2 & 0x1FFFFFFFu);
-              red_add_f64(&s2->cnt + odd, odd ? v2 : 1.0);
-              if (pk2 & (odd ? 1u << 31 : 1u << 30)) {
-                const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v2));
-                red_max_u64(&s2->minkey + odd, odd ? o - ORD_F64_MIN : ORD_F64_MAX - o);
-              }
+        for (int half = 0; half < 2; half++) {
+          const int src = (lane >> 1) + 16 * half;
+          const uint32_t pk2 = __shfl_sync(0xffffffffu, pk, src);
+          const uint32_t lo2 = __shfl_sync(0xffffffffu, blo, src), hi2 = __shfl_sync(0xffffffffu, bhi, src);
+          if (pk2 & (1u << 29)) {
+            GroupState* s2 = mbase + (pk2 & 0x1FFFFFFFu);
+            red_add_f64(&s2->cnt + odd, odd ? __hiloint2double((int)hi2, (int)lo2) : 1.0);
+            if (pk2 & (odd ? 1u << 31 : 1u << 30)) {
+              const bool neg = hi2 & 0x80000000u;
+              const uint32_t olo = neg ? ~lo2 : lo2, oh = neg ? ~hi2 : (hi2 | 0x80000000u);           // ord(v), halves
+              const uint32_t klo = odd ? olo : ~olo, khi = odd ? oh - 0x00100000u : 0xFFEFFFFFu - oh;  // maxkey : minkey
+              red_max_u64(&s2->minkey + odd, ((unsigned long long)khi << 32) | klo);
             }
           }
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty[s]);
+    if (lane == 0) mbar_arrive_relaxed(&S.empty[s]);
+    while (qcount >= 32u) qcount = agg_queue_round(P, Q, qcount, lane, use_hints);
   }
+  while (qcount > 0u) qcount = agg_queue_round(P, S.q[warp], qcount, lane, use_hints);
 }
 
 static int g_agg_smem = 0;
@@ -403,7 +485,7 @@ cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s) {
   int64_t n_tiles = p.tile_end - p.tile_begin;
   if (n_tiles <= 0) return cudaSuccess;
   if (!g_agg_smem) { cudaError_t e = agg_kernel_setup(); if (e != cudaSuccess) return e; }
-  int grid = (int)(n_tiles < (int64_t)sm_count ? n_tiles : (int64_t)sm_count);
+  int grid = (int)(n_tiles < (int64_t)sm_count * 2 ? n_tiles : (int64_t)sm_count * 2);     // two persistent CTAs per SM
   k_aggregate<<<grid, AGG_THREADS, g_agg_smem, s>>>(p);
   return cudaGetLastError();
 }

@@ -471,7 +471,7 @@ std::unique_ptr<Pane> dnz_window::new_pane(int64_t id) {
   if (!pane_pool.empty()) { p = std::move(pane_pool.back()); pane_pool.pop_back(); }
   else { p.reset(new Pane()); p->st.alloc((size_t)gcap * sizeof(GroupState)); }
   p->id = id;
-  if ((uint32_t)next_tag == 0) {      // 2^32 pane instances later the 32-bit tags would repeat: drop every hint first
+  if (next_tag >= (1ull << 31)) {     // tags live in [1, 2^31) so that "newer" is a signed 32-bit difference: drop every hint, restart
     CK(launch_clear_hints(slots.as<DictSlot>(), dict_cap, stream)); stats.total_launches++;
     next_tag = 1;
   }
@@ -806,7 +806,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
       AggParams P;
       P.batches = cur_scan->d_batches.as<BatchDesc>(); P.tiles = cur_scan->d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
       P.dict = dict_view();
-      P.flags = (cfg.flags & DNZ_FLAG_NO_HINTS) ? AGG_NO_HINTS : 0;
+      P.flags = ((cfg.flags & DNZ_FLAG_NO_HINTS) ? AGG_NO_HINTS : 0) | ((cfg.flags & DNZ_FLAG_NO_QUEUE) ? AGG_NO_QUEUE : 0);
       char* dp = d_ptrs.as<char>();
       P.panes.pane0 = pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
       P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
