@@ -37,6 +37,8 @@ WORKLOADS = {
     "cfg2": dict(rows=1_000_000_000, groups=100_000, rows_per_ms=10_000, window_ms=1000, slide_ms=0, filt=None, uuid=False),
     "cfg3": dict(rows=1_000_000_000, groups=1_000_000, rows_per_ms=10_000, window_ms=10_000, slide_ms=1000, filt=None, uuid=False),
     "cfg4": dict(rows=1_000_000_000, groups=100_000, rows_per_ms=10_000, window_ms=1000, slide_ms=0, filt=("max", ">", 113.0), uuid=False),
+    # experiment only (not a BASELINE config): cfg2 with ONE pane for the whole stream -- isolates pane-boundary effects
+    "cfg2w": dict(rows=1_000_000_000, groups=100_000, rows_per_ms=10_000, window_ms=1_000_000, slide_ms=0, filt=None, uuid=False),
     "cfg5": dict(rows=1_000_000_000, groups=10_000_000, rows_per_ms=8_000, window_ms=60_000, slide_ms=5000, filt=None, uuid=True),
 }
 BATCH_ROWS = 65536

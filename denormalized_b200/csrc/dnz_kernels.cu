@@ -157,11 +157,10 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 // =================================================================================================
 // k_aggregate: persistent (two CTAs of 17 warps per SM), warp-specialised.
 //
-// Warp 16 is the TMA producer.  Its 32 lanes fetch the descriptors of the CTA's next 32 tiles in parallel (TileDesc ->
-// BatchDesc -> pane table: three dependent global loads that would otherwise serialise per tile), then take turns: wait
-// for the ring slot, write the tile header (row count, key byte base, resolved pane state array + hint tag) into shared
-// memory and issue four 1-D bulk copies (timestamps, values, key offsets, key bytes; SASS UBLKCP) that complete on the
-// slot's `full` mbarrier.
+// The last warp is the TMA producer.  It claims tiles from a global counter (stream order), resolves their descriptors,
+// and per tile: waits for the ring slot, writes the tile header (row count, key byte base, resolved pane state array +
+// hint tag) into shared memory and issues four 1-D bulk copies (timestamps, values, key offsets, key bytes; SASS
+// UBLKCP) that complete on the slot's `full` mbarrier.
 //
 // Warps 0-15 consume, one row per thread (8 consumer warps per scheduler across the two CTAs hide the L2 round trip of
 // the probe).  Hot path per row: 3 LDS for value/offsets, 5 LDS.32 + funnel shifts + one LDS.128 mask for the <= 16 B
@@ -206,7 +205,7 @@ struct __align__(16) TileFetch {     // what the producer needs to hand one tile
 struct AggSmem {
   Stage st[STAGES];
   WarpQueue q[CONSUMER_WARPS];
-  TileFetch fetch[2][32];
+  TileFetch fetch[1][8];
   uint4 keymask[INLINE_KEY + 1];     // keymask[len] = byte mask of a len-byte key in four 32-bit words
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -310,9 +309,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
 
   if (warp == CONSUMER_WARPS) {
     // ------------------------------------------------------------ producer warp
-    // Lane j owns tile (group * 32 + j) of this CTA's sequence.  The three dependent descriptor loads (TileDesc ->
-    // BatchDesc -> pane table) of the NEXT group are issued before the current group's copies are handed out, so their
-    // latency hides behind 32 tiles of work; the results wait in shared memory (no register pressure on the kernel).
+    // Lanes 0..CLAIM-1 resolve the descriptors of the claimed tiles in parallel (TileDesc -> BatchDesc -> pane table: three
+    // dependent global loads that would otherwise serialise per tile) into shared memory; lane 0 then feeds the ring.
     auto fetch = [&](int64_t t, TileFetch& d) {
       StageHdr h; h.mbase = nullptr; h.tag = 0; h.pane_lo = 0; h.rowseq0 = 0; h.n_rows = 0; h.flags = 0; h.a0 = 0; h.tile_rel = 0;
       h.pad0 = 0; h.pad1 = h.pad2 = 0;
@@ -335,17 +333,23 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
       }
       d.h = h;
     };
+    // Tiles are claimed dynamically, CLAIM at a time, in stream order: all CTAs then work within a few hundred tiles of each
+    // other, so that two panes are in flight only for ~1 % of the rows around a pane boundary (hints of the older pane are
+    // dead once the newer pane's rows arrive) and the tail of the launch balances itself.
+    constexpr uint32_t CLAIM = 4;
+    const uint32_t n_tiles = (uint32_t)(P.tile_end - P.tile_begin);
     uint32_t it = 0;
-    const int64_t stride = gridDim.x;
-    int buf = 0;
-    fetch(P.tile_begin + blockIdx.x + stride * lane, S.fetch[0][lane]);
-    for (int64_t tb = P.tile_begin + blockIdx.x; tb < P.tile_end; tb += stride * 32, buf ^= 1) {
-      fetch(tb + stride * (32 + lane), S.fetch[buf ^ 1][lane]);
+    for (;;) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(P.tile_counter, CLAIM);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= n_tiles) break;
+      if (lane < (int)CLAIM) fetch(P.tile_begin + base + lane, S.fetch[0][lane]);
       __syncwarp();
       if (lane == 0) {
-        for (int j = 0; j < 32 && tb + stride * j < P.tile_end; j++, it++) {
+        for (uint32_t j = 0; j < CLAIM && base + j < n_tiles; j++, it++) {
           const int s = it % STAGES;
-          const TileFetch& f = S.fetch[buf][j];
+          const TileFetch& f = S.fetch[0][j];
           mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
           S.st[s].hdr = f.h;
           if (f.h.flags & TILE_FAST) {
@@ -361,6 +365,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
       }
       it = __shfl_sync(0xffffffffu, it, 0);
     }
+    if (lane == 0) {                                   // end marker for the consumers
+      const int s = it % STAGES;
+      mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
+      S.st[s].hdr.flags = TILE_END;
+      mbar_arrive(&S.full[s]);
+    }
     return;
   }
 
@@ -369,12 +379,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
   const uint32_t dmask = P.dict.mask;
   const bool use_hints = !(P.flags & AGG_NO_HINTS), use_queue = !(P.flags & AGG_NO_QUEUE);
   uint32_t qcount = 0;                 // warp-uniform
-  const uint32_t n_tiles = (uint32_t)(P.tile_end - P.tile_begin);
-  for (uint32_t it = 0; blockIdx.x + it * gridDim.x < n_tiles; it++) {
+  for (uint32_t it = 0;; it++) {
     const int s = it % STAGES;
     mbar_wait(&S.full[s], (it / STAGES) & 1u);
     const Stage& st = S.st[s];
     const StageHdr& H = st.hdr;
+    if (H.flags & TILE_END) break;
     // Everything derived from the thread index is recomputed per tile behind an opaque barrier: hoisted out of the loop
     // these values (lane masks, shuffle sources, queue address) cost registers the 64-register budget does not have, and
     // a spill is a local-memory access that queues behind the scattered traffic in the L1TEX FIFO.

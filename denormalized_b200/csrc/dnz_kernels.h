@@ -18,6 +18,7 @@ enum : int32_t {
   TILE_FAST = 1,          // all four column slices can be staged with cp.async.bulk (16 B aligned, fits BCAP, no bitmaps)
   TILE_PANE_UNIFORM = 2,  // every valid timestamp of the tile falls in pane_lo
   TILE_EMPTY = 4,         // no valid timestamp
+  TILE_END = 8,           // (stage header only) no more tiles for this CTA
 };
 
 struct BatchDesc {
@@ -94,6 +95,7 @@ struct AggParams {
   const BatchDesc* batches; const TileDesc* tiles; int64_t tile_begin, tile_end;
   DictView dict; PaneTable panes; DeferList defer;
   uint32_t flags;
+  uint32_t* tile_counter;   // zeroed per launch: CTAs claim tiles in stream order (keeps the tiles in flight within ~1 % of a pane)
 };
 enum : uint32_t { AGG_NO_HINTS = 1, AGG_NO_QUEUE = 2 };   // experiments: reduce min/max for every row; loop on collisions
 

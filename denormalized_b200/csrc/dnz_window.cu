@@ -818,6 +818,7 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
       P.defer.entries = d_defer[out_list].as<DeferEntry>();
       P.defer.count = reinterpret_cast<unsigned long long*>(ctl(64)); P.defer.cap = defer_cap;
       P.defer.flags = reinterpret_cast<uint32_t*>(ctl(72));
+      P.tile_counter = reinterpret_cast<uint32_t*>(ctl(76));     // zeroed with the deferred-row counters above
       const bool timing = iter == 0 && (cfg.flags & DNZ_FLAG_KERNEL_TIMING);
       if (iter == 0) {
         if (timing) CK(cudaEventRecord(ev0, stream));
