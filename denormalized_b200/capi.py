@@ -85,7 +85,7 @@ class StatsC(C.Structure):
 EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_ready",
            "dnz_window_poll_device",
            "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
-           "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_export_partials",
+           "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
            "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free"]
 
@@ -127,6 +127,8 @@ def lib():
         L.dnz_window_last_error.restype = C.c_char_p
         L.dnz_window_last_error.argtypes = [C.c_void_p]
         L.dnz_window_destroy.argtypes = [C.c_void_p]
+        L.dnz_window_reserve_input.restype = C.c_int32
+        L.dnz_window_reserve_input.argtypes = [C.c_void_p, C.c_int64]
         L.dnz_window_set_exchange.restype = C.c_int32
         L.dnz_window_set_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.dnz_host_alloc.restype = C.c_void_p
@@ -303,6 +305,9 @@ class GpuStreamingWindow:
     def watermark(self):
         v = int(self._L.dnz_window_watermark(self._h))
         return None if v == -(2 ** 63) else v
+
+    def reserve_input(self, bytes_per_launch):
+        self._check(self._L.dnz_window_reserve_input(self._h, int(bytes_per_launch)))
 
     def set_exchange(self, rank, world):
         self._check(self._L.dnz_window_set_exchange(self._h, rank, world))

@@ -166,10 +166,17 @@ struct Superbatch {
   std::vector<CopyDesc> gather;       // pinned host buffers pulled by one k_gather_copy launch when the superbatch is sealed
 };
 
-struct ResultSet {             // device columns of the rows emitted since the last poll
+// Device columns of emitted rows.  Two sets: emission appends to one of them; a set whose rows have all been handed out is
+// reset and becomes the next target, so a consumer that polls while input keeps streaming never makes the operator wait.
+// What may be handed out is decided by SNAPSHOTS: after every group of emit launches the cursor is copied to pinned memory
+// and an event is recorded; once the event has fired, rows below the snapshot are complete and stable (append-only).
+struct ResultSet {
   DevBuf key_off, key_bytes, key_valid, count, mn, mx, avg, sum, agg_valid, wstart, wend;
   uint64_t row_cap = 0, byte_cap = 0;
-  uint64_t rows = 0, bytes = 0;   // host view of the cursor (exact after sync_cursor)
+  uint64_t rows = 0, bytes = 0;           // host view of the cursor (exact after fetch_ctl)
+  uint64_t exp_rows = 0, exp_bytes = 0;   // prefix already handed to the consumer
+  size_t ctl_off = 128;                   // cursor (u64) + overflow flag (u32) inside the control block
+  PinnedBuf snap; cudaEvent_t snap_ev = nullptr; bool snap_issued = false;
 };
 
 enum { COL_COUNT = 0, COL_MIN = 1, COL_MAX = 2, COL_AVG = 3, COL_SUM = 4 };
@@ -219,7 +226,10 @@ struct dnz_window {
   Scan* cur_scan = nullptr;
   DevBuf d_ptrs, d_defer[2];
   PinnedBuf h_stage, h_small;
-  ResultSet res; bool res_consumed = false; bool ctl_fresh = false;
+  ResultSet rs[2]; int wr = 0; bool async_polls = false;
+  ResultSet& R() { return rs[wr]; }
+  cudaStream_t d2h_stream = nullptr;
+  bool res_consumed = false; bool ctl_fresh = false;
 
   // multi-GPU
   int rank = 0, world = 1;
@@ -254,7 +264,11 @@ struct dnz_window {
   void emit_normal(int64_t wm_new);
   void ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes);
   void reset_results();
-  void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output);
+  void reset_set(int i);
+  void snapshot_results();
+  void rotate_result_sets();
+  bool set_drained(ResultSet& r);
+  void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking);
   void fill_schema(ArrowSchema* schema);
 };
 
@@ -319,6 +333,8 @@ dnz_window::~dnz_window() {
   for (Superbatch* sb : {&cur, &sealed}) for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
   if (stream) cudaStreamSynchronize(stream);
   if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
+  for (auto& r : rs) if (r.snap_ev) cudaEventDestroy(r.snap_ev);
   for (auto& e : copy_done) if (e) cudaEventDestroy(e);
   for (auto& sc : scan) if (sc.done) cudaEventDestroy(sc.done);
   if (ev0) cudaEventDestroy(ev0);
@@ -388,6 +404,9 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   if (c->cuda_stream) { stream = (cudaStream_t)c->cuda_stream; own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
   CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+  rs[0].ctl_off = 128; rs[1].ctl_off = 160;
+  for (auto& r : rs) { CK(cudaEventCreateWithFlags(&r.snap_ev, cudaEventDisableTiming)); r.snap.reserve(64); }
   for (auto& e : copy_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(agg_kernel_setup());
@@ -460,9 +479,11 @@ void dnz_window::fetch_ctl() {
   key_bytes_total_host = *reinterpret_cast<const uint64_t*>(h + 16);
   defer_count_host = *reinterpret_cast<const uint64_t*>(h + 64);
   defer_flags_host = *reinterpret_cast<const uint32_t*>(h + 72);
-  uint64_t c = *reinterpret_cast<const uint64_t*>(h + 128);
-  res.rows = c >> 32; res.bytes = c & 0xFFFFFFFFull;
-  if (*reinterpret_cast<const uint32_t*>(h + 136)) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+  for (auto& r : rs) {
+    uint64_t c = *reinterpret_cast<const uint64_t*>(h + r.ctl_off);
+    r.rows = c >> 32; r.bytes = c & 0xFFFFFFFFull;
+    if (*reinterpret_cast<const uint32_t*>(h + r.ctl_off + 8)) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+  }
   stats.groups = n_groups_host;
 }
 
@@ -578,6 +599,7 @@ void dnz_window::push_host(ArrowArray* batch) {
   cur.batches.push_back(pb);
   cur.rows += n;
   stats.batches_in++; stats.rows_in += n;
+  if (cur.rows >= max_rows) seal_current();      // full: its transfer starts now, not when the next batch happens to arrive
 }
 
 void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
@@ -658,6 +680,7 @@ void dnz_window::launch_scan(Superbatch& sb) {
 void dnz_window::process_superbatch(Superbatch& sb) {
   if (sb.batches.empty()) return;
   if (res_consumed) reset_results();
+  rotate_result_sets();
   struct Cleanup {
     dnz_window* w; Superbatch* sb;
     ~Cleanup() {
@@ -892,32 +915,56 @@ void dnz_window::emit_normal(int64_t wm_new) {
 }
 
 void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
-  uint64_t need_rows = res.rows + add_rows, need_bytes = res.bytes + add_bytes;
+  uint64_t need_rows = R().rows + add_rows, need_bytes = R().bytes + add_bytes;
   if (need_bytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes between polls (Utf8 offsets are 32-bit); poll more often");
-  if (need_rows <= res.row_cap && need_bytes <= res.byte_cap) return;
+  if (need_rows <= R().row_cap && need_bytes <= R().byte_cap) return;
   auto grow = [&](DevBuf& b, size_t elem, uint64_t used, uint64_t cap) {
     DevBuf nb; nb.alloc((size_t)cap * elem + 64);
     if (used && b.p) CK(cudaMemcpyAsync(nb.p, b.p, (size_t)used * elem, cudaMemcpyDeviceToDevice, stream));
     CK(cudaStreamSynchronize(stream));
     b = std::move(nb);
   };
-  if (need_rows > res.row_cap) {
-    uint64_t cap = std::max<uint64_t>(need_rows, res.row_cap * 2);
-    grow(res.key_off, 4, res.rows, cap + 1); grow(res.key_valid, 1, res.rows, cap); grow(res.count, 8, res.rows, cap);
-    grow(res.mn, 8, res.rows, cap); grow(res.mx, 8, res.rows, cap); grow(res.avg, 8, res.rows, cap); grow(res.sum, 8, res.rows, cap);
-    grow(res.agg_valid, 1, res.rows, cap); grow(res.wstart, 8, res.rows, cap); grow(res.wend, 8, res.rows, cap);
-    res.row_cap = cap;
+  if (need_rows > R().row_cap) {
+    uint64_t cap = std::max<uint64_t>(need_rows, R().row_cap * 2);
+    grow(R().key_off, 4, R().rows, cap + 1); grow(R().key_valid, 1, R().rows, cap); grow(R().count, 8, R().rows, cap);
+    grow(R().mn, 8, R().rows, cap); grow(R().mx, 8, R().rows, cap); grow(R().avg, 8, R().rows, cap); grow(R().sum, 8, R().rows, cap);
+    grow(R().agg_valid, 1, R().rows, cap); grow(R().wstart, 8, R().rows, cap); grow(R().wend, 8, R().rows, cap);
+    R().row_cap = cap;
   }
-  if (need_bytes > res.byte_cap) {
-    uint64_t cap = std::max<uint64_t>(need_bytes, res.byte_cap * 2);
-    grow(res.key_bytes, 1, res.bytes, cap);
-    res.byte_cap = cap;
+  if (need_bytes > R().byte_cap) {
+    uint64_t cap = std::max<uint64_t>(need_bytes, R().byte_cap * 2);
+    grow(R().key_bytes, 1, R().bytes, cap);
+    R().byte_cap = cap;
   }
 }
 
-void dnz_window::reset_results() {
-  CK(cudaMemsetAsync(ctl(128), 0, 16, stream));
-  res.rows = 0; res.bytes = 0; res_consumed = false;
+void dnz_window::reset_set(int i) {
+  ResultSet& r = rs[i];
+  CK(cudaMemsetAsync(ctl(r.ctl_off), 0, 16, stream));
+  r.rows = 0; r.bytes = 0; r.exp_rows = 0; r.exp_bytes = 0; r.snap_issued = false;
+}
+void dnz_window::reset_results() { reset_set(wr); res_consumed = false; }
+
+// cursor of the current set -> pinned memory, in stream order behind the emit launches
+void dnz_window::snapshot_results() {
+  ResultSet& r = R();
+  CK(cudaMemcpyAsync(r.snap.p, ctl(r.ctl_off), 16, cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(r.snap_ev, stream));
+  r.snap_issued = true;
+}
+// every row of the set has been handed out and nothing is in flight for it
+bool dnz_window::set_drained(ResultSet& r) {
+  if (!r.snap_issued) return r.exp_rows == r.rows;
+  if (cudaEventQuery(r.snap_ev) != cudaSuccess) { cudaGetLastError(); return false; }
+  uint64_t c = *reinterpret_cast<volatile uint64_t*>(r.snap.p);
+  return (c >> 32) == r.exp_rows;
+}
+// Called before a superbatch's emits are enqueued (only matters when the consumer uses the non-blocking poll): reuse the
+// current set in place when it is drained, else switch to the other one if that is drained, else keep appending.
+void dnz_window::rotate_result_sets() {
+  if (!async_polls) return;
+  if (set_drained(rs[wr])) { if (rs[wr].exp_rows) reset_set(wr); return; }
+  if (set_drained(rs[wr ^ 1])) { if (rs[wr ^ 1].exp_rows || rs[wr ^ 1].rows) reset_set(wr ^ 1); wr ^= 1; }
 }
 
 // One k_emit launch per window: combine its panes, apply the fused FilterExec predicate, compact.
@@ -943,14 +990,15 @@ void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map
     E.filter_col = cfg.has_filter ? aggs[cfg.filter_agg].kind : 0; E.filter_op = cfg.filter_op; E.filter_lit = cfg.filter_literal;
     E.wstart = s; E.wend = s + L; E.n_groups = n_groups_host; E.rank = rank; E.world = world;
     E.dict = dict_view();
-    E.out.key_off = res.key_off.as<int32_t>(); E.out.key_bytes = res.key_bytes.as<uint8_t>(); E.out.key_valid = res.key_valid.as<uint8_t>();
-    E.out.count = res.count.as<int64_t>(); E.out.mn = res.mn.as<double>(); E.out.mx = res.mx.as<double>(); E.out.avg = res.avg.as<double>();
-    E.out.sum = res.sum.as<double>(); E.out.agg_valid = res.agg_valid.as<uint8_t>(); E.out.wstart = res.wstart.as<int64_t>(); E.out.wend = res.wend.as<int64_t>();
-    E.out.cursor = reinterpret_cast<unsigned long long*>(ctl(128)); E.out.row_cap = res.row_cap; E.out.byte_cap = res.byte_cap;
-    E.out.overflow = reinterpret_cast<uint32_t*>(ctl(136));
+    E.out.key_off = R().key_off.as<int32_t>(); E.out.key_bytes = R().key_bytes.as<uint8_t>(); E.out.key_valid = R().key_valid.as<uint8_t>();
+    E.out.count = R().count.as<int64_t>(); E.out.mn = R().mn.as<double>(); E.out.mx = R().mx.as<double>(); E.out.avg = R().avg.as<double>();
+    E.out.sum = R().sum.as<double>(); E.out.agg_valid = R().agg_valid.as<uint8_t>(); E.out.wstart = R().wstart.as<int64_t>(); E.out.wend = R().wend.as<int64_t>();
+    E.out.cursor = reinterpret_cast<unsigned long long*>(ctl(R().ctl_off)); E.out.row_cap = R().row_cap; E.out.byte_cap = R().byte_cap;
+    E.out.overflow = reinterpret_cast<uint32_t*>(ctl(R().ctl_off + 8));
     CK(launch_emit(E, stream));
     stats.total_launches++; stats.windows_emitted++;
   }
+  snapshot_results();
   ctl_fresh = false;
 }
 
@@ -976,9 +1024,27 @@ void dnz_window::fill_schema(ArrowSchema* schema) {
   schema->release = release_schema; schema->private_data = sp;
 }
 
-void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output) {
-  fetch_ctl(); ctl_fresh = false;
-  const uint64_t n = res.rows, nbytes = res.bytes;
+// Hands out every emitted row that is COMPLETE on the device: per result set, the rows between what was exported before and
+// the newest snapshot whose event has fired (older set first).  `blocking` callers have synchronised the stream, so every
+// snapshot has fired; the non-blocking poll simply leaves rows of still-running emits for the next call.  The device->host
+// copies run on their own stream, never behind queued input.
+void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking) {
+  if (blocking) { CK(cudaStreamSynchronize(stream)); }
+  struct Range { ResultSet* r; uint64_t r0, r1, b0, b1; };
+  std::vector<Range> ranges;
+  for (int k = 0; k < 2; k++) {
+    ResultSet& r = rs[k == 0 ? (wr ^ 1) : wr];
+    if (!r.snap_issued) continue;
+    if (cudaEventQuery(r.snap_ev) != cudaSuccess) { cudaGetLastError(); continue; }
+    const volatile uint64_t* sp = reinterpret_cast<volatile uint64_t*>(r.snap.p);
+    const uint64_t c = sp[0];
+    if (static_cast<uint32_t>(sp[1])) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+    const uint64_t rows = c >> 32, bytes = c & 0xFFFFFFFFull;
+    if (rows > r.exp_rows) ranges.push_back(Range{&r, r.exp_rows, rows, r.exp_bytes, bytes});
+  }
+  uint64_t n = 0, nbytes = 0;
+  for (auto& g : ranges) { n += g.r1 - g.r0; nbytes += g.b1 - g.b0; }
+  if (nbytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes in one poll (Utf8 offsets are 32-bit); poll more often");
   auto* ep = new ExportPrivate();
   std::unique_ptr<ExportPrivate> guard(ep);
   const size_t total = round_up((n + 1) * 4, 64) + round_up(nbytes, 64) + 2 * round_up(n, 64) + 7 * round_up(n * 8, 64) +
@@ -986,21 +1052,35 @@ void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has
   ep->block = g_pinned_pool.get(total, ep->block_cap);
   size_t used = 0;
   auto pinned = [&](size_t bytes) -> void* { void* p = (char*)ep->block + used; used += round_up(std::max<size_t>(bytes, 8), 64); return p; };
-  auto fetch = [&](const DevBuf& b, size_t bytes) -> void* {
-    void* h = pinned(bytes);
-    if (bytes) { CK(cudaMemcpyAsync(h, b.p, bytes, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (int64_t)bytes; }
+  // one column of every range, back to back
+  auto fetch = [&](DevBuf ResultSet::*col, size_t elem, bool by_bytes, size_t extra) -> void* {
+    char* h = (char*)pinned((by_bytes ? nbytes : n) * elem + extra);
+    size_t at = 0;
+    for (auto& g : ranges) {
+      const uint64_t lo = by_bytes ? g.b0 : g.r0, hi = by_bytes ? g.b1 : g.r1;
+      const size_t bytes = (size_t)(hi - lo) * elem;
+      if (bytes) { CK(cudaMemcpyAsync(h + at, (g.r->*col).template as<char>() + lo * elem, bytes, cudaMemcpyDeviceToHost, d2h_stream)); stats.d2h_bytes += (int64_t)bytes; }
+      at += bytes;
+    }
     return h;
   };
-  int32_t* koff = (int32_t*)pinned((n + 1) * 4);
-  if (n) { CK(cudaMemcpyAsync(koff, res.key_off.p, n * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (int64_t)n * 4; }
-  uint8_t* kbytes = (uint8_t*)fetch(res.key_bytes, nbytes);
-  uint8_t* kvalid = (uint8_t*)fetch(res.key_valid, n);
-  int64_t* count = (int64_t*)fetch(res.count, n * 8);
-  double* mn = (double*)fetch(res.mn, n * 8); double* mx = (double*)fetch(res.mx, n * 8);
-  double* avg = (double*)fetch(res.avg, n * 8); double* sum = (double*)fetch(res.sum, n * 8);
-  uint8_t* avalid = (uint8_t*)fetch(res.agg_valid, n);
-  int64_t* ws = (int64_t*)fetch(res.wstart, n * 8); int64_t* we = (int64_t*)fetch(res.wend, n * 8);
-  CK(cudaStreamSynchronize(stream));
+  int32_t* koff = (int32_t*)fetch(&ResultSet::key_off, 4, false, 4);
+  uint8_t* kbytes = (uint8_t*)fetch(&ResultSet::key_bytes, 1, true, 0);
+  uint8_t* kvalid = (uint8_t*)fetch(&ResultSet::key_valid, 1, false, 0);
+  int64_t* count = (int64_t*)fetch(&ResultSet::count, 8, false, 0);
+  double* mn = (double*)fetch(&ResultSet::mn, 8, false, 0); double* mx = (double*)fetch(&ResultSet::mx, 8, false, 0);
+  double* avg = (double*)fetch(&ResultSet::avg, 8, false, 0); double* sum = (double*)fetch(&ResultSet::sum, 8, false, 0);
+  uint8_t* avalid = (uint8_t*)fetch(&ResultSet::agg_valid, 1, false, 0);
+  int64_t* ws = (int64_t*)fetch(&ResultSet::wstart, 8, false, 0); int64_t* we = (int64_t*)fetch(&ResultSet::wend, 8, false, 0);
+  CK(cudaStreamSynchronize(d2h_stream));
+  {   // key offsets are relative to each set's byte buffer: rebase them onto the concatenated export
+    uint64_t row_at = 0, byte_at = 0;
+    for (auto& g : ranges) {
+      const int64_t delta = (int64_t)byte_at - (int64_t)g.b0;
+      if (delta != 0) for (uint64_t i = row_at; i < row_at + (g.r1 - g.r0); i++) koff[i] = (int32_t)(koff[i] + delta);
+      row_at += g.r1 - g.r0; byte_at += g.b1 - g.b0;
+    }
+  }
   koff[n] = (int32_t)nbytes;
   // byte-per-row validity -> Arrow bitmaps
   auto pack = [&](const uint8_t* v, int64_t& nulls) -> uint8_t* {
@@ -1046,7 +1126,10 @@ void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has
   if (schema) fill_schema(schema);
   if (has_output) *has_output = n > 0;
   stats.rows_out += (int64_t)n;
-  reset_results();
+  for (auto& g : ranges) { g.r->exp_rows = g.r1; g.r->exp_bytes = g.b1; }
+  if (blocking) {         // stream idle: drained sets can be recycled right away
+    for (int i = 0; i < 2; i++) if (rs[i].exp_rows && set_drained(rs[i])) reset_set(i);
+  }
 }
 
 // =================================================================================================
@@ -1103,7 +1186,7 @@ int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchem
   if (!out) fail(DNZ_ERR_INVALID, "null out");
   w->process_pending();
   if (w->res_consumed) w->reset_results();
-  w->export_arrow(out, out_schema, has_output);
+  w->export_arrow(out, out_schema, has_output, true);
   DNZ_CATCH(w)
 }
 
@@ -1111,7 +1194,8 @@ int32_t dnz_window_poll_ready(dnz_window* w, struct ArrowArray* out, struct Arro
   DNZ_TRY(w)
   if (!out) fail(DNZ_ERR_INVALID, "null out");
   if (w->res_consumed) w->reset_results();
-  w->export_arrow(out, out_schema, has_output);
+  w->async_polls = true;
+  w->export_arrow(out, out_schema, has_output, false);
   DNZ_CATCH(w)
 }
 
@@ -1121,12 +1205,14 @@ int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out) {
   w->process_pending();
   if (w->res_consumed) w->reset_results();
   w->fetch_ctl(); w->ctl_fresh = false;
-  out->n_rows = (int64_t)w->res.rows; out->key_bytes_len = (int64_t)w->res.bytes;
-  out->key_off = w->res.key_off.as<int32_t>(); out->key_bytes = w->res.key_bytes.as<uint8_t>(); out->key_valid = w->res.key_valid.as<uint8_t>();
-  out->count = w->res.count.as<int64_t>(); out->min = w->res.mn.as<double>(); out->max = w->res.mx.as<double>();
-  out->avg = w->res.avg.as<double>(); out->sum = w->res.sum.as<double>(); out->agg_valid = w->res.agg_valid.as<uint8_t>();
-  out->window_start_ms = w->res.wstart.as<int64_t>(); out->window_end_ms = w->res.wend.as<int64_t>();
-  w->stats.rows_out += (int64_t)w->res.rows;
+  if (w->R().exp_rows || w->rs[w->wr ^ 1].rows > w->rs[w->wr ^ 1].exp_rows)
+    fail(DNZ_ERR_UNSUPPORTED, "poll_device after a partial Arrow poll: drain with dnz_window_poll first");
+  out->n_rows = (int64_t)w->R().rows; out->key_bytes_len = (int64_t)w->R().bytes;
+  out->key_off = w->R().key_off.as<int32_t>(); out->key_bytes = w->R().key_bytes.as<uint8_t>(); out->key_valid = w->R().key_valid.as<uint8_t>();
+  out->count = w->R().count.as<int64_t>(); out->min = w->R().mn.as<double>(); out->max = w->R().mx.as<double>();
+  out->avg = w->R().avg.as<double>(); out->sum = w->R().sum.as<double>(); out->agg_valid = w->R().agg_valid.as<uint8_t>();
+  out->window_start_ms = w->R().wstart.as<int64_t>(); out->window_end_ms = w->R().wend.as<int64_t>();
+  w->stats.rows_out += (int64_t)w->R().rows;
   w->res_consumed = true;         // buffers stay valid until the next call that produces output
   DNZ_CATCH(w)
 }
@@ -1159,6 +1245,15 @@ int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
   DNZ_TRY(w)
   if (world < 1 || rank < 0 || rank >= world) fail(DNZ_ERR_INVALID, "bad rank/world");
   w->rank = rank; w->world = world;
+  DNZ_CATCH(w)
+}
+int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch) {
+  DNZ_TRY(w)
+  if (bytes_per_launch < 0) fail(DNZ_ERR_INVALID, "negative size");
+  for (Arena& a : w->in_arena) {
+    size_t have = 0; for (auto& s : a.slabs) have += s.bytes;
+    if (have < (size_t)bytes_per_launch) { DevBuf b; b.alloc(round_up((size_t)bytes_per_launch - have, Arena::SLAB)); a.slabs.push_back(std::move(b)); }
+  }
   DNZ_CATCH(w)
 }
 int32_t dnz_window_export_partials(dnz_window* w, dnz_partials*) {

@@ -174,6 +174,11 @@ int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, int64_
                                    const uint8_t* key_bytes, int64_t key_bytes_len);
 
 /* ---- Arrow<->device buffer manager helpers ---------------------------------------------------------- */
+/* Reserves the device staging area for host batches up front (both halves of the double buffer, `bytes_per_launch`
+ * each; ~40 B per row of max_rows_per_launch for the sensor schema) so that a fresh operator does not pay for
+ * device allocations while its first batches stream in.  Optional; without it the arena grows on demand.
+ * (≙ the buffer-capacity knobs of a DataFusion operator, e.g. batch_size; no direct counterpart.) */
+int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch);
 /* Page-locked host allocation: Arrow buffers placed here are copied host->device at full PCIe speed without a
  * staging copy (arrow-rs: Buffer::from_custom_allocation). */
 void* dnz_host_alloc(int64_t bytes);

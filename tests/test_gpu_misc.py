@@ -66,3 +66,29 @@ def test_full_size_cfg2_properties():
             assert 0.80 < len(cnt) / (100 * G) < 0.85     # P(pass) = 1 - (113/115)^100 = 0.826
         w.close()
     dev.free()
+
+
+@pytest.mark.parametrize("L,S,filt", [(1000, 0, None), (4000, 1000, ("max", ">", 113))])
+def test_non_blocking_poll_hands_out_every_row_exactly_once(L, S, filt):
+    """dnz_window_poll_ready never waits for queued input; whatever it hands out over the life of the stream, plus the final
+    blocking poll, is exactly the oracle's output (two result sets rotating underneath, launches of 8 Ki rows)."""
+    from oracle import synth_batch
+    from tests.helpers import gpu_window, record_batch_rows, to_record_batch
+    nb, n, G, rpm = 60, 4096, 500, 20
+    batches = [synth_batch(i * n, n, groups=G, rows_per_ms=rpm) for i in range(nb)]
+    last = int(batches[-1].ts[-1])
+    batches.append(rows_to_batch([((last // 1000 + 1) * 1000 + 2 * L, 1.0, b"sentinel")]))
+    want = run_oracle_batches(batches, L, S, filt)
+    w = gpu_window(L, S, filt, expected_groups=G, max_rows_per_launch=8192)
+    got, polls_with_rows = [], 0
+    for i, b in enumerate(batches):
+        w.push(to_record_batch(b))
+        if i % 3 == 2:
+            rb = w.poll_ready()
+            polls_with_rows += rb.num_rows > 0
+            got += record_batch_rows(rb)
+    got += record_batch_rows(w.poll())
+    assert w.poll().num_rows == 0
+    w.close()
+    assert polls_with_rows >= 3 and len(want) > 1000
+    assert_rows_equal(got, want)
