@@ -71,12 +71,18 @@ class DeviceResultC(C.Structure):
                 ("window_end_ms", C.c_void_p)]
 
 
+class PartialsC(C.Structure):
+    _fields_ = [("n_entries", C.c_int64), ("entries", C.c_void_p), ("owner_counts", C.POINTER(C.c_int64)),
+                ("key_bytes_len", C.c_int64), ("key_bytes", C.c_void_p), ("owner_key_bytes", C.POINTER(C.c_int64)),
+                ("pane_lo", C.c_int64), ("pane_hi", C.c_int64)]
+
+
 class StatsC(C.Structure):
     _fields_ = [("rows_in", C.c_int64), ("batches_in", C.c_int64), ("rows_out", C.c_int64), ("windows_emitted", C.c_int64),
                 ("groups", C.c_int64), ("agg_launches", C.c_int64), ("total_launches", C.c_int64),
                 ("agg_kernel_ms", C.c_double), ("agg_algorithmic_bytes", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("deferred_rows", C.c_int64), ("generic_tiles", C.c_int64),
-                ("fast_tiles", C.c_int64), ("late_batches", C.c_int64)]
+                ("fast_tiles", C.c_int64), ("late_batches", C.c_int64), ("exchanged_out", C.c_int64), ("exchanged_in", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,7 +91,7 @@ class StatsC(C.Structure):
 EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_ready",
            "dnz_window_poll_device",
            "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
-           "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_export_partials",
+           "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_process", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
            "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free"]
 
@@ -131,6 +137,13 @@ def lib():
         L.dnz_window_reserve_input.argtypes = [C.c_void_p, C.c_int64]
         L.dnz_window_set_exchange.restype = C.c_int32
         L.dnz_window_set_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.dnz_window_process.restype = C.c_int32
+        L.dnz_window_process.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.dnz_window_export_partials.restype = C.c_int32
+        L.dnz_window_export_partials.argtypes = [C.c_void_p, C.c_int64, C.POINTER(PartialsC)]
+        L.dnz_window_import_partials.restype = C.c_int32
+        L.dnz_window_import_partials.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64),
+                                                 C.c_int64, C.c_int64]
         L.dnz_host_alloc.restype = C.c_void_p
         L.dnz_host_alloc.argtypes = [C.c_int64]
         L.dnz_host_free.argtypes = [C.c_void_p]
@@ -311,6 +324,27 @@ class GpuStreamingWindow:
 
     def set_exchange(self, rank, world):
         self._check(self._L.dnz_window_set_exchange(self._h, rank, world))
+        self._world = world
+
+    def process(self):
+        """Aggregate everything queued; returns the local watermark (None if there is none yet)."""
+        v = C.c_int64(0)
+        self._check(self._L.dnz_window_process(self._h, C.byref(v)))
+        return None if v.value == -(2 ** 63) else v.value
+
+    def export_partials(self, watermark_ms):
+        """-> dict(entries=(device ptr, n), keys=(device ptr, bytes), owner_counts, owner_key_bytes, pane_lo, pane_hi)."""
+        p = PartialsC()
+        self._check(self._L.dnz_window_export_partials(self._h, -(2 ** 63) if watermark_ms is None else int(watermark_ms), C.byref(p)))
+        w = self._world
+        return dict(entries=(p.entries or 0, int(p.n_entries)), keys=(p.key_bytes or 0, int(p.key_bytes_len)),
+                    owner_counts=[int(p.owner_counts[i]) for i in range(w)], owner_key_bytes=[int(p.owner_key_bytes[i]) for i in range(w)],
+                    pane_lo=int(p.pane_lo), pane_hi=int(p.pane_hi))
+
+    def import_partials(self, entries_ptr, src_counts, keys_ptr, src_key_bytes, pane_lo, pane_hi):
+        w = self._world
+        sc = (C.c_int64 * w)(*[int(x) for x in src_counts]); sk = (C.c_int64 * w)(*[int(x) for x in src_key_bytes])
+        self._check(self._L.dnz_window_import_partials(self._h, C.c_void_p(entries_ptr), sc, C.c_void_p(keys_ptr), sk, int(pane_lo), int(pane_hi)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -22,15 +22,24 @@ __global__ void k_init_minmax(BatchMinMax* mm, int64_t n) {
   if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].key_bytes = 0; mm[i].n_fast = 0; mm[i].n_tiles = 0; }
 }
 
-// one warp per tile, 8 tiles per CTA; aligned tiles are read with 128-bit loads, 16 in flight per lane
+// one warp per tile, SCAN_TILES_PER_CTA consecutive tiles per CTA; aligned tiles are read with 128-bit loads.  The batch that
+// owns a tile is found by ONE binary search per CTA (10 dependent loads for 1 K batches -- per warp that search was three
+// quarters of the kernel's time); warps walk forward from there.
+constexpr int SCAN_TILES_PER_CTA = 32;
 __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__ batches, int64_t n_batches, int64_t n_tiles,
                                                     int64_t pane_ms, TileDesc* __restrict__ tiles, BatchMinMax* mm, int allow_fast) {
-  const int lane = threadIdx.x & 31;
-  int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (t >= n_tiles) return;
-  // batch that owns tile t: last b with tile0 <= t
-  int64_t lo = 0, hi = n_batches - 1;
-  while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (batches[mid].tile0 <= t) lo = mid; else hi = mid - 1; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int64_t s_b0;
+  const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILES_PER_CTA;
+  if (threadIdx.x == 0) {      // batch that owns tile t0: last b with tile0 <= t0
+    int64_t lo = 0, hi = n_batches - 1;
+    while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (batches[mid].tile0 <= t0) lo = mid; else hi = mid - 1; }
+    s_b0 = lo;
+  }
+  __syncthreads();
+  int64_t lo = s_b0;
+  for (int64_t t = t0 + warp; t < t0 + SCAN_TILES_PER_CTA && t < n_tiles; t += 8) {
+  while (lo + 1 < n_batches && batches[lo + 1].tile0 <= t) lo++;
   const BatchDesc bd = batches[lo];
   int64_t row0 = (t - bd.tile0) * TILE;
   int n = (int)min((int64_t)TILE, bd.n_rows - row0);
@@ -76,13 +85,14 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
     atomicAdd((unsigned long long*)&mm[lo].n_tiles, 1ull);
     if (td.flags & TILE_FAST) atomicAdd((unsigned long long*)&mm[lo].n_fast, 1ull);
   }
+  }
 }
 
 cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_t n_tiles, int64_t pane_ms, TileDesc* tiles,
                              BatchMinMax* minmax, bool allow_fast, cudaStream_t s) {
   if (n_batches <= 0 || n_tiles <= 0) return cudaSuccess;
   k_init_minmax<<<(unsigned)((n_batches + 255) / 256), 256, 0, s>>>(minmax, n_batches);
-  k_tile_scan<<<(unsigned)((n_tiles + 7) / 8), 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
+  k_tile_scan<<<(unsigned)((n_tiles + SCAN_TILES_PER_CTA - 1) / SCAN_TILES_PER_CTA), 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -123,14 +123,33 @@ struct EmitParams {
   EmitOut out;
 };
 
-// Multi-GPU partial-state packets (DNZ_PARTIAL_BYTES = 64)
+// Multi-GPU pane exchange: one packet per (pane, group) partial state a rank holds for a key it does not own
+// (DNZ_PARTIAL_BYTES = 64).  owner(key) = key hash % world (the NULL key belongs to rank 0).
 struct __align__(16) PartialEntry {
-  int64_t wstart;
+  int64_t pane;
   unsigned long long cnt; double sum; unsigned long long minkey, maxkey;
   unsigned long long nullrows, fz;
-  uint32_t key_off, key_len;     // into the accompanying key byte arena; key_len == 0xFFFFFFFF: NULL key
+  uint32_t key_off, key_len;     // bytes at key_off inside the sender's key segment FOR THIS OWNER; key_len == 0xFFFFFFFF: NULL key
 };
 static_assert(sizeof(PartialEntry) == 64, "packet size");
+constexpr int MAX_WORLD = 64;
+struct PackParams {
+  const GroupState* st; const unsigned long long* nullrows; const unsigned long long* fz;   // one pane
+  int64_t pane; uint32_t n_groups; int32_t rank, world;
+  DictView dict;
+  PartialEntry* entries; uint8_t* key_bytes;     // pass 1 output, grouped by owner
+  unsigned long long* owner_cursor;              // [world] (entries << 32) | key bytes, running over all panes of the export
+  unsigned long long owner_base[MAX_WORLD];      // pass 1: (first entry << 32) | first key byte of every owner's segment
+  int32_t pass;                                  // 0: count, 1: write
+};
+struct MergeParams {
+  const PartialEntry* entries; int64_t n_entries; const uint8_t* key_bytes;
+  int32_t world;
+  int64_t src_entry_end[MAX_WORLD];              // prefix sums over the sending ranks
+  int64_t src_key_base[MAX_WORLD];
+  DictView dict; PaneTable panes;
+  uint32_t* error;                               // set when a table was full (the host sizes them beforehand)
+};
 
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (dnz_kernels.cu)
@@ -145,12 +164,9 @@ cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, Dict
 cudaError_t launch_clear_hints(DictSlot* slots, uint32_t cap, cudaStream_t s);
 cudaError_t agg_kernel_setup();
 
-// exchange (multi-GPU)
-cudaError_t launch_pack_partials(const EmitParams& p, PartialEntry* entries, uint8_t* key_bytes,
-                                 unsigned long long* owner_cursor /*[world] (rows<<32|bytes)*/,
-                                 const unsigned long long* owner_base /*[world]*/, int pass, cudaStream_t s);
-cudaError_t launch_merge_partials(const PartialEntry* entries, int64_t n, const uint8_t* key_bytes, DictView dict,
-                                  PaneTable panes, int64_t window_ms, DeferList defer, cudaStream_t s);
+// exchange (multi-GPU, dnz_exchange.cu)
+cudaError_t launch_pack_partials(const PackParams& p, cudaStream_t s);
+cudaError_t launch_merge_partials(const MergeParams& p, cudaStream_t s);
 
 // Arrow<->device buffer manager: one launch pulls every pinned host buffer of a superbatch over PCIe with 128-bit loads
 // (hundreds of 0.5 MiB cudaMemcpyAsync calls reach only ~25 GB/s on this platform; see profiles/h2d_probe.py)

@@ -231,8 +231,15 @@ struct dnz_window {
   cudaStream_t d2h_stream = nullptr;
   bool res_consumed = false; bool ctl_fresh = false;
 
-  // multi-GPU
+  // multi-GPU pane exchange
   int rank = 0, world = 1;
+  bool has_lwm = false; int64_t lwm = 0;          // local watermark (exchange mode: emission follows the GLOBAL one)
+  int64_t exported_pane_upto = INT64_MIN;
+  DevBuf d_part_entries, d_part_keys, d_owner_cursor;
+  std::vector<int64_t> h_owner_counts, h_owner_bytes;
+  void export_partials(int64_t watermark, dnz_partials* out);
+  void import_partials(const uint8_t* entries, const int64_t* src_counts, const uint8_t* key_bytes, const int64_t* src_key_bytes,
+                       int64_t pane_lo, int64_t pane_hi);
 
   dnz_stats stats{};
   std::string err; int32_t sticky = 0;
@@ -733,7 +740,7 @@ void dnz_window::process_chunk(Superbatch& sb) {
 
   // ---- runs: maximal sequences of batches without late rows are aggregated by ONE launch; a batch that contains rows
   // for an already emitted window ("dirty") is aggregated alone so that the re-opened windows hold exactly its rows.
-  bool cur_has_wm = has_wm; int64_t cur_wm = wm;
+  bool cur_has_wm = world > 1 ? has_lwm : has_wm; int64_t cur_wm = world > 1 ? lwm : wm;
   size_t run_start = nb; int64_t run_wm_after = 0;
   for (size_t i = 0; i < nb; i++) {
     if (bds[i].n_rows == 0) continue;
@@ -741,6 +748,9 @@ void dnz_window::process_chunk(Superbatch& sb) {
     int64_t first_pane_end = (floor_div(mn, pane_ms) + 1) * pane_ms;
     bool dirty = cur_has_wm && first_pane_end <= cur_wm;
     int64_t new_wm = (!cur_has_wm || cur_wm <= mn) ? mn : cur_wm;     // process_watermark (:255-266)
+    if (dirty && world > 1 && first_pane_end <= (exported_pane_upto == INT64_MIN ? INT64_MIN : (exported_pane_upto + 1) * pane_ms))
+      fail(DNZ_ERR_UNSUPPORTED, "batch %lld is late for a pane that was already exchanged (exchange mode needs in-order input)", (long long)bds[i].seq);
+    if (world > 1) dirty = false;      // nothing has been emitted locally: late rows simply join their (still local) panes
     if (dirty) {
       if (run_start != nb) { execute_run(mm, b0, run_start, i, false, 0, run_wm_after); run_start = nb; }
       execute_run(mm, b0, i, i + 1, true, cur_wm, new_wm);
@@ -895,7 +905,8 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
     for (auto& kv : late_panes) if (pane_pool.size() < 16) pane_pool.push_back(std::move(kv.second));
     late_panes.clear();
   }
-  emit_normal(wm_after);
+  if (world > 1) { if (!has_lwm || lwm <= wm_after) lwm = wm_after; has_lwm = true; }   // emission waits for the global watermark
+  else emit_normal(wm_after);
   g_tr.mark("emit");
 }
 
@@ -1132,6 +1143,105 @@ void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pane exchange (see include/dnz_gpu.h)
+void dnz_window::export_partials(int64_t watermark, dnz_partials* out) {
+  process_pending();
+  memset(out, 0, sizeof *out);
+  h_owner_counts.assign((size_t)world, 0); h_owner_bytes.assign((size_t)world, 0);
+  out->owner_counts = h_owner_counts.data(); out->owner_key_bytes = h_owner_bytes.data();
+  out->pane_lo = 0; out->pane_hi = -1;
+  if (watermark == INT64_MIN) return;
+  const int64_t hi = floor_div(watermark, pane_ms) - 1;          // panes with end <= watermark
+  int64_t lo = exported_pane_upto == INT64_MIN ? (panes.empty() ? hi + 1 : panes.begin()->first) : exported_pane_upto + 1;
+  if (hi < lo) return;
+  std::vector<Pane*> send;
+  for (auto& kv : panes) if (kv.first >= lo && kv.first <= hi) send.push_back(kv.second.get());
+  out->pane_lo = lo; out->pane_hi = hi;
+  exported_pane_upto = hi;
+  if (send.empty()) return;
+  fetch_ctl(); ctl_fresh = false;
+  if (n_groups_host == 0) return;
+  d_owner_cursor.reserve((size_t)world * 8);
+  h_small.reserve((size_t)std::max(256, world * 8));
+  PackParams P; memset(&P, 0, sizeof P);
+  P.n_groups = n_groups_host; P.rank = rank; P.world = world; P.dict = dict_view();
+  P.owner_cursor = d_owner_cursor.as<unsigned long long>();
+  auto run_pass = [&](int pass) {
+    CK(cudaMemsetAsync(d_owner_cursor.p, 0, (size_t)world * 8, stream));
+    P.pass = pass;
+    for (Pane* p : send) {
+      P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
+      CK(launch_pack_partials(P, stream)); stats.total_launches++;
+    }
+  };
+  run_pass(0);
+  CK(cudaMemcpyAsync(h_small.p, d_owner_cursor.p, (size_t)world * 8, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  uint64_t n_total = 0, b_total = 0;
+  for (int o = 0; o < world; o++) {
+    uint64_t c = h_small.as<uint64_t>()[o];
+    h_owner_counts[(size_t)o] = (int64_t)(c >> 32); h_owner_bytes[(size_t)o] = (int64_t)(c & 0xFFFFFFFFull);
+    P.owner_base[o] = (n_total << 32) | b_total;
+    n_total += c >> 32; b_total += c & 0xFFFFFFFFull;
+    if (n_total >= (1ull << 31) || b_total >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2^31 packets or key bytes in one exchange step");
+  }
+  if (n_total == 0) return;
+  d_part_entries.reserve((size_t)n_total * sizeof(PartialEntry)); d_part_keys.reserve((size_t)b_total + 64);
+  P.entries = d_part_entries.as<PartialEntry>(); P.key_bytes = d_part_keys.as<uint8_t>();
+  run_pass(1);
+  CK(cudaStreamSynchronize(stream));
+  out->n_entries = (int64_t)n_total; out->entries = d_part_entries.as<uint8_t>();
+  out->key_bytes_len = (int64_t)b_total; out->key_bytes = d_part_keys.as<uint8_t>();
+  stats.exchanged_out += (int64_t)n_total;
+}
+
+void dnz_window::import_partials(const uint8_t* entries, const int64_t* src_counts, const uint8_t* key_bytes,
+                                 const int64_t* src_key_bytes, int64_t pane_lo, int64_t pane_hi) {
+  MergeParams M; memset(&M, 0, sizeof M);
+  int64_t n = 0, kb = 0;
+  for (int r = 0; r < world; r++) {
+    if (src_counts[r] < 0 || src_key_bytes[r] < 0) fail(DNZ_ERR_INVALID, "negative split size");
+    M.src_key_base[r] = kb; n += src_counts[r]; kb += src_key_bytes[r]; M.src_entry_end[r] = n;
+  }
+  if (n == 0) return;
+  if (!entries || (kb && !key_bytes)) fail(DNZ_ERR_INVALID, "null packet buffers");
+  if (pane_hi < pane_lo || pane_hi - pane_lo >= (1 << 16)) fail(DNZ_ERR_INVALID, "bad pane range");
+  // every received key may be new here: size the dictionary and the long-key arena first so that the merge cannot fail
+  fetch_ctl(); ctl_fresh = false;
+  while ((uint64_t)n_groups_host + (uint64_t)n > gcap) dict_grow();
+  {
+    uint64_t arena_used = *reinterpret_cast<const uint64_t*>(h_small.as<char>() + 8);
+    while (arena_used + (uint64_t)kb + 64 > arena_cap) arena_grow();
+  }
+  const int64_t np = pane_hi - pane_lo + 1;
+  for (int64_t p = pane_lo; p <= pane_hi; p++) ensure_side_arrays(get_pane(p, true));
+  const size_t pb = (size_t)np * sizeof(void*);
+  h_stage.reserve(7 * pb); d_ptrs.reserve(7 * pb);
+  void** hp = h_stage.as<void*>();
+  for (int64_t p = pane_lo; p <= pane_hi; p++) {
+    const size_t k = (size_t)(p - pane_lo);
+    Pane* m = get_pane(p, false);
+    hp[0 * np + k] = m->st.p; hp[1 * np + k] = nullptr; hp[2 * np + k] = m->nullrows.p; hp[3 * np + k] = nullptr;
+    hp[4 * np + k] = m->fz.p; hp[5 * np + k] = nullptr; hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m->tag & 0xFFFFFFFFull));
+  }
+  CK(cudaMemcpyAsync(d_ptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(ctl(96), 0, 4, stream));
+  char* dp = d_ptrs.as<char>();
+  M.panes.pane0 = pane_lo; M.panes.n_panes = (int32_t)np; M.panes.pane_ms = pane_ms;
+  M.panes.main = (GroupState* const*)(dp + 0 * pb); M.panes.late = (GroupState* const*)(dp + 1 * pb);
+  M.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); M.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
+  M.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); M.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+  M.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
+  M.entries = reinterpret_cast<const PartialEntry*>(entries); M.n_entries = n; M.key_bytes = key_bytes; M.world = world;
+  M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(96));
+  CK(launch_merge_partials(M, stream)); stats.total_launches++;
+  fetch_ctl(); ctl_fresh = false;
+  uint32_t err = *reinterpret_cast<const uint32_t*>(h_small.as<char>() + 96);
+  if (err) fail(DNZ_ERR_NOMEM, "pane merge failed (flags %u): table sizing error", err);
+  stats.exchanged_in += n;
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -1237,14 +1347,21 @@ int32_t dnz_window_reset_stats(dnz_window* w) {
   w->stats.groups = g;
   return DNZ_OK;
 }
-int64_t dnz_window_watermark(const dnz_window* w) { return (w && w->has_wm) ? w->wm : INT64_MIN; }
+int64_t dnz_window_watermark(const dnz_window* w) {
+  if (!w) return INT64_MIN;
+  if (w->world > 1) return w->has_lwm ? w->lwm : INT64_MIN;      // exchange mode: the LOCAL watermark (emission follows the global one)
+  return w->has_wm ? w->wm : INT64_MIN;
+}
 const char* dnz_window_last_error(const dnz_window* w) { return w ? w->err.c_str() : g_last_error.c_str(); }
 void dnz_window_destroy(dnz_window* w) { delete w; }
 
 int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
   DNZ_TRY(w)
   if (world < 1 || rank < 0 || rank >= world) fail(DNZ_ERR_INVALID, "bad rank/world");
+  if (world > MAX_WORLD) fail(DNZ_ERR_UNSUPPORTED, "world > %d", MAX_WORLD);
+  if (w->stats.rows_in > 0 && world != w->world) fail(DNZ_ERR_INVALID, "set_exchange must precede the first batch");
   w->rank = rank; w->world = world;
+  if (world > 1) { w->need_nullrows = true; w->need_fz = true; for (auto& kv : w->panes) w->ensure_side_arrays(kv.second.get()); }
   DNZ_CATCH(w)
 }
 int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch) {
@@ -1256,14 +1373,25 @@ int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch) {
   }
   DNZ_CATCH(w)
 }
-int32_t dnz_window_export_partials(dnz_window* w, dnz_partials*) {
+int32_t dnz_window_process(dnz_window* w, int64_t* local_watermark_ms) {
   DNZ_TRY(w)
-  fail(DNZ_ERR_UNSUPPORTED, "pane exchange not built yet");
+  w->process_pending();
+  if (local_watermark_ms) *local_watermark_ms = w->world > 1 ? (w->has_lwm ? w->lwm : INT64_MIN) : (w->has_wm ? w->wm : INT64_MIN);
   DNZ_CATCH(w)
 }
-int32_t dnz_window_import_partials(dnz_window* w, const uint8_t*, int64_t, const uint8_t*, int64_t) {
+int32_t dnz_window_export_partials(dnz_window* w, int64_t watermark_ms, dnz_partials* out) {
   DNZ_TRY(w)
-  fail(DNZ_ERR_UNSUPPORTED, "pane exchange not built yet");
+  if (!out) fail(DNZ_ERR_INVALID, "null out");
+  if (w->world <= 1) fail(DNZ_ERR_INVALID, "dnz_window_set_exchange was not called");
+  w->export_partials(watermark_ms, out);
+  DNZ_CATCH(w)
+}
+int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, const int64_t* src_counts, const uint8_t* key_bytes,
+                                   const int64_t* src_key_bytes, int64_t pane_lo, int64_t pane_hi) {
+  DNZ_TRY(w)
+  if (w->world <= 1) fail(DNZ_ERR_INVALID, "dnz_window_set_exchange was not called");
+  if (!src_counts || !src_key_bytes) fail(DNZ_ERR_INVALID, "null split arrays");
+  w->import_partials(entries, src_counts, key_bytes, src_key_bytes, pane_lo, pane_hi);
   DNZ_CATCH(w)
 }
 

@@ -105,6 +105,7 @@ typedef struct {
   int64_t deferred_rows;        /* rows replayed after a table grew                      */
   int64_t generic_tiles; int64_t fast_tiles;
   int64_t late_batches;         /* batches that contained late rows (exact re-open path) */
+  int64_t exchanged_out; int64_t exchanged_in;   /* pane-exchange packets sent / merged   */
 } dnz_stats;
 
 /* replaces: StreamingWindowExec::try_new + ExecutionPlan::execute(partition, ctx)
@@ -152,26 +153,40 @@ const char* dnz_window_last_error(const dnz_window* w);
 /* replaces: Drop for GroupedWindowAggStream */
 void dnz_window_destroy(dnz_window* w);
 
-/* ---- multi-GPU pane exchange: the exchange of per-window partial aggregates replaces
- * RepartitionExec(Hash(group keys)) (physical_optimizer/coalesce_before_streaming_window_aggregate.rs:63-73).
- * A rank exports, for every window that closed, the partial states of the keys it does NOT own, packed by
- * owner rank; the caller moves the packets with one all-to-all (NCCL, via torch.distributed) and the owner
- * merges them before it emits.  owner(key) = hash64(key) % world. ------------------------------------- */
+/* ---- multi-GPU pane exchange: replaces RepartitionExec(Hash(group keys))
+ * (physical_optimizer/coalesce_before_streaming_window_aggregate.rs:63-73) when the input is NOT key-partitioned.
+ * Every rank aggregates the batches it was dealt into its own panes.  One exchange step, driven by the caller
+ * (denormalized_b200/exchange.py does it with torch.distributed; the Rust shim would use NCCL directly):
+ *   1. dnz_window_process          aggregate what is queued, learn the local watermark
+ *   2. all-reduce(min) of the local watermarks -> global watermark
+ *   3. dnz_window_export_partials  pack, per owner rank, the partial states of the keys this rank does NOT own for every
+ *                                  pane that ended at or before the global watermark (owner = key hash % world)
+ *   4. one all-to-all (NCCL over NVLink) of the packets and their key bytes
+ *   5. dnz_window_import_partials  the owner merges them into its panes (count +, sum +, min/max, ...)
+ *   6. dnz_window_flush(global watermark) + dnz_window_poll: every rank emits the closed windows of ITS keys.
+ * In exchange mode windows are emitted only by step 6 (the watermark is global: no rank emits early, which also removes the
+ * reference's cross-partition watermark race); batches that arrive late for an exchanged pane are rejected
+ * with DNZ_ERR_UNSUPPORTED. ------------------------------------------------------------------------------------ */
 typedef struct {
-  int64_t n_entries;            /* packed entries (sorted by owner rank)                       */
-  const uint8_t* entries;       /* device: n_entries * DNZ_PARTIAL_BYTES                        */
-  const int64_t* owner_counts;  /* host: entries per owner rank (world entries)                 */
-  int64_t key_bytes_len;        /* device key byte arena accompanying the entries               */
+  int64_t n_entries;              /* packed entries, grouped by owner rank                        */
+  const uint8_t* entries;         /* device: n_entries * DNZ_PARTIAL_BYTES                         */
+  const int64_t* owner_counts;    /* host: entries per owner rank (world entries)                  */
+  int64_t key_bytes_len;          /* device key byte arena accompanying the entries                */
   const uint8_t* key_bytes;
-  const int64_t* owner_key_bytes; /* host: key bytes per owner rank                             */
+  const int64_t* owner_key_bytes; /* host: key bytes per owner rank (world entries)                */
+  int64_t pane_lo, pane_hi;       /* pane ids covered by this export (pane_hi < pane_lo: none)     */
 } dnz_partials;
 #define DNZ_PARTIAL_BYTES 64
 int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world);
-/* Aggregates everything queued; packs the partial states of all windows that closed. */
-int32_t dnz_window_export_partials(dnz_window* w, dnz_partials* out);
-/* Merges packets received from the other ranks (device pointers), then the next poll emits owned keys. */
-int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, int64_t n_entries,
-                                   const uint8_t* key_bytes, int64_t key_bytes_len);
+/* Aggregates everything queued (no emission in exchange mode).  *local_watermark_ms = INT64_MIN if none yet. */
+int32_t dnz_window_process(dnz_window* w, int64_t* local_watermark_ms);
+/* Packs the partial states of all panes that ended at or before `watermark_ms` and were not exported before.  The
+ * buffers stay valid until the next export. */
+int32_t dnz_window_export_partials(dnz_window* w, int64_t watermark_ms, dnz_partials* out);
+/* Merges packets received from the other ranks (device pointers; src_counts / src_key_bytes: per sending rank, in rank
+ * order) into panes pane_lo..pane_hi (the union of the ranks' exported ranges). */
+int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, const int64_t* src_counts,
+                                   const uint8_t* key_bytes, const int64_t* src_key_bytes, int64_t pane_lo, int64_t pane_hi);
 
 /* ---- Arrow<->device buffer manager helpers ---------------------------------------------------------- */
 /* Reserves the device staging area for host batches up front (both halves of the double buffer, `bytes_per_launch`
