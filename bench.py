@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--max-rows-per-launch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="N>1: skip the extra leg with un-partitioned input + pane all-to-all")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="extra DNZ_FLAG_* bits for the operator (experiments)")
     return ap.parse_args()
@@ -340,6 +341,54 @@ def main():
     except Exception:
         pass
 
+    # ---- N>1 only: the same stream NOT key-partitioned -- every rank sees every key, batches are dealt to ranks, and the
+    # closed panes' partial states meet at their owners through ONE all-to-all per exchange step (NCCL over NVLink):
+    # RepartitionExec(Hash) replaced by the pane exchange (denormalized_b200/exchange.py).  Reported beside `value`.
+    exchange = None
+    if world > 1 and not args.no_exchange:
+        from denormalized_b200.exchange import TorchTransport, exchange_step
+        dev.free()
+        devx = d.DeviceBatches(rows, BATCH_ROWS, seed=42 + rank, groups=G, rows_per_ms=wl["rows_per_ms"], uuid_keys=wl["uuid"], device=local)
+        endm = d.DeviceBatches(1, 1, seed=7, groups=1, rows_per_ms=1, t0_ms=close_wm, device=local)     # end-of-stream marker row
+        tr = TorchTransport(device=f"cuda:{local}")
+
+        def step_exchange(w):
+            n_out = 0
+            for g0 in range(0, devx.n_batches, GROUP):
+                n = min(GROUP, devx.n_batches - g0)
+                w.push_device(array=C.cast(C.byref(devx.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
+                n_out += exchange_step(w, tr, emit="device").n_rows
+            w.push_device(endm)
+            return n_out + exchange_step(w, tr, emit="device").n_rows
+
+        def xwindow():
+            w = new_window(); w.set_exchange(rank, world); return w
+        xo = 0
+        for _ in range(max(1, args.warmup - 1)):
+            w = xwindow(); xo = step_exchange(w); w.close()
+        xw = [xwindow() for _ in range(args.steps)]
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        for w in xw:
+            xo = step_exchange(w)
+        x1.record(stream)
+        barrier()
+        tx = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device="cuda"); dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        to = torch.tensor([xo], dtype=torch.int64, device="cuda"); dist.all_reduce(to)
+        xs = [w.stats() for w in xw]
+        tp = torch.tensor([sum(s["exchanged_out"] for s in xs)], dtype=torch.int64, device="cuda"); dist.all_reduce(tp)
+        for w in xw:
+            w.close()
+        xms = float(tx.item())
+        exchange = {"value": rows * world * args.steps / (xms * 1e-3), "unit": "rows/s", "ms_per_step": xms / args.steps,
+                    "rows_out_per_step": int(to.item()), "packets_per_step": int(tp.item()) // args.steps,
+                    "nvlink_bytes_per_step": int(tp.item()) // args.steps * 80,
+                    "what": f"{rows} rows/GPU of ONE {G}-key stream dealt to {world} GPUs (not key-partitioned); per 64 Mi rows: "
+                            "watermark all-reduce(min), one all-to-all of 64 B pane packets + key bytes, owner merge, owners emit"}
+        devx.free(); endm.free()
+        log(f"exchange leg: {xms / args.steps:.2f} ms/step")
+
     # ---- e2e: host Arrow buffers (pinned) through dnz_window_push / dnz_window_poll
     e2e = None
     if not args.no_e2e:
@@ -434,6 +483,8 @@ def main():
                              "launches": int(agg_launches), "avg_launch_ms": agg_ms / max(agg_launches, 1),
                              "algorithmic_bytes_per_row": agg_bytes / max(rows * args.steps, 1)},
                 "e2e": e2e, "cpu_baseline": cpu}
+        if exchange:
+            line["exchange"] = exchange
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -79,7 +79,8 @@ def device_bytes(torch, ptr, nbytes, device):
 
 def exchange_step(window, transport, emit=True):
     """One collective exchange step of a GpuStreamingWindow in exchange mode.  Returns the emitted RecordBatch (this rank's
-    keys, every window that closed under the GLOBAL watermark), or None when `emit` is False."""
+    keys, every window that closed under the GLOBAL watermark); emit="device" returns the device-resident result struct of
+    dnz_window_poll_device instead; emit=False only moves and merges the partials."""
     torch = transport.torch
     gw = transport.global_watermark(window.process())
     parts = window.export_partials(gw)
@@ -100,7 +101,7 @@ def exchange_step(window, transport, emit=True):
         return None
     if gw is not None:
         window.flush(gw)
-    return window.poll()
+    return window.poll_device() if emit == "device" else window.poll()
 
 
 class LocalTransport:

@@ -80,3 +80,20 @@ def test_exchange_rejects_late_batches_for_exchanged_panes():
         wins[0].process()
     for w in wins:
         w.close()
+
+
+def test_exchange_over_nccl():
+    """Two ranks on two GPUs, packets over NCCL (skipped on single-GPU boxes)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(root, "tests", "mgpu_exchange_worker.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and "NCCL exchange ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
