@@ -295,8 +295,15 @@ def main():
             n = min(GROUP, dev.n_batches - g0)
             w.push_device(array=C.cast(C.byref(dev.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
             n_out += w.poll_device().n_rows
-        w.flush(close_wm)
-        return n_out + w.poll_device().n_rows
+        # close the remaining windows a few at a time: one poll must stay below 2 GiB of key bytes (Utf8 offsets are 32-bit),
+        # which 10 M 36-byte keys x 12 open sliding windows (cfg 5) would exceed
+        step_ms = max(wl["slide_ms"] or wl["window_ms"], 1000) * (1 if G >= 4_000_000 else 64)
+        wm = (last_ts // 1000) * 1000
+        while wm < close_wm:
+            wm = min(wm + step_ms, close_wm)
+            w.flush(wm)
+            n_out += w.poll_device().n_rows
+        return n_out
 
     def barrier():
         if world > 1:

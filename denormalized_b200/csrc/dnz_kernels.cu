@@ -172,21 +172,22 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 // hint tag) into shared memory and issues four 1-D bulk copies (timestamps, values, key offsets, key bytes; SASS
 // UBLKCP) that complete on the slot's `full` mbarrier.
 //
-// Warps 0-15 consume, one row per thread (8 consumer warps per scheduler across the two CTAs hide the L2 round trip of
-// the probe).  Hot path per row: 3 LDS for value/offsets, 5 LDS.32 + funnel shifts + one LDS.128 mask for the <= 16 B
+// The other 13 warps consume, one row per thread (26 consumer warps per SM across the two CTAs hide the L2 round trip of
+// the probe).  Hot path per row: 3 LDS for value/offsets, 4-5 LDS.32 + funnel shifts + clamp-shift masks for the <= 16 B
 // key, a 32-bit hash, ONE 32 B dictionary-slot load (LDG.E.256) that also carries the group's min/max hint; a row whose
-// slot holds another key is parked in the warp's retry queue; then reductions issued by lane PAIRS: lanes 2j / 2j+1 update
-// {cnt, sum} with one red.add.f64 and {minkey, maxkey} with one red.max.u64 of the same row, so an instruction touches
-// 16 sectors instead of 32, and the min/max pair is skipped for rows that cannot beat the hint.  Everything rare (empty
-// or locked slot -> insert, keys > 16 B, +-0.0, tiles spanning panes, late panes) is outlined into __noinline__ helpers
-// so that the hot loop stays ~300 SASS instructions per 64 rows (profiles/README.md).
+// slot holds another key is parked in the warp's retry queue; count and sum are reduced by lane PAIRS: lanes 2j / 2j+1
+// update {cnt, sum} of the same row with one red.add.f64 (16 sectors per instruction instead of 32); min / max are reduced
+// by the row's own lane for the ~7 % of the rows the hint lets through.  Everything rare (empty or locked slot -> insert,
+// keys > 16 B, +-0.0 / non-finite values, tiles spanning panes, late panes) is outlined into __noinline__ helpers so
+// that the hot loop stays ~330 SASS instructions per 32 rows (profiles/README.md).
 // =================================================================================================
-struct __align__(16) StageHdr {
+struct __align__(16) StageHdr {   // the consumers read the first two 16 B words with one LDS.128 each (2 wavefronts per tile, not 8)
+  int32_t n_rows, flags, a0; uint32_t tag;
   GroupState* mbase;            // main state array of the tile's pane when every row can take the paired path, else nullptr
+  uint32_t tile_rel, pane_rel;  // tile index inside the launch; pane index relative to PaneTable::pane0 (when mbase != nullptr)
   long long pane_lo;
   unsigned long long rowseq0;   // (batch arrival seq << 32) | first row of the tile inside its batch
-  int32_t n_rows, flags, a0, pad0;
-  uint32_t tag, tile_rel, pad1, pad2;
+  uint32_t pad[4];
 };
 static_assert(sizeof(StageHdr) == 64, "header size");
 struct __align__(128) Stage {
@@ -216,7 +217,6 @@ struct AggSmem {
   Stage st[STAGES];
   WarpQueue q[CONSUMER_WARPS];
   TileFetch fetch[1][8];
-  uint4 keymask[INLINE_KEY + 1];     // keymask[len] = byte mask of a len-byte key in four 32-bit words
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
 };
@@ -309,12 +309,6 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
     for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
     mbar_fence_init();
   }
-  if (tid <= INLINE_KEY) {
-    uint32_t m[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { int keep = tid - 4 * i; m[i] = keep <= 0 ? 0u : keep >= 4 ? 0xFFFFFFFFu : ((1u << (8 * keep)) - 1u); }
-    S.keymask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
-  }
   __syncthreads();
 
   if (warp == CONSUMER_WARPS) {
@@ -323,7 +317,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
     // dependent global loads that would otherwise serialise per tile) into shared memory; lane 0 then feeds the ring.
     auto fetch = [&](int64_t t, TileFetch& d) {
       StageHdr h; h.mbase = nullptr; h.tag = 0; h.pane_lo = 0; h.rowseq0 = 0; h.n_rows = 0; h.flags = 0; h.a0 = 0; h.tile_rel = 0;
-      h.pad0 = 0; h.pad1 = h.pad2 = 0;
+      h.pane_rel = 0; h.pad[0] = h.pad[1] = h.pad[2] = h.pad[3] = 0;
       d.nts = d.noff = d.nby = 0;
       if (t < P.tile_end) {
         const TileDesc td = P.tiles[t];
@@ -337,7 +331,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
           d.nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
           if (td.flags & TILE_PANE_UNIFORM) {
             int64_t pi = td.pane_lo - P.panes.pane0;
-            if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) { h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; }
+            if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) { h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; h.pane_rel = (uint32_t)pi; }
           }
         }
       }
@@ -394,29 +388,35 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
     mbar_wait(&S.full[s], (it / STAGES) & 1u);
     const Stage& st = S.st[s];
     const StageHdr& H = st.hdr;
-    if (H.flags & TILE_END) break;
+    const int4 h0 = *reinterpret_cast<const int4*>(&H.n_rows);            // n_rows, flags, a0, tag
+    if (h0.y & TILE_END) break;
     // Everything derived from the thread index is recomputed per tile behind an opaque barrier: hoisted out of the loop
     // these values (lane masks, shuffle sources, queue address) cost registers the 64-register budget does not have, and
     // a spill is a local-memory access that queues behind the scattered traffic in the L1TEX FIFO.
     uint32_t tix = (uint32_t)tid; asm volatile("" : "+r"(tix));
     const int lane = (int)(tix & 31u), odd = (int)(tix & 1u);
     WarpQueue& Q = S.q[tix >> 5];
-    if (!(H.flags & TILE_FAST)) {
+    if (!(h0.y & TILE_FAST)) {
       agg_tile_generic(P, H.tile_rel, (int)tix);
     } else {
+      const uint4 h1 = *reinterpret_cast<const uint4*>(&H.mbase);         // mbase, tile_rel, pane_rel
       const uint32_t r = tix;
-      const bool live = r < (uint32_t)H.n_rows;
-      GroupState* const mbase = H.mbase;
+      const bool live = r < (uint32_t)h0.x;
+      GroupState* const mbase = reinterpret_cast<GroupState*>(((uint64_t)h1.y << 32) | h1.x);
       const double v = st.val[r];
       const int32_t o0 = st.off[r], o1 = st.off[r + 1];
-      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - H.a0) : 0u;
-      const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, sh = (addr & 3u) * 8u;
+      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - h0.z) : 0u;
+      const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, mis = addr & 3u, sh = mis * 8u;
       uint32_t a[5];
 #pragma unroll
-      for (int j = 0; j < 5; j++) a[j] = lds32(q + 4u * j);
-      const uint4 m = S.keymask[min(klen, (uint32_t)INLINE_KEY)];
-      const uint32_t w0 = __funnelshift_r(a[0], a[1], sh) & m.x, w1 = __funnelshift_r(a[1], a[2], sh) & m.y;
-      const uint32_t w2 = __funnelshift_r(a[2], a[3], sh) & m.z, w3 = __funnelshift_r(a[3], a[4], sh) & m.w;
+      for (int j = 0; j < 4; j++) a[j] = lds32(q + 4u * j);
+      a[4] = (mis + klen > 16u) ? lds32(q + 16u) : 0u;                    // a 5th word only when the key straddles it
+      // byte mask of word i of a klen-byte key: 0xFFFFFFFF >> clamp(32 - 8 * (klen - 4 i), 0, 32)  (shf.r.clamp saturates at 32)
+      const int mb = 32 - 8 * (int)min(klen, (uint32_t)INLINE_KEY);
+      const uint32_t w0 = __funnelshift_r(a[0], a[1], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb, 0));
+      const uint32_t w1 = __funnelshift_r(a[1], a[2], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 32, 0));
+      const uint32_t w2 = __funnelshift_r(a[2], a[3], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 64, 0));
+      const uint32_t w3 = __funnelshift_r(a[3], a[4], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 96, 0));
       uint32_t idx = hash_words(w0, w1, w2, w3, klen) & dmask;
       // paired-path row: finite and not +-0.0 (everything else goes through the general per-row path)
       const uint32_t bhi = (uint32_t)__double2hiint(v), blo = (uint32_t)__double2loint(v);
@@ -440,35 +440,40 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
         if (park) {
           const uint32_t pos = qcount + __popc(bal & ((1u << lane) - 1u));
           Q.key[pos] = make_uint4(w0, w1, w2, w3);
-          Q.meta[pos] = make_uint2(idx, klen | ((uint32_t)(H.pane_lo - P.panes.pane0) << 8));
+          Q.meta[pos] = make_uint2(idx, klen | (h1.w << 8));
           Q.val[pos] = v;
-          Q.row[pos] = (H.tile_rel << 10) | r;
+          Q.row[pos] = (h1.z << 10) | r;
         }
         qcount += __popc(bal);
       }
       if (need_slow) { const uint64_t gs = agg_probe_slow(P, st.bytes + kb, klen); gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true; }
       uint32_t pk = 0;
       if (hit) {
-        if (gid >= GID_DEFER_ARENA) defer_row(P.defer, H.tile_rel, r, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
+        if (gid >= GID_DEFER_ARENA) defer_row(P.defer, h1.z, r, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
         else if (plain) {
           // hints: top 16 bits of minkey / maxkey follow from the high word of ord(v) alone (no borrow from the low word)
           const uint32_t ohi = (bhi & 0x80000000u) ? ~bhi : (bhi | 0x80000000u);
           const uint32_t tmin = (0xFFEFFFFFu - ohi) >> 16, tmax = (ohi - 0x00100000u) >> 16;
           uint32_t hmin = 0, hmax = 0;
-          const uint32_t tag = H.tag;
+          const uint32_t tag = (uint32_t)h0.w;
           const uint32_t htag = (uint32_t)(hint >> 32);
           if (use_hints && htag == tag) { hmin = (uint32_t)(hint >> 16) & 0xFFFFu; hmax = (uint32_t)hint & 0xFFFFu; }
           // CTAs drift apart by up to a few million rows, so around a pane boundary two panes are in flight: a straggler of
           // the OLDER pane (smaller tag; tags live in [1, 2^31)) never replaces the newer pane's hint -- it just reduces
           if (use_hints && (int32_t)(htag - tag) <= 0 && (tmin > hmin || tmax > hmax))
             st_relaxed_u64(const_cast<uint64_t*>(&slots[idx].hint), ((uint64_t)tag << 32) | ((uint64_t)max(hmin, tmin) << 16) | (uint64_t)max(hmax, tmax));
-          pk = gid | (1u << 29) | (tmin >= hmin ? 1u << 30 : 0u) | (tmax >= hmax ? 1u << 31 : 0u);
+          // min / max: the hint lets ~7 % of the rows through; they are reduced here, by the row's own lane (pairing them as
+          // well would make every warp execute the key computation for two half-warps almost every tile)
+          const uint32_t olo = (bhi & 0x80000000u) ? ~blo : blo;
+          if (tmin >= hmin) red_max_u64(&mbase[gid].minkey, ((unsigned long long)(0xFFEFFFFFu - ohi) << 32) | (uint32_t)~olo);
+          if (tmax >= hmax) red_max_u64(&mbase[gid].maxkey, ((unsigned long long)(ohi - 0x00100000u) << 32) | olo);
+          pk = gid | (1u << 29);
         } else {
           agg_apply_slow(P, H, r, st.ts[r], v, gid);
         }
       }
-      // reductions by lane pairs: lanes 2j / 2j+1 serve the row of lane j (+16): {cnt, sum} as one red.add.f64 pair,
-      // {minkey, maxkey} as one red.max.u64 pair -> 16 sectors per instruction
+      // count and sum by lane pairs: lanes 2j / 2j+1 serve the row of lane j (+16): {cnt, sum} as ONE red.add.f64 on adjacent
+      // words of the state sector -> 16 sectors per instruction, half the reduction wavefronts of two scalar reductions
       if (mbase != nullptr) {                       // warp-uniform
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -478,12 +483,6 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
           if (pk2 & (1u << 29)) {
             GroupState* s2 = mbase + (pk2 & 0x1FFFFFFFu);
             red_add_f64(&s2->cnt + odd, odd ? __hiloint2double((int)hi2, (int)lo2) : 1.0);
-            if (pk2 & (odd ? 1u << 31 : 1u << 30)) {
-              const bool neg = hi2 & 0x80000000u;
-              const uint32_t olo = neg ? ~lo2 : lo2, oh = neg ? ~hi2 : (hi2 | 0x80000000u);           // ord(v), halves
-              const uint32_t klo = odd ? olo : ~olo, khi = odd ? oh - 0x00100000u : 0xFFEFFFFFu - oh;  // maxkey : minkey
-              red_max_u64(&s2->minkey + odd, ((unsigned long long)khi << 32) | klo);
-            }
           }
         }
       }
