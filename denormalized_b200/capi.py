@@ -22,6 +22,7 @@ FLAG_KERNEL_TIMING = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_NO_HINTS = 4
 FLAG_NO_QUEUE = 8
+FLAG_NO_PRIVATE = 16
 INTERNAL_METADATA_COLUMN = "_streaming_internal_metadata"   # crates/common/src/lib.rs:5
 
 

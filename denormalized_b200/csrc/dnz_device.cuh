@@ -244,6 +244,7 @@ __device__ __forceinline__ uint32_t dict_lookup(const DictView& d, const KeyRef&
     uint32_t g = dict_step(d, idx, k, key_shared, adv);
     if (g != 0xFFFFFFFFu) { if (slot_out) *slot_out = idx; return g; }
     if (adv) idx = (idx + 1) & d.mask;
+    else __nanosleep(100);      // slot locked by an insert in flight (possibly by another lane of this warp): let it finish
   }
 }
 

@@ -274,7 +274,7 @@ __device__ __noinline__ uint32_t agg_queue_round(const AggParams& P, WarpQueue& 
     if (done) {
       if (gid >= GID_DEFER_ARENA) defer_row(P.defer, ro >> 10, ro & 1023u, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
       else {
-        GroupState* s = P.panes.main[pi] + gid;        // parked rows come from tiles with a plain main pane and v != +-0.0
+        GroupState* s = (P.priv ? P.priv + ((size_t)blockIdx.x * P.panes.n_panes + pi) * P.priv_groups : P.panes.main[pi]) + gid;   // parked rows: plain main pane, v != +-0.0
         const uint32_t tag = (uint32_t)P.panes.tag_main[pi];
         const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v));
         const bool okmin = v <= 1.7976931348623157e308, okmax = v >= -1.7976931348623157e308;
@@ -331,7 +331,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
           d.nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
           if (td.flags & TILE_PANE_UNIFORM) {
             int64_t pi = td.pane_lo - P.panes.pane0;
-            if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) { h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; h.pane_rel = (uint32_t)pi; }
+            if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) {
+              h.mbase = P.panes.main[pi]; h.tag = (uint32_t)P.panes.tag_main[pi]; h.pane_rel = (uint32_t)pi;
+              if (P.priv && h.mbase) h.mbase = P.priv + ((size_t)blockIdx.x * P.panes.n_panes + pi) * P.priv_groups;
+            }
           }
         }
       }
@@ -381,7 +384,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
   // -------------------------------------------------------------- consumer warps: one row per thread
   const DictSlot* const slots = P.dict.slots;
   const uint32_t dmask = P.dict.mask;
-  const bool use_hints = !(P.flags & AGG_NO_HINTS), use_queue = !(P.flags & AGG_NO_QUEUE);
+  // hints are switched off together with the private pane copies (low cardinality): the copies make every reduction cheap, and
+  // hint stores into a few hundred hot dictionary sectors that every SM keeps reading bounce those lines between the two L2
+  // partitions (ncu on cfg 1: 57 % of the samples waiting for the probe, LSU pipe 6 % busy)
+  const bool use_hints = !(P.flags & AGG_NO_HINTS) && P.priv == nullptr, use_queue = !(P.flags & AGG_NO_QUEUE);
   uint32_t qcount = 0;                 // warp-uniform
   for (uint32_t it = 0;; it++) {
     const int s = it % STAGES;
@@ -500,12 +506,40 @@ cudaError_t agg_kernel_setup() {
   return cudaFuncSetAttribute(k_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, g_agg_smem);
 }
 
+int aggregate_grid(int64_t n_tiles, int sm_count) {
+  return (int)(n_tiles < (int64_t)sm_count * 2 ? n_tiles : (int64_t)sm_count * 2);          // two persistent CTAs per SM
+}
 cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s) {
   int64_t n_tiles = p.tile_end - p.tile_begin;
   if (n_tiles <= 0) return cudaSuccess;
   if (!g_agg_smem) { cudaError_t e = agg_kernel_setup(); if (e != cudaSuccess) return e; }
-  int grid = (int)(n_tiles < (int64_t)sm_count * 2 ? n_tiles : (int64_t)sm_count * 2);     // two persistent CTAs per SM
-  k_aggregate<<<grid, AGG_THREADS, g_agg_smem, s>>>(p);
+  k_aggregate<<<aggregate_grid(n_tiles, sm_count), AGG_THREADS, g_agg_smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// Fold the per-CTA private pane copies into the panes: thread per (pane of the launch, group id).
+__global__ void __launch_bounds__(256) k_merge_private(const __grid_constant__ AggParams P, int n_cta) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pi = blockIdx.y;
+  if (g >= P.priv_groups) return;
+  GroupState* dst = P.panes.main[pi];
+  if (!dst) return;
+  double cnt = 0.0, sum = 0.0; unsigned long long mn = 0, mx = 0; bool first = true;
+  for (int c = 0; c < n_cta; c++) {
+    const GroupState s = P.priv[((size_t)c * P.panes.n_panes + pi) * P.priv_groups + g];
+    if (s.cnt != 0.0) { sum = first ? s.sum : sum + s.sum; first = false; cnt += s.cnt; }
+    mn = max(mn, s.minkey); mx = max(mx, s.maxkey);
+  }
+  if (cnt == 0.0) return;
+  GroupState* d = dst + g;                      // the slow paths may have reduced into the pane concurrently-ordered before: add
+  red_add_f64(&d->cnt, cnt); red_add_f64(&d->sum, sum);
+  if (mn) red_max_u64(&d->minkey, mn);
+  if (mx) red_max_u64(&d->maxkey, mx);
+}
+cudaError_t launch_merge_private(const AggParams& p, int grid, cudaStream_t s) {
+  if (!p.priv || grid <= 0) return cudaSuccess;
+  dim3 g((p.priv_groups + 255) / 256, (unsigned)p.panes.n_panes);
+  k_merge_private<<<g, 256, 0, s>>>(p, grid);
   return cudaGetLastError();
 }
 cudaError_t launch_aggregate_generic(const AggParams& p, int sm_count, cudaStream_t s) {

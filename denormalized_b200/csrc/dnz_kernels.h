@@ -96,6 +96,11 @@ struct AggParams {
   DictView dict; PaneTable panes; DeferList defer;
   uint32_t flags;
   uint32_t* tile_counter;   // zeroed per launch: CTAs claim tiles in stream order (keeps the tiles in flight within ~1 % of a pane)
+  // Low cardinality: with a few thousand groups every state sector is hit by thousands of reductions per launch and the L2
+  // atomic unit serialises per address (18 G rows/s at 1 K groups, profiles/microbench).  The paired / hinted reductions then
+  // go to a PRIVATE zero-initialised copy of the pane per CTA, priv[(cta * n_panes + pane) * priv_groups + gid], which
+  // k_merge_private folds into the pane afterwards (everything is commutative).  nullptr: disabled.
+  GroupState* priv; uint32_t priv_groups;
 };
 enum : uint32_t { AGG_NO_HINTS = 1, AGG_NO_QUEUE = 2 };   // experiments: reduce min/max for every row; loop on collisions
 
@@ -156,6 +161,8 @@ struct MergeParams {
 cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_t n_tiles, int64_t pane_ms,
                              TileDesc* tiles, BatchMinMax* minmax, bool allow_fast, cudaStream_t s);
 cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s);
+int aggregate_grid(int64_t n_tiles, int sm_count);
+cudaError_t launch_merge_private(const AggParams& p, int grid, cudaStream_t s);
 cudaError_t launch_aggregate_generic(const AggParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n_entries, cudaStream_t s);
 cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);

@@ -224,7 +224,7 @@ struct dnz_window {
     std::vector<BatchDesc> bds; int64_t n_tiles = 0; bool launched = false;
   } scan[2];
   Scan* cur_scan = nullptr;
-  DevBuf d_ptrs, d_defer[2];
+  DevBuf d_ptrs, d_defer[2], d_priv;
   PinnedBuf h_stage, h_small;
   ResultSet rs[2]; int wr = 0; bool async_polls = false;
   ResultSet& R() { return rs[wr]; }
@@ -852,11 +852,22 @@ void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0
       P.defer.count = reinterpret_cast<unsigned long long*>(ctl(64)); P.defer.cap = defer_cap;
       P.defer.flags = reinterpret_cast<uint32_t*>(ctl(72));
       P.tile_counter = reinterpret_cast<uint32_t*>(ctl(76));     // zeroed with the deferred-row counters above
+      // low cardinality: private pane copies per CTA (see AggParams::priv)
+      P.priv = nullptr; P.priv_groups = 0;
+      const int agg_grid = aggregate_grid(t1 - t0, sm_count);
+      const size_t priv_bytes = (size_t)agg_grid * (size_t)np * gcap * sizeof(GroupState);
+      const bool use_priv = iter == 0 && !dirty && gcap <= 8192 && priv_bytes <= (256ull << 20) && !(cfg.flags & (DNZ_FLAG_FORCE_GENERIC | DNZ_FLAG_NO_PRIVATE));
+      if (use_priv) {
+        d_priv.reserve(priv_bytes);
+        CK(cudaMemsetAsync(d_priv.p, 0, priv_bytes, stream));
+        P.priv = d_priv.as<GroupState>(); P.priv_groups = gcap;
+      }
       const bool timing = iter == 0 && (cfg.flags & DNZ_FLAG_KERNEL_TIMING);
       if (iter == 0) {
         if (timing) CK(cudaEventRecord(ev0, stream));
         if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
         else CK(launch_aggregate(P, sm_count, stream));
+        if (use_priv) { CK(launch_merge_private(P, agg_grid, stream)); stats.total_launches++; }
         if (timing) CK(cudaEventRecord(ev1, stream));
         stats.agg_launches++; stats.total_launches++;
       } else {

@@ -38,6 +38,7 @@ enum { DNZ_OP_GT = 0, DNZ_OP_GTE = 1, DNZ_OP_LT = 2, DNZ_OP_LTE = 3, DNZ_OP_EQ =
 #define DNZ_FLAG_KERNEL_TIMING 1u  /* record CUDA events around every aggregate-kernel launch (dnz_stats) */
 #define DNZ_FLAG_FORCE_GENERIC 2u  /* testing: disable the TMA-staged fast path                           */
 #define DNZ_FLAG_NO_HINTS 4u        /* experiments: disable the per-group min/max reduction filter                 */
+#define DNZ_FLAG_NO_PRIVATE 16u     /* experiments: no per-CTA private pane copies for low-cardinality streams        */
 #define DNZ_FLAG_NO_QUEUE 8u        /* experiments: colliding probes loop in place instead of using the retry queue */
 
 typedef struct {

@@ -77,7 +77,8 @@ def test_min_max_quirks_and_filter_total_order():
 
 @pytest.mark.parametrize("L,S", [(1000, 0), (4000, 1000)])
 @pytest.mark.parametrize("late", [False, True])
-def test_minmax_hints_never_lose_an_extreme(L, S, late):
+@pytest.mark.parametrize("expected_groups", [0, 16])      # 16: small tables => per-CTA private pane copies (low-cardinality path)
+def test_minmax_hints_never_lose_an_extreme(L, S, late, expected_groups):
     """Few keys x many rows per pane, fast (TMA-staged) tiles, one launch per batch: the per-group min/max reduction filter
     (DictSlot::hint) is hit hard -- trends, sign changes, tiny/huge magnitudes, values equal in their top 16 key bits,
     panes revisited by late batches (new pane instances => new hint tags)."""
@@ -106,10 +107,10 @@ def test_minmax_hints_never_lose_an_extreme(L, S, late):
         t += 300
     batches.append(sentinel(t + 3 * L))
     want = run_oracle_batches(batches, L, S)
-    got, st = run_gpu(batches, L, S)
+    got, st = run_gpu(batches, L, S, expected_groups=expected_groups)
     assert st["fast_tiles"] > 30 and (st["late_batches"] > 0) == late
     assert_rows_equal(got, want, check_seq=True)
-    got2, _ = run_gpu(batches, L, S, per_batch_poll=False)
+    got2, _ = run_gpu(batches, L, S, per_batch_poll=False, expected_groups=expected_groups)
     assert_rows_equal(got2, want)
 
 
