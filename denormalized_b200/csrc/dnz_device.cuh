@@ -141,14 +141,24 @@ __device__ __forceinline__ void load_key(const uint8_t* p, uint32_t len, KeyRef&
     k.k0 = (uint64_t)w[0] | ((uint64_t)w[1] << 32); k.k1 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
     k.hash = hash_inline(k.k0, k.k1, len);
   } else {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)len * 0xff51afd7ed558ccdull);
-    for (uint32_t i = 0; i < len; i++) {
-      uint8_t c;
-      if (SHARED) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_u32(p + i))); c = (uint8_t)v; }
-      else c = __ldg(p + i);
-      h = (h ^ c) * 0x100000001B3ull; h ^= h >> 29;
+    // long key: two 32-bit multiply-xorshift lanes over its little-endian 32-bit words (aligned loads + funnel shifts; the
+    // byte-at-a-time version cost ~250 instructions for a 36 B UUID and was the whole kernel for such streams)
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u), sh = mis * 8u;
+    const uint8_t* q = p - mis;
+    const uint32_t nk = (len + 3u) >> 2, nw = (mis + len + 3u) >> 2;
+    uint32_t h1 = 0x9E3779B1u * (len + 1u), h2 = 0x85EBCA77u ^ len;
+    uint32_t prev = ld_word<SHARED>(q);
+    for (uint32_t i = 0; i < nk; i++) {
+      const uint32_t next = (i + 1u < nw) ? ld_word<SHARED>(q + 4u * (i + 1u)) : 0u;
+      uint32_t w = __funnelshift_r(prev, next, sh);
+      prev = next;
+      if (i + 1u == nk && (len & 3u)) w &= (1u << ((len & 3u) * 8u)) - 1u;
+      h1 = (h1 ^ w) * 0x85EBCA6Bu; h1 ^= h1 >> 15;
+      h2 = (h2 + w) * 0xC2B2AE3Du; h2 = (h2 << 13) | (h2 >> 19);
     }
-    h = mix64(h);
+    h1 ^= h2 * 0x27D4EB2Fu; h1 ^= h1 >> 16; h1 *= 0x165667B1u; h1 ^= h1 >> 13;
+    h2 ^= h1 * 0x9E3779B1u; h2 ^= h2 >> 15; h2 *= 0x85EBCA6Bu; h2 ^= h2 >> 16;
+    const uint64_t h = ((uint64_t)h2 << 32) | h1;
     k.k0 = h; k.k1 = 0; k.hash = h;
   }
 }
@@ -192,9 +202,20 @@ __device__ __forceinline__ uint32_t dict_try_insert(const DictView& d, DictSlot*
 }
 
 __device__ __forceinline__ bool dict_long_equal(const DictView& d, uint64_t arena_off, const KeyRef& k, bool key_shared) {
-  // __ldcg: arena bytes of OTHER keys sharing an L1 sector may have been cached before this key was written
-  for (uint32_t i = 0; i < k.len; i++)
-    if (__ldcg(d.arena + arena_off + i) != ld_key_byte(k.ptr + i, key_shared)) return false;
+  // word-wise; arena entries are 8 B aligned.  __ldcg: arena bytes of OTHER keys sharing an L1 sector may have been cached
+  // before this key was written
+  const uint32_t* aw = reinterpret_cast<const uint32_t*>(d.arena + arena_off);
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(k.ptr) & 3u), sh = mis * 8u;
+  const uint8_t* q = k.ptr - mis;
+  const uint32_t nk = (k.len + 3u) >> 2, nw = (mis + k.len + 3u) >> 2;
+  uint32_t prev = key_shared ? ld_word<true>(q) : ld_word<false>(q);
+  for (uint32_t i = 0; i < nk; i++) {
+    const uint32_t next = (i + 1u < nw) ? (key_shared ? ld_word<true>(q + 4u * (i + 1u)) : ld_word<false>(q + 4u * (i + 1u))) : 0u;
+    uint32_t w = __funnelshift_r(prev, next, sh), a = __ldcg(aw + i);
+    prev = next;
+    if (i + 1u == nk && (k.len & 3u)) { const uint32_t m = (1u << ((k.len & 3u) * 8u)) - 1u; w &= m; a &= m; }
+    if (w != a) return false;
+  }
   return true;
 }
 

@@ -716,7 +716,10 @@ void dnz_window::prealloc() {
   d_ptrs.reserve(7 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
   h_stage.reserve((size_t)7 * 1024 * sizeof(void*)); h_small.reserve(256);
   for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
-  ensure_result_capacity((uint64_t)gcap * 8, (uint64_t)gcap * 16 * 8);
+  {   // room for a few windows' worth of rows; grows on demand (one poll is limited to 2 GiB of key bytes by the 32-bit Utf8 offsets)
+    const uint64_t rows0 = std::min<uint64_t>((uint64_t)gcap * 8, 64ull << 20);
+    ensure_result_capacity(rows0, std::min<uint64_t>(rows0 * 16, (1ull << 31) - (1ull << 20)));
+  }
 }
 
 void dnz_window::process_chunk(Superbatch& sb) {
