@@ -194,7 +194,7 @@ __device__ __forceinline__ uint32_t dict_try_insert(const DictView& d, DictSlot*
     slot->k0 = k.k0; slot->k1 = k.k1;
   }                                                  // slot->hint stays 0 (= no hint) from the zero fill
   slot->len = k.len;
-  d.slot_of_gid[g] = slot_idx;
+  d.gid_key[g] = GidKey{k.k0, k.len > (uint32_t)INLINE_KEY ? arena_off : k.k1, k.len, 0u};
   atomicAdd(d.key_bytes_total, (unsigned long long)k.len);
   __threadfence();
   st_release_u32(&slot->state, g + 1);
@@ -249,7 +249,7 @@ __device__ __forceinline__ uint32_t dict_lookup_null(const DictView& d) {
       if (old != 0) continue;
       uint32_t g = atomicAdd(d.n_groups, 1u);
       if (g >= d.gcap) { st_release_u32(d.null_gid, 0u); return GID_DEFER_GROUPS; }
-      d.slot_of_gid[g] = 0xFFFFFFFFu;
+      d.gid_key[g] = GidKey{0ull, 0ull, 0xFFFFFFFFu, 0u};
       __threadfence();
       st_release_u32(d.null_gid, g + 1);
       return g;

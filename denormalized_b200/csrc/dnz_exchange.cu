@@ -15,15 +15,10 @@ __global__ void __launch_bounds__(256) k_pack_partials(const __grid_constant__ P
   const GroupState s = P.st[g];
   const unsigned long long nr = P.nullrows ? P.nullrows[g] : 0ull;
   if (s.cnt == 0.0 && nr == 0ull) return;
-  const uint32_t si = P.dict.slot_of_gid[g];
-  uint32_t klen = 0; uint64_t h = 0;
-  const DictSlot* sl = nullptr;
-  if (si != 0xFFFFFFFFu) {
-    sl = P.dict.slots + si;
-    klen = sl->len;
-    h = klen <= (uint32_t)INLINE_KEY ? hash_inline(sl->k0, sl->k1, klen) : sl->k0;
-  }
-  const int owner = si == 0xFFFFFFFFu ? 0 : (int)(h % (uint64_t)P.world);
+  const GidKey gk = P.dict.gid_key[g];
+  const bool null_key = gk.len == 0xFFFFFFFFu;
+  const uint32_t klen = null_key ? 0u : gk.len;
+  const int owner = null_key ? 0 : (int)((klen <= (uint32_t)INLINE_KEY ? hash_inline(gk.k0, gk.k1, klen) : gk.k0) % (uint64_t)P.world);
   if (owner == P.rank) return;
   const uint32_t kpad = (klen + 7u) & ~7u;
   const unsigned long long c = atomicAdd(P.owner_cursor + owner, (1ull << 32) | kpad);
@@ -33,15 +28,15 @@ __global__ void __launch_bounds__(256) k_pack_partials(const __grid_constant__ P
   PartialEntry e;
   e.pane = P.pane; e.cnt = (unsigned long long)s.cnt; e.sum = s.sum; e.minkey = s.minkey; e.maxkey = s.maxkey;
   e.nullrows = nr; e.fz = P.fz ? P.fz[g] : ~0ull;
-  e.key_off = boff; e.key_len = si == 0xFFFFFFFFu ? 0xFFFFFFFFu : klen;
+  e.key_off = boff; e.key_len = null_key ? 0xFFFFFFFFu : klen;
   P.entries[row] = e;
-  if (sl) {
+  if (!null_key) {
     uint8_t* dst = P.key_bytes + (P.owner_base[owner] & 0xFFFFFFFFull) + boff;
     if (klen <= (uint32_t)INLINE_KEY) {
-      const uint64_t w[2] = {sl->k0, sl->k1};
+      const uint64_t w[2] = {gk.k0, gk.k1};
       for (uint32_t i = 0; i < klen; i++) dst[i] = (uint8_t)(w[i >> 3] >> ((i & 7) * 8));
     } else {
-      const uint8_t* src = P.dict.arena + sl->k1;
+      const uint8_t* src = P.dict.arena + gk.k1;
       for (uint32_t i = 0; i < klen; i++) dst[i] = src[i];
     }
   }

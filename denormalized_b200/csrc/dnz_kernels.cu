@@ -566,13 +566,10 @@ __device__ __forceinline__ bool predicate(int op, long long a, long long b) {
   switch (op) { case 0: return a > b; case 1: return a >= b; case 2: return a < b; case 3: return a <= b; case 4: return a == b; default: return a != b; }
 }
 
-__device__ __forceinline__ uint64_t key_hash_of_gid(const DictView& d, uint32_t gid, uint32_t& len_out, uint32_t& slot_out) {
-  uint32_t si = d.slot_of_gid[gid];
-  slot_out = si;
-  if (si == 0xFFFFFFFFu) { len_out = 0; return 0; }            // NULL key hashes to 0 (owner = rank 0)
-  const DictSlot& sl = d.slots[si];
-  len_out = sl.len;
-  return sl.len <= (uint32_t)INLINE_KEY ? hash_inline(sl.k0, sl.k1, sl.len) : sl.k0;
+// owner hash of a group's key (NULL key: 0 -> rank 0)
+__device__ __forceinline__ uint64_t key_hash(const GidKey& gk) {
+  if (gk.len == 0xFFFFFFFFu) return 0;
+  return gk.len <= (uint32_t)INLINE_KEY ? hash_inline(gk.k0, gk.k1, gk.len) : gk.k0;
 }
 
 struct Combined { unsigned long long cnt, nullrows, mnk, mxk, fz; double sum; bool present; };   // cnt: exact integer
@@ -591,17 +588,20 @@ __device__ __forceinline__ Combined combine_panes(const EmitParams& P, uint32_t 
   return c;
 }
 
+constexpr int EMIT_STAGE = 12288;     // key bytes a block stages in shared memory before one coalesced copy
 __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams P) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  bool keep = false; uint32_t klen = 0, slot = 0; Combined c; c.cnt = 0; c.sum = 0; c.mnk = c.mxk = 0; c.fz = ~0ull; c.nullrows = 0; c.present = false;
+  bool keep = false; uint32_t klen = 0; Combined c; c.cnt = 0; c.sum = 0; c.mnk = c.mxk = 0; c.fz = ~0ull; c.nullrows = 0; c.present = false;
+  GidKey gk; gk.k0 = gk.k1 = 0; gk.len = 0; gk.pad = 0;
   double mn = 0, mx = 0, avg = 0;
   bool agg_ok = false;
   if (g < P.n_groups) {
     c = combine_panes(P, g);
     if (c.present) {
-      uint64_t h = key_hash_of_gid(P.dict, g, klen, slot);
-      keep = P.world <= 1 || (int)(h % (uint64_t)P.world) == P.rank;
+      gk = P.dict.gid_key[g];
+      klen = gk.len == 0xFFFFFFFFu ? 0u : gk.len;
+      keep = P.world <= 1 || (int)(key_hash(gk) % (uint64_t)P.world) == P.rank;
       agg_ok = c.cnt != 0;
       if (agg_ok) {
         unsigned long long bmn = unord_bits(ORD_F64_MAX - c.mnk), bmx = unord_bits(c.mxk + ORD_F64_MIN);
@@ -628,7 +628,8 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams
   uint32_t row_pre = __popc(ballot & ((1u << lane) - 1u));
   uint32_t byte_inc = kb;
   for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, byte_inc, o); if (lane >= o) byte_inc += x; }
-  __shared__ uint32_t wrows[8], wbytes[8]; __shared__ unsigned long long base;
+  __shared__ uint32_t wrows[8], wbytes[8]; __shared__ unsigned long long base; __shared__ uint32_t s_tb;
+  __shared__ __align__(16) uint8_t stage[EMIT_STAGE + 8];
   if (lane == 31) { wrows[warp] = __popc(ballot); wbytes[warp] = byte_inc; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -636,26 +637,43 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams
     for (int i = 0; i < 8; i++) { uint32_t r = wrows[i], b = wbytes[i]; wrows[i] = tr; wbytes[i] = tb; tr += r; tb += b; }
     unsigned long long res = 0;
     if (tr) res = atomicAdd(P.out.cursor, ((unsigned long long)tr << 32) | tb);
-    base = res;
+    base = res; s_tb = tb;
     if (tr && ((res >> 32) + tr > P.out.row_cap || (res & 0xFFFFFFFFull) + tb > P.out.byte_cap)) { atomicOr(P.out.overflow, 1u); base = ~0ull; }
   }
   __syncthreads();
-  if (!keep || base == ~0ull) return;
-  uint64_t row = (base >> 32) + wrows[warp] + row_pre;
-  uint32_t boff = (uint32_t)(base & 0xFFFFFFFFull) + wbytes[warp] + (byte_inc - kb);
+  if (base == ~0ull) return;                          // block-uniform
   const EmitOut& O = P.out;
-  O.key_off[row] = (int32_t)boff;
-  O.key_valid[row] = slot != 0xFFFFFFFFu;
-  if (slot != 0xFFFFFFFFu) {
-    const DictSlot& sl = P.dict.slots[slot];
+  const uint32_t bbase = (uint32_t)(base & 0xFFFFFFFFull), tb = s_tb;
+  const uint32_t boff = bbase + wbytes[warp] + (byte_inc - kb);
+  // key bytes: staged in shared memory at their position relative to the block's (4 B aligned-down) output offset, then
+  // written with coalesced 32-bit stores (was: one scattered byte store per key byte)
+  const bool staged = tb <= (uint32_t)EMIT_STAGE;
+  const uint32_t abase = bbase & ~3u;
+  if (keep && klen) {
+    uint8_t* dst = staged ? stage + (boff - abase) : O.key_bytes + boff;
     if (klen <= (uint32_t)INLINE_KEY) {
-      uint64_t w[2] = {sl.k0, sl.k1};
-      for (uint32_t i = 0; i < klen; i++) O.key_bytes[boff + i] = (uint8_t)(w[i >> 3] >> ((i & 7) * 8));
+      const uint64_t w[2] = {gk.k0, gk.k1};
+      for (uint32_t i = 0; i < klen; i++) dst[i] = (uint8_t)(w[i >> 3] >> ((i & 7) * 8));
     } else {
-      const uint8_t* src = P.dict.arena + sl.k1;
-      for (uint32_t i = 0; i < klen; i++) O.key_bytes[boff + i] = src[i];
+      const uint8_t* src = P.dict.arena + gk.k1;
+      for (uint32_t i = 0; i < klen; i++) dst[i] = src[i];
     }
   }
+  if (staged && tb) {
+    __syncthreads();
+    const uint32_t lo = bbase - abase, hi = lo + tb;              // staged byte range [lo, hi)
+    const uint32_t w0 = (lo + 3u) >> 2, w1 = hi >> 2;              // full words [w0, w1)
+    for (uint32_t w = w0 + threadIdx.x; w < w1; w += 256)
+      reinterpret_cast<uint32_t*>(O.key_bytes + abase)[w] = reinterpret_cast<const uint32_t*>(stage)[w];
+    if (threadIdx.x == 0) {                                        // ragged edges (neighbouring blocks own the other bytes of these words)
+      for (uint32_t b = lo; b < min(w0 * 4u, hi); b++) O.key_bytes[abase + b] = stage[b];
+      for (uint32_t b = max(w1 * 4u, min(w0 * 4u, hi)); b < hi; b++) O.key_bytes[abase + b] = stage[b];
+    }
+  }
+  if (!keep) return;
+  const uint64_t row = (base >> 32) + wrows[warp] + row_pre;
+  O.key_off[row] = (int32_t)boff;
+  O.key_valid[row] = gk.len != 0xFFFFFFFFu;
   O.count[row] = (long long)c.cnt;
   O.mn[row] = mn; O.mx[row] = mx; O.avg[row] = avg; O.sum[row] = agg_ok ? c.sum : 0.0;
   O.agg_valid[row] = agg_ok;
@@ -740,7 +758,6 @@ __global__ void k_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictV
     }
     DictSlot* d = nd.slots + idx;
     d->k0 = s.k0; d->k1 = s.k1; d->hint = s.hint; d->len = s.len;
-    nd.slot_of_gid[s.state - 1] = idx;
     __threadfence();
     d->state = s.state;
   }

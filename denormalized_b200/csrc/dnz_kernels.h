@@ -58,12 +58,15 @@ struct __align__(32) DictSlot {
 // as "no hint".
 constexpr uint32_t SLOT_EMPTY = 0u, SLOT_LOCKED = 0xFFFFFFFFu;
 
+// key of a group id: inline words (or hash64 / arena offset for keys > INLINE_KEY) and length; len == 0xFFFFFFFF: the NULL key
+struct GidKey { uint64_t k0, k1; uint32_t len, pad; };
+
 struct DictView {
   DictSlot* slots; uint32_t mask;     // capacity - 1 (power of two, 4 * gcap)
   uint32_t gcap;                      // group ids must stay < gcap (capacity of the per-pane state arrays)
   uint32_t* n_groups;                 // device counter
   uint32_t* null_gid;                 // 0 = unassigned, 0xFFFFFFFF locked, else gid + 1 (group of the NULL key)
-  uint32_t* slot_of_gid;              // gid -> slot (0xFFFFFFFF for the NULL-key group)
+  GidKey* gid_key;                    // gid -> key (dense, written at insert: emission and the pane exchange read keys coalesced)
   uint8_t* arena; unsigned long long* arena_used; uint64_t arena_cap;   // bytes of keys longer than INLINE_KEY
   unsigned long long* key_bytes_total;                                  // sum of key lengths over all groups
 };

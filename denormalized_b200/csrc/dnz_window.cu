@@ -195,7 +195,7 @@ struct dnz_window {
   int64_t max_rows = 64ll << 20;
 
   // dictionary
-  DevBuf slots, slot_of_gid, arena;
+  DevBuf slots, gid_key, arena;
   // one 256 B device control block so that a single D2H copy fetches everything the host needs after a launch:
   //   +0   n_groups(u32) null_gid(u32) arena_used(u64) key_bytes_total(u64)
   //   +64  deferred-row count(u64) flags(u32)
@@ -435,7 +435,7 @@ DictView dnz_window::dict_view() const {
   d.n_groups = c32; d.null_gid = c32 + 1;
   d.arena_used = reinterpret_cast<unsigned long long*>(c32 + 2);
   d.key_bytes_total = reinterpret_cast<unsigned long long*>(c32 + 4);
-  d.slot_of_gid = slot_of_gid.as<uint32_t>();
+  d.gid_key = gid_key.as<GidKey>();
   d.arena = arena.as<uint8_t>(); d.arena_cap = arena_cap;
   return d;
 }
@@ -445,10 +445,10 @@ void dnz_window::dict_alloc(uint32_t new_gcap) {
   uint32_t new_cap = new_gcap * 4;     // load factor <= 25 %: the probe length of the slowest lane paces a warp
   DevBuf ns, ng;
   ns.alloc((size_t)new_cap * sizeof(DictSlot)); CK(cudaMemsetAsync(ns.p, 0, ns.bytes, stream));
-  ng.alloc((size_t)new_gcap * 4); CK(cudaMemsetAsync(ng.p, 0xFF, ng.bytes, stream));
+  ng.alloc((size_t)new_gcap * sizeof(GidKey)); CK(cudaMemsetAsync(ng.p, 0, ng.bytes, stream));
   if (dict_cap) {
-    CK(cudaMemcpyAsync(ng.p, slot_of_gid.p, (size_t)gcap * 4, cudaMemcpyDeviceToDevice, stream));
-    DictView nd = dict_view(); nd.slots = ns.as<DictSlot>(); nd.mask = new_cap - 1; nd.gcap = new_gcap; nd.slot_of_gid = ng.as<uint32_t>();
+    CK(cudaMemcpyAsync(ng.p, gid_key.p, (size_t)gcap * sizeof(GidKey), cudaMemcpyDeviceToDevice, stream));
+    DictView nd = dict_view(); nd.slots = ns.as<DictSlot>(); nd.mask = new_cap - 1; nd.gcap = new_gcap; nd.gid_key = ng.as<GidKey>();
     CK(launch_dict_rehash(slots.as<DictSlot>(), dict_cap, nd, stream)); stats.total_launches++;
     // grow every live pane
     auto grow = [&](DevBuf& b, size_t elem, int fill) {
@@ -463,7 +463,7 @@ void dnz_window::dict_alloc(uint32_t new_gcap) {
     pane_pool.clear();
     CK(cudaStreamSynchronize(stream));
   }
-  slots = std::move(ns); slot_of_gid = std::move(ng);
+  slots = std::move(ns); gid_key = std::move(ng);
   dict_cap = new_cap; gcap = new_gcap;
 }
 void dnz_window::dict_grow() {
