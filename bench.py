@@ -186,7 +186,7 @@ def run_reference(args, wl):
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference algorithm (oracle/, hash-partitioned over all host cores); the Rust "
                     "reference itself cannot be built in this image"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=claim_stdout(), flush=True)
 
 
 def workload_config(args, wl, world):
@@ -250,8 +250,23 @@ def export_all(d, batches):
     return arr
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so fd 1 is pointed at
+    stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     wl = dict(WORKLOADS[args.workload])
     if args.rows:
         wl["rows"] = args.rows
@@ -492,7 +507,7 @@ def main():
                 "e2e": e2e, "cpu_baseline": cpu}
         if exchange:
             line["exchange"] = exchange
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
