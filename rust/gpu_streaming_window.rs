@@ -50,6 +50,21 @@ extern "C" {
     fn dnz_window_poll_ready(w: *mut DnzWindow, out: *mut FFI_ArrowArray, schema: *mut FFI_ArrowSchema, has_output: *mut i32) -> i32;
     fn dnz_window_last_error(w: *const DnzWindow) -> *const c_char;
     fn dnz_window_destroy(w: *mut DnzWindow);
+    // capacity hint: device staging for host batches, reserved when the stream is created (not while it runs)
+    fn dnz_window_reserve_input(w: *mut DnzWindow, bytes_per_launch: i64) -> i32;
+    // multi-GPU pane exchange: one handle per GPU, partition -> device; the shim would drive these around
+    // an ncclGroupStart/ncclSend/ncclRecv/ncclGroupEnd all-to-all (cudarc::nccl) once per closed pane group
+    fn dnz_window_set_exchange(w: *mut DnzWindow, rank: i32, world: i32) -> i32;
+    fn dnz_window_process(w: *mut DnzWindow, local_watermark_ms: *mut i64) -> i32;
+    fn dnz_window_export_partials(w: *mut DnzWindow, watermark_ms: i64, out: *mut DnzPartials) -> i32;
+    fn dnz_window_import_partials(w: *mut DnzWindow, entries: *const u8, src_counts: *const i64, key_bytes: *const u8,
+                                  src_key_bytes: *const i64, pane_lo: i64, pane_hi: i64) -> i32;
+    fn dnz_window_flush(w: *mut DnzWindow, watermark_ms: i64) -> i32;
+}
+#[repr(C)]
+pub struct DnzPartials {
+    n_entries: i64, entries: *const u8, owner_counts: *const i64, key_bytes_len: i64, key_bytes: *const u8,
+    owner_key_bytes: *const i64, pane_lo: i64, pane_hi: i64,
 }
 
 fn dnz_err(w: *const DnzWindow) -> DataFusionError {
