@@ -31,10 +31,16 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ int64_t s_b0;
   const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILES_PER_CTA;
-  if (threadIdx.x == 0) {      // batch that owns tile t0: last b with tile0 <= t0
-    int64_t lo = 0, hi = n_batches - 1;
-    while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (batches[mid].tile0 <= t0) lo = mid; else hi = mid - 1; }
-    s_b0 = lo;
+  if (warp == 0) {             // batch that owns tile t0: last b with tile0 <= t0 (tile0 is non-decreasing); 32-ary search by one
+    int64_t lo = 0, hi = n_batches;   // warp: 2 dependent load rounds for 1 K batches instead of 10
+    while (hi - lo > 1) {
+      const int64_t step = (hi - lo + 31) / 32, b = lo + step * lane;
+      const bool ok = b < hi && batches[b].tile0 <= t0;
+      const unsigned m = __ballot_sync(0xffffffffu, ok) | 1u;
+      const int last = 31 - __clz((int)m);
+      lo = lo + step * last; hi = min(hi, lo + step);
+    }
+    if (lane == 0) s_b0 = lo;
   }
   __syncthreads();
   int64_t lo = s_b0;
@@ -43,6 +49,7 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
   const BatchDesc bd = batches[lo];
   int64_t row0 = (t - bd.tile0) * TILE;
   int n = (int)min((int64_t)TILE, bd.n_rows - row0);
+  const int32_t o_lane = lane < 2 ? bd.off[row0 + (lane ? n : 0)] : 0;      // key byte range: in flight while the timestamps stream
   long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
   const long long* ts = reinterpret_cast<const long long*>(bd.ts) + row0;
   if (!bd.ts_valid && (reinterpret_cast<uintptr_t>(ts) & 15u) == 0) {
@@ -62,10 +69,10 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
     mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
+  const int32_t o0 = __shfl_sync(0xffffffffu, o_lane, 0), o1 = __shfl_sync(0xffffffffu, o_lane, 1);
   if (lane == 0) {
     TileDesc td;
     td.batch = (int32_t)lo; td.row0 = (int32_t)row0; td.n_rows = n; td.flags = 0;
-    int32_t o0 = bd.off[row0], o1 = bd.off[row0 + n];
     td.byte0 = o0; td.byte_len = o1 - o0; td.pad = 0;
     td.ts_min = mn; td.ts_max = mx; td.pane_lo = 0;
     if (cnt == 0) td.flags |= TILE_EMPTY;
