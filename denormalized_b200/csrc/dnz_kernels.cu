@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_deferred(const __grid_constant__ AggPar
 }
 
 // =================================================================================================
-// k_aggregate: persistent (two CTAs of 17 warps per SM), warp-specialised.
+// k_aggregate: persistent (two CTAs of 14 warps per SM), warp-specialised.
 //
 // The last warp is the TMA producer.  It claims tiles from a global counter (stream order), resolves their descriptors,
 // and per tile: waits for the ring slot, writes the tile header (row count, key byte base, resolved pane state array +
@@ -223,7 +223,7 @@ struct __align__(16) TileFetch {     // what the producer needs to hand one tile
 struct AggSmem {
   Stage st[STAGES];
   WarpQueue q[CONSUMER_WARPS];
-  TileFetch fetch[1][8];
+  TileFetch fetch[2][8];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
 };
@@ -353,17 +353,22 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
     constexpr uint32_t CLAIM = 4;
     const uint32_t n_tiles = (uint32_t)(P.tile_end - P.tile_begin);
     uint32_t it = 0;
-    for (;;) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(P.tile_counter, CLAIM);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= n_tiles) break;
-      if (lane < (int)CLAIM) fetch(P.tile_begin + base + lane, S.fetch[0][lane]);
+    // the NEXT claim (atomic + three dependent descriptor loads, ~4 us) is resolved while the current one feeds the ring
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.tile_counter, CLAIM);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base < n_tiles && lane < (int)CLAIM) fetch(P.tile_begin + base + lane, S.fetch[0][lane]);
+    int buf = 0;
+    while (base < n_tiles) {
+      uint32_t nbase = 0;
+      if (lane == 0) nbase = atomicAdd(P.tile_counter, CLAIM);
+      nbase = __shfl_sync(0xffffffffu, nbase, 0);
+      if (nbase < n_tiles && lane < (int)CLAIM) fetch(P.tile_begin + nbase + lane, S.fetch[buf ^ 1][lane]);
       __syncwarp();
       if (lane == 0) {
         for (uint32_t j = 0; j < CLAIM && base + j < n_tiles; j++, it++) {
           const int s = it % STAGES;
-          const TileFetch& f = S.fetch[0][j];
+          const TileFetch& f = S.fetch[buf][j];
           mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);
           S.st[s].hdr = f.h;
           if (f.h.flags & TILE_FAST) {
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
         }
       }
       it = __shfl_sync(0xffffffffu, it, 0);
+      base = nbase; buf ^= 1;
     }
     if (lane == 0) {                                   // end marker for the consumers
       const int s = it % STAGES;
