@@ -305,11 +305,18 @@ def main():
     GROUP = int(os.environ.get('DNZ_BENCH_GROUP', '1024'))       # batches (64 Mi rows) pushed between polls: emitted windows are consumed as the stream advances
 
     def step_device(w):
+        """One pass over the device-resident stream.  Batches are pushed 64 Mi rows at a time; the operator pipelines them (tile scan
+        of group g+1 | aggregate + emission of group g | verification of group g-1) and the emitted windows are consumed as the
+        stream advances with the non-forcing poll, so the host never waits between two kernels."""
         n_out = 0
         for g0 in range(0, dev.n_batches, GROUP):
             n = min(GROUP, dev.n_batches - g0)
             w.push_device(array=C.cast(C.byref(dev.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
-            n_out += w.poll_device().n_rows
+            while True:
+                r = w.poll_device_ready()
+                if r.n_rows == 0:
+                    break
+                n_out += r.n_rows
         # close the remaining windows a few at a time: one poll must stay below 2 GiB of key bytes (Utf8 offsets are 32-bit),
         # which 10 M 36-byte keys x 12 open sliding windows (cfg 5) would exceed
         step_ms = max(wl["slide_ms"] or wl["window_ms"], 1000) * (1 if G >= 4_000_000 else 64)
@@ -317,7 +324,11 @@ def main():
         while wm < close_wm:
             wm = min(wm + step_ms, close_wm)
             w.flush(wm)
-            n_out += w.poll_device().n_rows
+            while True:
+                r = w.poll_device()
+                if r.n_rows == 0:
+                    break
+                n_out += r.n_rows
         return n_out
 
     def barrier():

@@ -23,6 +23,7 @@ FLAG_FORCE_GENERIC = 2
 FLAG_NO_HINTS = 4
 FLAG_NO_QUEUE = 8
 FLAG_NO_PRIVATE = 16
+FLAG_SYNCHRONOUS = 32
 INTERNAL_METADATA_COLUMN = "_streaming_internal_metadata"   # crates/common/src/lib.rs:5
 
 
@@ -83,14 +84,15 @@ class StatsC(C.Structure):
                 ("groups", C.c_int64), ("agg_launches", C.c_int64), ("total_launches", C.c_int64),
                 ("agg_kernel_ms", C.c_double), ("agg_algorithmic_bytes", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("deferred_rows", C.c_int64), ("generic_tiles", C.c_int64),
-                ("fast_tiles", C.c_int64), ("late_batches", C.c_int64), ("exchanged_out", C.c_int64), ("exchanged_in", C.c_int64)]
+                ("fast_tiles", C.c_int64), ("late_batches", C.c_int64), ("exchanged_out", C.c_int64), ("exchanged_in", C.c_int64),
+                ("h2d_pageable_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dnz_window_poll", "dnz_window_poll_ready",
-           "dnz_window_poll_device",
+           "dnz_window_poll_device", "dnz_window_poll_device_ready",
            "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
            "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_process", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
@@ -123,6 +125,8 @@ def lib():
         L.dnz_window_poll_ready.argtypes = [C.c_void_p, C.POINTER(ArrowArrayC), C.POINTER(ArrowSchemaC), C.POINTER(C.c_int32)]
         L.dnz_window_poll_device.restype = C.c_int32
         L.dnz_window_poll_device.argtypes = [C.c_void_p, C.POINTER(DeviceResultC)]
+        L.dnz_window_poll_device_ready.restype = C.c_int32
+        L.dnz_window_poll_device_ready.argtypes = [C.c_void_p, C.POINTER(DeviceResultC)]
         L.dnz_window_flush.restype = C.c_int32
         L.dnz_window_flush.argtypes = [C.c_void_p, C.c_int64]
         L.dnz_window_stats.restype = C.c_int32
@@ -281,6 +285,11 @@ class GpuStreamingWindow:
     def poll_device(self) -> DeviceResultC:
         r = DeviceResultC()
         self._check(self._L.dnz_window_poll_device(self._h, C.byref(r)))
+        return r
+
+    def poll_device_ready(self) -> DeviceResultC:
+        r = DeviceResultC()
+        self._check(self._L.dnz_window_poll_device_ready(self._h, C.byref(r)))
         return r
 
     def fetch_device_result(self, r: DeviceResultC, max_keys=None) -> dict:

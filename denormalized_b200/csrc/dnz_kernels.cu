@@ -22,12 +22,19 @@ __global__ void k_init_minmax(BatchMinMax* mm, int64_t n) {
   if (i < n) { mm[i].ts_min = INT64_MAX; mm[i].ts_max = INT64_MIN; mm[i].n_valid = 0; mm[i].key_bytes = 0; mm[i].n_fast = 0; mm[i].n_tiles = 0; }
 }
 
-// one warp per tile, SCAN_TILES_PER_CTA consecutive tiles per CTA; aligned tiles are read with 128-bit loads.  The batch that
-// owns a tile is found by ONE binary search per CTA (10 dependent loads for 1 K batches -- per warp that search was three
-// quarters of the kernel's time); warps walk forward from there.
+// One warp per tile, SCAN_TILES_PER_CTA consecutive tiles per CTA, four CONSECUTIVE tiles per warp.  The batch that owns the
+// CTA's first tile is found by one 32-ary search; warps walk forward from there.  The kernel has to stream 8 B per row and was
+// instruction-bound (605 warp instructions per 416-row tile: 64-bit min/max chains, 64-bit shuffles, a 64-bit division), so:
+//   * timestamps are reduced as 32-bit offsets from the tile's first timestamp (u = ts - first + 2^31: one 64-bit subtract,
+//     an OR of the high words that proves the offsets fit, 32-bit min / max); a tile whose timestamps spread over more than
+//     +-24 days takes the 64-bit path
+//   * the warp reduction is three REDUX instructions
+//   * the pane of the minimum comes from one multiplication by 1 / pane_ms in double precision (exact below 2^53) plus a fix-up
+//   * the per-batch results are accumulated over the warp's tiles and flushed with one set of atomics per batch change.
 constexpr int SCAN_TILES_PER_CTA = 32;
-__global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__ batches, int64_t n_batches, int64_t n_tiles,
-                                                    int64_t pane_ms, TileDesc* __restrict__ tiles, BatchMinMax* mm, int allow_fast) {
+constexpr int SCAN_TILES_PER_WARP = 4;
+__global__ void __launch_bounds__(256, 3) k_tile_scan(const BatchDesc* __restrict__ batches, int64_t n_batches, int64_t n_tiles,
+                                                    int64_t pane_ms, double inv_pane_ms, TileDesc* __restrict__ tiles, BatchMinMax* mm, int allow_fast) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ int64_t s_b0;
   const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILES_PER_CTA;
@@ -44,62 +51,106 @@ __global__ void __launch_bounds__(256) k_tile_scan(const BatchDesc* __restrict__
   }
   __syncthreads();
   int64_t lo = s_b0;
-  for (int64_t t = t0 + warp; t < t0 + SCAN_TILES_PER_CTA && t < n_tiles; t += 8) {
-  while (lo + 1 < n_batches && batches[lo + 1].tile0 <= t) lo++;
-  const BatchDesc bd = batches[lo];
-  int64_t row0 = (t - bd.tile0) * TILE;
-  int n = (int)min((int64_t)TILE, bd.n_rows - row0);
-  const int32_t o_lane = lane < 2 ? bd.off[row0 + (lane ? n : 0)] : 0;      // key byte range: in flight while the timestamps stream
-  long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
-  const long long* ts = reinterpret_cast<const long long*>(bd.ts) + row0;
-  if (!bd.ts_valid && (reinterpret_cast<uintptr_t>(ts) & 15u) == 0) {
-    const longlong2* p = reinterpret_cast<const longlong2*>(ts);
-    const int np = n >> 1;
-#pragma unroll 4
-    for (int i = lane; i < np; i += 32) { longlong2 v = __ldg(p + i); mn = min(mn, min(v.x, v.y)); mx = max(mx, max(v.x, v.y)); }
-    if ((n & 1) && lane == 0) { long long v = ts[n - 1]; mn = min(mn, v); mx = max(mx, v); }
-    cnt = (lane == 0) ? n : 0;
-  } else {
-    for (int r = lane; r < n; r += 32) {
-      bool ok = bd.ts_valid == nullptr || bit_at(bd.ts_valid, bd.ts_vbit + row0 + r);
-      if (ok) { long long v = ts[r]; mn = min(mn, v); mx = max(mx, v); cnt++; }
+  // per-batch accumulators of this warp (meaningful in lane 0)
+  int64_t acc_b = -1; long long acc_mn = INT64_MAX, acc_mx = INT64_MIN; unsigned long long acc_valid = 0, acc_bytes = 0, acc_fast = 0, acc_tiles = 0;
+  auto flush = [&]() {
+    if (lane == 0 && acc_b >= 0) {
+      BatchMinMax* m = mm + acc_b;
+      if (acc_valid) { atomicMin((long long*)&m->ts_min, acc_mn); atomicMax((long long*)&m->ts_max, acc_mx); atomicAdd((unsigned long long*)&m->n_valid, acc_valid); }
+      atomicAdd((unsigned long long*)&m->key_bytes, acc_bytes); atomicAdd((unsigned long long*)&m->n_tiles, acc_tiles);
+      if (acc_fast) atomicAdd((unsigned long long*)&m->n_fast, acc_fast);
+    }
+    acc_mn = INT64_MAX; acc_mx = INT64_MIN; acc_valid = acc_bytes = acc_fast = acc_tiles = 0;
+  };
+  const int64_t tw0 = t0 + (int64_t)warp * SCAN_TILES_PER_WARP;
+  for (int64_t t = tw0; t < tw0 + SCAN_TILES_PER_WARP && t < n_tiles; t++) {
+    while (lo + 1 < n_batches && batches[lo + 1].tile0 <= t) lo++;
+    if (lo != acc_b) { flush(); acc_b = lo; }
+    const BatchDesc bd = batches[lo];
+    const int64_t row0 = (t - bd.tile0) * TILE;
+    const int n = (int)min((int64_t)TILE, bd.n_rows - row0);
+    const int32_t o_lane = lane < 2 ? bd.off[row0 + (lane ? n : 0)] : 0;      // key byte range: in flight while the timestamps stream
+    long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
+    const long long* ts = reinterpret_cast<const long long*>(bd.ts) + row0;
+    if (!bd.ts_valid && (reinterpret_cast<uintptr_t>(ts) & 15u) == 0) {
+      const longlong2* p = reinterpret_cast<const longlong2*>(ts);
+      const int np = n >> 1;
+      static_assert(TILE <= 7 * 64, "seven 16 B loads per lane cover a tile");
+      // all loads of the tile are issued back to back (a loop with a per-lane trip count ends up in the compiler's serial
+      // remainder loop: one dependent round trip per iteration)
+      longlong2 v[7];
+      const long long first = __ldg(ts);                                    // same address for the whole warp: one transaction
+      const long long tail = (n & 1) ? __ldg(ts + n - 1) : first;           // odd row count (last tile of a batch)
+#pragma unroll
+      for (int k = 0; k < 7; k++) { const int i = lane + 32 * k; v[k] = i < np ? __ldg(p + i) : make_longlong2(first, tail); }
+      const long long basem = first - 0x80000000ll;
+      uint32_t mn32 = 0xFFFFFFFFu, mx32 = 0u, orhi = 0u;
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        const unsigned long long u0 = (unsigned long long)(v[k].x - basem), u1 = (unsigned long long)(v[k].y - basem);
+        orhi |= (uint32_t)(u0 >> 32) | (uint32_t)(u1 >> 32);
+        mn32 = min(mn32, min((uint32_t)u0, (uint32_t)u1)); mx32 = max(mx32, max((uint32_t)u0, (uint32_t)u1));
+      }
+      { const unsigned long long ut = (unsigned long long)(tail - basem); orhi |= (uint32_t)(ut >> 32); mn32 = min(mn32, (uint32_t)ut); mx32 = max(mx32, (uint32_t)ut); }
+      orhi = __reduce_or_sync(0xffffffffu, orhi);
+      if (orhi == 0u) {
+        mn32 = __reduce_min_sync(0xffffffffu, mn32); mx32 = __reduce_max_sync(0xffffffffu, mx32);
+        mn = basem + (long long)mn32; mx = basem + (long long)mx32;
+      } else {                                                             // widely spread timestamps: 64-bit path
+#pragma unroll
+        for (int k = 0; k < 7; k++) { mn = min(mn, min(v[k].x, v[k].y)); mx = max(mx, max(v[k].x, v[k].y)); }
+        mn = min(mn, tail); mx = max(mx, tail);
+        for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+      }
+      cnt = n;
+    } else {
+      for (int r = lane; r < n; r += 32) {
+        bool ok = bd.ts_valid == nullptr || bit_at(bd.ts_valid, bd.ts_vbit + row0 + r);
+        if (ok) { long long v = ts[r]; mn = min(mn, v); mx = max(mx, v); cnt++; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+    }
+    const int32_t o0 = __shfl_sync(0xffffffffu, o_lane, 0), o1 = __shfl_sync(0xffffffffu, o_lane, 1);
+    if (lane == 0) {
+      TileDesc td;
+      td.batch = (int32_t)lo; td.row0 = (int32_t)row0; td.n_rows = n; td.flags = 0;
+      td.byte0 = o0; td.byte_len = o1 - o0; td.pad = 0;
+      td.ts_min = mn; td.ts_max = mx; td.pane_lo = 0;
+      if (cnt == 0) td.flags |= TILE_EMPTY;
+      else {
+        // floor(mn / pane_ms): timestamps in [0, 2^53) (negative ones are rejected by the host before aggregation, and the pane of
+        // such a tile is never used); the product is within one unit of the quotient, the remainder test makes it exact
+        long long q;
+        if (mn >= 0 && mn < (1ll << 53)) {
+          q = (long long)((double)mn * inv_pane_ms);
+          long long r = mn - q * pane_ms;
+          if (r < 0) { q--; r += pane_ms; } else if (r >= pane_ms) { q++; r -= pane_ms; }
+        } else q = mn / pane_ms;
+        td.pane_lo = q;
+        if (mx < (q + 1) * pane_ms) td.flags |= TILE_PANE_UNIFORM;     // == (mx / pane_ms == pane_lo) for ts >= 0
+        acc_mn = min(acc_mn, mn); acc_mx = max(acc_mx, mx); acc_valid += (unsigned long long)cnt;
+      }
+      bool aligned = ((reinterpret_cast<uintptr_t>(bd.ts + row0) | reinterpret_cast<uintptr_t>(bd.val + row0) |
+                       reinterpret_cast<uintptr_t>(bd.off + row0) | reinterpret_cast<uintptr_t>(bd.bytes)) & 15u) == 0;
+      if (allow_fast && (bd.flags & BATCH_BULK_OK) && aligned && !bd.ts_valid && !bd.val_valid && !bd.key_valid &&
+          td.byte_len <= BCAP && cnt > 0)
+        td.flags |= TILE_FAST;
+      tiles[t] = td;
+      acc_bytes += (unsigned long long)td.byte_len; acc_tiles += 1;
+      if (td.flags & TILE_FAST) acc_fast += 1;
     }
   }
-  for (int o = 16; o; o >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  const int32_t o0 = __shfl_sync(0xffffffffu, o_lane, 0), o1 = __shfl_sync(0xffffffffu, o_lane, 1);
-  if (lane == 0) {
-    TileDesc td;
-    td.batch = (int32_t)lo; td.row0 = (int32_t)row0; td.n_rows = n; td.flags = 0;
-    td.byte0 = o0; td.byte_len = o1 - o0; td.pad = 0;
-    td.ts_min = mn; td.ts_max = mx; td.pane_lo = 0;
-    if (cnt == 0) td.flags |= TILE_EMPTY;
-    else {
-      td.pane_lo = mn / pane_ms;                       // timestamps >= 0 are enforced on the host before aggregation
-      if (mx < (td.pane_lo + 1) * pane_ms) td.flags |= TILE_PANE_UNIFORM;     // == (mx / pane_ms == pane_lo) for ts >= 0, without a second 64-bit division (~150 instructions, issued for the whole warp)
-      atomicMin((long long*)&mm[lo].ts_min, mn); atomicMax((long long*)&mm[lo].ts_max, mx);
-      atomicAdd((unsigned long long*)&mm[lo].n_valid, (unsigned long long)cnt);
-    }
-    bool aligned = ((reinterpret_cast<uintptr_t>(bd.ts + row0) | reinterpret_cast<uintptr_t>(bd.val + row0) |
-                     reinterpret_cast<uintptr_t>(bd.off + row0) | reinterpret_cast<uintptr_t>(bd.bytes)) & 15u) == 0;
-    if (allow_fast && (bd.flags & BATCH_BULK_OK) && aligned && !bd.ts_valid && !bd.val_valid && !bd.key_valid &&
-        td.byte_len <= BCAP && cnt > 0)
-      td.flags |= TILE_FAST;
-    tiles[t] = td;
-    atomicAdd((unsigned long long*)&mm[lo].key_bytes, (unsigned long long)td.byte_len);
-    atomicAdd((unsigned long long*)&mm[lo].n_tiles, 1ull);
-    if (td.flags & TILE_FAST) atomicAdd((unsigned long long*)&mm[lo].n_fast, 1ull);
-  }
-  }
+  flush();
 }
 
 cudaError_t launch_tile_scan(const BatchDesc* batches, int64_t n_batches, int64_t n_tiles, int64_t pane_ms, TileDesc* tiles,
                              BatchMinMax* minmax, bool allow_fast, cudaStream_t s) {
   if (n_batches <= 0 || n_tiles <= 0) return cudaSuccess;
   k_init_minmax<<<(unsigned)((n_batches + 255) / 256), 256, 0, s>>>(minmax, n_batches);
-  k_tile_scan<<<(unsigned)((n_tiles + SCAN_TILES_PER_CTA - 1) / SCAN_TILES_PER_CTA), 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, tiles, minmax, allow_fast ? 1 : 0);
+  k_tile_scan<<<(unsigned)((n_tiles + SCAN_TILES_PER_CTA - 1) / SCAN_TILES_PER_CTA), 256, 0, s>>>(batches, n_batches, n_tiles, pane_ms, 1.0 / (double)pane_ms, tiles, minmax, allow_fast ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -491,17 +542,19 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
           agg_apply_slow(P, H, r, st.ts[r], v, gid);
         }
       }
-      // count and sum by lane pairs: lanes 2j / 2j+1 serve the row of lane j (+16): {cnt, sum} as ONE red.add.f64 on adjacent
-      // words of the state sector -> 16 sectors per instruction, half the reduction wavefronts of two scalar reductions
+      // count and sum by lane pairs: in each of two instructions lanes 2j / 2j+1 update {cnt, sum} of ONE row -- adjacent words of
+      // the state sector, 16 sectors per instruction, half the reduction wavefronts of two scalar reductions.  First the rows of
+      // the even lanes (the row's own lane adds its value to sum, the odd partner adds 1.0 to cnt), then the rows of the odd
+      // lanes: one xor-shuffle of the packed group id serves both (the value never leaves its lane).
       if (mbase != nullptr) {                       // warp-uniform
+        const uint32_t pk2 = __shfl_xor_sync(0xffffffffu, pk, 1);
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-          const int src = (lane >> 1) + 16 * half;
-          const uint32_t pk2 = __shfl_sync(0xffffffffu, pk, src);
-          const uint32_t lo2 = __shfl_sync(0xffffffffu, blo, src), hi2 = __shfl_sync(0xffffffffu, bhi, src);
-          if (pk2 & (1u << 29)) {
-            GroupState* s2 = mbase + (pk2 & 0x1FFFFFFFu);
-            red_add_f64(&s2->cnt + odd, odd ? __hiloint2double((int)hi2, (int)lo2) : 1.0);
+          const bool own = (odd == half);
+          const uint32_t p = own ? pk : pk2;
+          if (p & (1u << 29)) {
+            GroupState* s2 = mbase + (p & 0x1FFFFFFFu);
+            red_add_f64(own ? &s2->sum : &s2->cnt, own ? v : 1.0);
           }
         }
       }
@@ -609,7 +662,11 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ EmitParams
   GidKey gk; gk.k0 = gk.k1 = 0; gk.len = 0; gk.pad = 0;
   double mn = 0, mx = 0, avg = 0;
   bool agg_ok = false;
-  if (g < P.n_groups) {
+  if (P.gate) {                                       // block-uniform
+    if ((P.gate[0] | P.gate[4] | P.gate[8]) != 0ull) { if (threadIdx.x == 0 && P.blocked) *P.blocked = 1u; return; }
+  }
+  const uint32_t n_groups = min(min(*P.dict.n_groups, P.dict.gcap), P.n_groups);
+  if (g < n_groups) {
     c = combine_panes(P, g);
     if (c.present) {
       gk = P.dict.gid_key[g];

@@ -125,8 +125,12 @@ struct EmitParams {
   int32_t n_panes; int32_t has_filter; int32_t filter_col /*0 count 1 min 2 max 3 avg 4 sum*/; int32_t filter_op;
   double filter_lit;
   int64_t wstart, wend;
-  uint32_t n_groups;
+  uint32_t n_groups;             // upper bound (grid size); the kernel clamps to the device counter
   int32_t rank, world;           // multi-GPU: emit only keys with hash64 % world == rank (world <= 1: all)
+  // speculative pipeline: gate[0], gate[4], gate[8] are the deferred-row counters of the three pipeline slots (nullptr: not
+  // gated).  While any of them is non-zero some rows of an earlier launch have not been applied yet: the launch does nothing
+  // and raises *blocked so that the host issues it again after the replay.
+  const unsigned long long* gate; uint32_t* blocked;
   DictView dict;
   EmitOut out;
 };

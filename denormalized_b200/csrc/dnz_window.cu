@@ -2,6 +2,7 @@
 //
 // Mirrors GroupedWindowAggStream (crates/core/src/physical_plan/continuous/grouped_window_agg_stream.rs):
 //   push/poll           <-> poll_next_inner (:326-349): watermark -> windows -> frames.push -> process_watermark -> trigger
+//   pipeline (Slot)     <-> the stream's poll loop, three superbatches deep: scan k+1 | aggregate + emit k | verify k-1
 //   PaneStore           <-> window_frames: BTreeMap<SystemTime, GroupedAggWindowFrame> (:63-82), re-organised as hop-sized
 //                           panes shared by the L/S windows that overlap them
 //   Dictionary          <-> GroupValues (one per frame in the reference; one per stream here, ids are stable)
@@ -112,6 +113,23 @@ struct DevBuf {
   void alloc(size_t n) { release(); if (n == 0) n = 256; p = dev_alloc(n); bytes = n; }
   // grow without preserving contents
   void reserve(size_t n) { if (n > bytes) alloc(std::max(n, bytes + bytes / 2)); }
+  // grow in stream order on `st`, keeping the first `keep` bytes: no host synchronisation (work enqueued on `st` before this call
+  // still sees the old block, which is freed behind it)
+  void regrow_on(cudaStream_t st, size_t n, size_t keep) {
+    AllocCtx& c = alloc_ctx();
+    if (!c.async_ok) {
+      DevBuf nb; nb.alloc(n);
+      if (keep && p) CK(cudaMemcpyAsync(nb.p, p, keep, cudaMemcpyDeviceToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      *this = std::move(nb);
+      return;
+    }
+    void* np = nullptr;
+    CK(cudaMallocAsync(&np, n, st));
+    if (keep && p) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
+    if (p) cudaFreeAsync(p, st);
+    p = np; bytes = n;
+  }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -120,9 +138,9 @@ struct PinnedBuf {
   ~PinnedBuf() { if (p) cudaFreeHost(p); }
   void reserve(size_t n) {
     if (n <= bytes) return;
+    const size_t want = std::max(n, bytes * 2);
     if (p) cudaFreeHost(p);
     p = nullptr; bytes = 0;
-    size_t want = std::max(n, bytes * 2);
     CK(cudaMallocHost(&p, want)); bytes = want;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -152,6 +170,7 @@ struct Pane {
   DevBuf st, nullrows, fz;
 };
 
+
 struct PendingBatch {
   BatchDesc d{};
   int64_t key_bytes = 0;
@@ -159,11 +178,38 @@ struct PendingBatch {
   ArrowArray moved{};
 };
 
-// Batches queued for one aggregate pass (<= max_rows_per_launch rows).  Host batches are copied into the superbatch's
-// arena while the PREVIOUS superbatch is being aggregated, so PCIe transfers overlap kernels and host-side planning.
-struct Superbatch {
-  std::vector<PendingBatch> batches; int64_t rows = 0; int arena = 0; bool copies = false;
+// One superbatch (<= max_rows_per_launch rows) travelling through the pipeline.  Three of them rotate:
+//   FILLING   batches are being pushed; host batches are copied into the slot's arena as they arrive (copy stream)
+//   SEALED    the tile scan (per-batch watermarks, per-tile byte ranges) has been enqueued
+//   LAUNCHED  the aggregate launch and the emission of the windows it closes have been enqueued, a snapshot of the
+//             control block follows them in stream order
+//   FREE      the snapshot has been inspected on the host (`verify`): nothing was deferred, or it has been replayed
+// so that in steady state the host never waits between a kernel and the next one: while slot k's aggregate runs, slot k+1's
+// scan is already queued behind it and the host is one full superbatch ahead.
+constexpr int NSLOT = 3;
+struct Slot {
+  enum State { FREE, FILLING, SEALED, LAUNCHED };
+  State state = FREE;
+  int idx = 0;
+  std::vector<PendingBatch> batches; int64_t rows = 0; bool copies = false;
   std::vector<CopyDesc> gather;       // pinned host buffers pulled by one k_gather_copy launch when the superbatch is sealed
+  Arena arena; cudaEvent_t copy_done = nullptr;
+  DevBuf d_copy_descs; PinnedBuf h_copy_descs;
+  // tile scan
+  DevBuf d_batches, d_tiles, d_minmax; PinnedBuf h_batches, h_minmax; cudaEvent_t scan_done = nullptr;
+  std::vector<BatchDesc> bds; int64_t n_tiles = 0; bool scanned = false;
+  // aggregate launch (its own staging: the async copies read these buffers when the stream gets there)
+  DevBuf d_ptrs, d_defer[2]; PinnedBuf h_ptrs;
+  PinnedBuf snap; cudaEvent_t done = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false; double alg_bytes = 0;
+  // what was enqueued speculatively behind the aggregate launch (replayed by verify() when rows were deferred)
+  bool speculative = false;
+  int64_t t0 = 0, t1 = 0, pmin = 0, pmax = -1;
+  std::vector<int64_t> emit_starts;
+  uint64_t add_rows_bound = 0, add_bytes_bound = 0; int emit_set = 0;
+  int64_t rows_launched = 0;
+  std::vector<std::unique_ptr<Pane>> retired;      // panes whose last window was emitted behind this launch
+  size_t ctl_off() const { return 64 + 32 * (size_t)idx; }     // defer count (u64) flags (u32) tile counter (u32) emit-blocked (u32)
 };
 
 // Device columns of emitted rows.  Two sets: emission appends to one of them; a set whose rows have all been handed out is
@@ -173,13 +219,14 @@ struct Superbatch {
 struct ResultSet {
   DevBuf key_off, key_bytes, key_valid, count, mn, mx, avg, sum, agg_valid, wstart, wend;
   uint64_t row_cap = 0, byte_cap = 0;
-  uint64_t rows = 0, bytes = 0;           // host view of the cursor (exact after fetch_ctl)
+  uint64_t rows = 0, bytes = 0;           // host view of the cursor: an UPPER BOUND while launches are in flight, exact after fetch_ctl
   uint64_t exp_rows = 0, exp_bytes = 0;   // prefix already handed to the consumer
-  size_t ctl_off = 128;                   // cursor (u64) + overflow flag (u32) inside the control block
+  size_t ctl_off = 192;                   // cursor (u64) + overflow flag (u32) inside the control block
   PinnedBuf snap; cudaEvent_t snap_ev = nullptr; bool snap_issued = false;
 };
 
 enum { COL_COUNT = 0, COL_MIN = 1, COL_MAX = 2, COL_AVG = 3, COL_SUM = 4 };
+constexpr size_t CTL_BYTES = 256, CTL_MERGE_ERR = 224;
 
 }  // namespace
 
@@ -190,52 +237,55 @@ struct dnz_window {
   int key_col = -1, val_col = -1, meta_col = -1, ts_child = -1, n_input_cols = 0;
   int dev = 0; int sm_count = 148;
   cudaStream_t stream = nullptr; bool own_stream = false;
-  cudaStream_t copy_stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;
   int64_t L = 0, S = 0, pane_ms = 0; int panes_per_window = 1;
   int64_t max_rows = 64ll << 20;
 
   // dictionary
   DevBuf slots, gid_key, arena;
   // one 256 B device control block so that a single D2H copy fetches everything the host needs after a launch:
-  //   +0   n_groups(u32) null_gid(u32) arena_used(u64) key_bytes_total(u64)
-  //   +64  deferred-row count(u64) flags(u32)
-  //   +128 result cursor(u64: rows<<32|bytes) overflow(u32)
+  //   +0    n_groups(u32) null_gid(u32) arena_used(u64) key_bytes_total(u64)
+  //   +64 + 32 s   pipeline slot s: deferred-row count(u64) flags(u32) tile counter(u32) emit-blocked(u32)
+  //   +192  result set 0: cursor(u64: rows<<32|bytes) overflow(u32);  +208 result set 1
+  //   +224  pane-merge error flags (exchange)
   DevBuf d_ctl;
   char* ctl(size_t off) const { return d_ctl.as<char>() + off; }
   uint32_t dict_cap = 0, gcap = 0; uint64_t arena_cap = 0;
-  uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0; uint64_t defer_count_host = 0; uint32_t defer_flags_host = 0;
+  // host knowledge of the device counters: exact as of the last inspected snapshot ("known"), plus what launches enqueued since
+  // then can have added at most ("bound")
+  uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0, arena_used_host = 0;
+  int64_t rows_since_known = 0;
+  uint64_t defer_count_host = 0; uint32_t defer_flags_host = 0;
 
   // panes
   std::map<int64_t, std::unique_ptr<Pane>> panes;
+  std::map<int64_t, std::unique_ptr<Pane>> late_panes;     // one-batch panes of the exact late path (alive only inside a dirty run)
   std::vector<std::unique_ptr<Pane>> pane_pool;
   bool need_nullrows = false, need_fz = false;
   uint64_t next_tag = 1;   // pane instance tags (low 32 bits are stored in the hints)
   bool has_wm = false; int64_t wm = 0;
   int64_t emitted_upto = INT64_MIN;
 
-  // pending input
-  Superbatch cur, sealed; bool has_sealed = false; int64_t next_seq = 0;
-  std::vector<PendingBatch>* active = nullptr;    // batches of the superbatch being aggregated
-  Arena in_arena[2]; cudaEvent_t copy_done[2] = {nullptr, nullptr};
+  // pipeline
+  Slot slot[NSLOT]; int fill = 0; int64_t next_seq = 0;
+  std::vector<int> sealed_order;      // SEALED slots, oldest first
+  std::vector<int> launched_order;    // LAUNCHED slots, oldest first
+  Slot& cur() { return slot[fill]; }
+  bool in_process = false;            // an error thrown while true kills the stream (sticky), as the reference's panics do
 
   // scratch
-  struct Scan {
-    DevBuf d_batches, d_tiles, d_minmax; PinnedBuf h_batches, h_minmax, h_tiles; cudaEvent_t done = nullptr;
-    std::vector<BatchDesc> bds; int64_t n_tiles = 0; bool launched = false;
-  } scan[2];
-  Scan* cur_scan = nullptr;
-  DevBuf d_ptrs, d_defer[2], d_priv;
-  PinnedBuf h_stage, h_small;
+  DevBuf d_priv, d_copy_cursor;
+  PinnedBuf h_small;
   ResultSet rs[2]; int wr = 0; bool async_polls = false;
   ResultSet& R() { return rs[wr]; }
   cudaStream_t d2h_stream = nullptr;
-  bool res_consumed = false; bool ctl_fresh = false;
+  bool res_consumed = false;
 
   // multi-GPU pane exchange
   int rank = 0, world = 1;
   bool has_lwm = false; int64_t lwm = 0;          // local watermark (exchange mode: emission follows the GLOBAL one)
   int64_t exported_pane_upto = INT64_MIN;
-  DevBuf d_part_entries, d_part_keys, d_owner_cursor;
+  DevBuf d_part_entries, d_part_keys, d_owner_cursor, d_xptrs; PinnedBuf h_xptrs;
   std::vector<int64_t> h_owner_counts, h_owner_bytes;
   void export_partials(int64_t watermark, dnz_partials* out);
   void import_partials(const uint8_t* entries, const int64_t* src_counts, const uint8_t* key_bytes, const int64_t* src_key_bytes,
@@ -249,33 +299,48 @@ struct dnz_window {
   DictView dict_view() const;
   void dict_alloc(uint32_t new_gcap);
   void dict_grow();
-  void arena_grow();
+  void arena_grow(uint64_t at_least);
   void fetch_ctl();
+  void parse_ctl(const char* h);
+  template <class F> void for_each_live_pane(F f);
   Pane* get_pane(int64_t id, bool create);
+  Pane* find_pane(int64_t id);
   std::unique_ptr<Pane> new_pane(int64_t id);
   void ensure_side_arrays(Pane* p);
-  void retire_panes();
+  void retire_panes(Slot* sl);
   void push_host(ArrowArray* batch);
   void push_dev(const dnz_device_batch* b, int64_t n);
   void process_pending();
+  void drain();
   void seal_current();
-  void process_superbatch(Superbatch& sb);
+  void finish_copies(Slot& s);
+  void launch_scan(Slot& s);
+  void launch_slot(Slot& s);
+  void verify(Slot& s);
+  void release_slot(Slot& s);
   void prealloc();
-  void process_chunk(Superbatch& sb);
-  void launch_scan(Superbatch& sb);
-  void finish_copies(Superbatch& sb);
-  DevBuf d_copy_descs[2]; PinnedBuf h_copy_descs[2]; DevBuf d_copy_cursor;
-  void execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0, size_t rb0, size_t rb1,
-                   bool dirty, int64_t horizon, int64_t wm_after);
-  void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src);
-  void emit_normal(int64_t wm_new);
+  struct Run { size_t b0, b1; bool dirty; int64_t horizon, wm_after; };
+  void plan_runs(Slot& s, const std::vector<BatchMinMax>& mm, std::vector<Run>& runs);
+  struct RunGeom { int64_t t0 = 0, t1 = 0, pmin = INT64_MAX, pmax = INT64_MIN, rows = 0; double alg_bytes = 0; bool val_nulls = false; };
+  RunGeom run_geometry(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r);
+  void prepare_panes(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r, const RunGeom& g);
+  AggParams build_agg_params(Slot& s, const RunGeom& g, bool dirty, int64_t horizon, int out_list);
+  void launch_aggregate_pass(Slot& s, const RunGeom& g, AggParams& P, bool dirty);
+  void resolve_deferred(Slot& s, const RunGeom& g, bool dirty, int64_t horizon);
+  void execute_run_sync(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r);
+  void emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src, bool gated, Slot* sl);
+  void emit_normal(int64_t wm_new, bool gated, Slot* sl);
+  std::map<int64_t, Pane*> pane_sources();
   void ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes);
+  uint32_t groups_bound() const;
+  uint64_t key_bytes_bound() const;
   void reset_results();
   void reset_set(int i);
   void snapshot_results();
   void rotate_result_sets();
   bool set_drained(ResultSet& r);
   void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking);
+  void export_device(dnz_device_result* out, bool blocking);
   void fill_schema(ArrowSchema* schema);
 };
 
@@ -333,19 +398,19 @@ const char* agg_format(int kind) { return kind == DNZ_AGG_COUNT ? "l" : "g"; }
 
 }  // namespace
 
+
 // =================================================================================================
 dnz_window::~dnz_window() {
   cudaSetDevice(dev);
   if (copy_stream) cudaStreamSynchronize(copy_stream);
-  for (Superbatch* sb : {&cur, &sealed}) for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
   if (stream) cudaStreamSynchronize(stream);
+  for (Slot& s : slot) {
+    for (auto& pb : s.batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+    for (cudaEvent_t e : {s.copy_done, s.scan_done, s.done, s.ev0, s.ev1}) if (e) cudaEventDestroy(e);
+  }
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
   for (auto& r : rs) if (r.snap_ev) cudaEventDestroy(r.snap_ev);
-  for (auto& e : copy_done) if (e) cudaEventDestroy(e);
-  for (auto& sc : scan) if (sc.done) cudaEventDestroy(sc.done);
-  if (ev0) cudaEventDestroy(ev0);
-  if (ev1) cudaEventDestroy(ev1);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -412,13 +477,20 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
   CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
-  rs[0].ctl_off = 128; rs[1].ctl_off = 160;
+  rs[0].ctl_off = 192; rs[1].ctl_off = 208;
   for (auto& r : rs) { CK(cudaEventCreateWithFlags(&r.snap_ev, cudaEventDisableTiming)); r.snap.reserve(64); }
-  for (auto& e : copy_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  for (int i = 0; i < NSLOT; i++) {
+    Slot& s = slot[i]; s.idx = i;
+    CK(cudaEventCreateWithFlags(&s.copy_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.scan_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CK(cudaEventCreate(&s.ev0)); CK(cudaEventCreate(&s.ev1));
+    s.snap.reserve(CTL_BYTES);
+  }
+  slot[0].state = Slot::FILLING; fill = 0;
   CK(agg_kernel_setup());
 
-  d_ctl.alloc(256); CK(cudaMemsetAsync(d_ctl.p, 0, 256, stream));
+  d_ctl.alloc(CTL_BYTES); CK(cudaMemsetAsync(d_ctl.p, 0, CTL_BYTES, stream));
   uint64_t eg = c->expected_groups > 0 ? (uint64_t)c->expected_groups : (1ull << 16);
   uint64_t g0 = 1024; while (g0 < eg + eg / 8) g0 <<= 1;
   if (g0 > (1ull << 29)) fail(DNZ_ERR_INVALID, "expected_groups too large");
@@ -440,9 +512,20 @@ DictView dnz_window::dict_view() const {
   return d;
 }
 
+template <class F> void dnz_window::for_each_live_pane(F f) {
+  for (auto& kv : panes) f(kv.second.get());
+  for (auto& kv : late_panes) f(kv.second.get());
+  for (Slot& s : slot) for (auto& p : s.retired) f(p.get());
+}
+
+// Slots per group id.  The first probe of a key misses its home slot with probability ~ load / 2; every miss costs a second
+// scattered 32 B transaction (and a trip through the warp's retry queue), while an EMPTY slot is never touched by a lookup --
+// the L2 footprint of the table is its occupied sectors, not its capacity.  So small and medium tables are kept very sparse.
+static uint32_t dict_slots_per_group(uint32_t gcap_) { return gcap_ <= (1u << 20) ? 16u : gcap_ <= (1u << 23) ? 8u : 4u; }
+
 // (re)allocate dictionary + per-pane state arrays for `new_gcap` groups, preserving contents
 void dnz_window::dict_alloc(uint32_t new_gcap) {
-  uint32_t new_cap = new_gcap * 4;     // load factor <= 25 %: the probe length of the slowest lane paces a warp
+  uint32_t new_cap = new_gcap * dict_slots_per_group(new_gcap);
   DevBuf ns, ng;
   ns.alloc((size_t)new_cap * sizeof(DictSlot)); CK(cudaMemsetAsync(ns.p, 0, ns.bytes, stream));
   ng.alloc((size_t)new_gcap * sizeof(GidKey)); CK(cudaMemsetAsync(ng.p, 0, ng.bytes, stream));
@@ -450,16 +533,17 @@ void dnz_window::dict_alloc(uint32_t new_gcap) {
     CK(cudaMemcpyAsync(ng.p, gid_key.p, (size_t)gcap * sizeof(GidKey), cudaMemcpyDeviceToDevice, stream));
     DictView nd = dict_view(); nd.slots = ns.as<DictSlot>(); nd.mask = new_cap - 1; nd.gcap = new_gcap; nd.gid_key = ng.as<GidKey>();
     CK(launch_dict_rehash(slots.as<DictSlot>(), dict_cap, nd, stream)); stats.total_launches++;
-    // grow every live pane
-    auto grow = [&](DevBuf& b, size_t elem, int fill) {
+    // grow every live pane: the open ones, the one-batch late panes of a dirty run, and retired panes still awaiting their
+    // (possibly re-issued) emission
+    auto grow = [&](DevBuf& b, size_t elem, int fill_byte) {
       if (!b.p) return;
       DevBuf nb; nb.alloc((size_t)new_gcap * elem);
       CK(cudaMemcpyAsync(nb.p, b.p, (size_t)gcap * elem, cudaMemcpyDeviceToDevice, stream));
-      CK(cudaMemsetAsync((char*)nb.p + (size_t)gcap * elem, fill, (size_t)(new_gcap - gcap) * elem, stream));
+      CK(cudaMemsetAsync((char*)nb.p + (size_t)gcap * elem, fill_byte, (size_t)(new_gcap - gcap) * elem, stream));
       CK(cudaStreamSynchronize(stream));
       b = std::move(nb);
     };
-    for (auto& kv : panes) { grow(kv.second->st, sizeof(GroupState), 0); grow(kv.second->nullrows, 8, 0); grow(kv.second->fz, 8, 0xFF); }
+    for_each_live_pane([&](Pane* p) { grow(p->st, sizeof(GroupState), 0); grow(p->nullrows, 8, 0); grow(p->fz, 8, 0xFF); });
     pane_pool.clear();
     CK(cudaStreamSynchronize(stream));
   }
@@ -470,34 +554,57 @@ void dnz_window::dict_grow() {
   if (gcap >= (1u << 29)) fail(DNZ_ERR_NOMEM, "more than 2^29 groups");
   dict_alloc(gcap * 2);
 }
-void dnz_window::arena_grow() {
-  DevBuf na; na.alloc(arena_cap * 2);
+// Long-key arena.  Inserters reserve space with an atomicAdd BEFORE they know whether it fits, so after an overflow the device
+// counter has run past the capacity by the bytes of every failed attempt: an upper bound of what the deferred rows need.
+void dnz_window::arena_grow(uint64_t at_least) {
+  uint64_t ncap = std::max<uint64_t>(arena_cap * 2, at_least);
+  ncap = round_up(ncap, 1 << 20);
+  DevBuf na; na.alloc(ncap);
   CK(cudaMemcpyAsync(na.p, arena.p, arena_cap, cudaMemcpyDeviceToDevice, stream));
   CK(cudaStreamSynchronize(stream));
-  arena = std::move(na); arena_cap *= 2;
+  arena = std::move(na); arena_cap = ncap;
 }
-// one small D2H + sync: group count, key bytes, deferred rows, result cursor
+
+void dnz_window::parse_ctl(const char* h) {
+  n_groups_host = std::min(*reinterpret_cast<const uint32_t*>(h), gcap);
+  arena_used_host = *reinterpret_cast<const uint64_t*>(h + 8);
+  key_bytes_total_host = *reinterpret_cast<const uint64_t*>(h + 16);
+  for (auto& r : rs)
+    if (*reinterpret_cast<const uint32_t*>(h + r.ctl_off + 8)) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+  stats.groups = n_groups_host;
+}
+// one small D2H + sync: every launch enqueued so far has completed, the host view becomes exact
 void dnz_window::fetch_ctl() {
-  h_small.reserve(256);
-  CK(cudaMemcpyAsync(h_small.p, d_ctl.p, 192, cudaMemcpyDeviceToHost, stream));
+  h_small.reserve(CTL_BYTES);
+  CK(cudaMemcpyAsync(h_small.p, d_ctl.p, CTL_BYTES, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   const char* h = h_small.as<char>();
-  n_groups_host = std::min(*reinterpret_cast<const uint32_t*>(h), gcap);
-  key_bytes_total_host = *reinterpret_cast<const uint64_t*>(h + 16);
-  defer_count_host = *reinterpret_cast<const uint64_t*>(h + 64);
-  defer_flags_host = *reinterpret_cast<const uint32_t*>(h + 72);
+  parse_ctl(h);
+  rows_since_known = 0;
   for (auto& r : rs) {
     uint64_t c = *reinterpret_cast<const uint64_t*>(h + r.ctl_off);
     r.rows = c >> 32; r.bytes = c & 0xFFFFFFFFull;
-    if (*reinterpret_cast<const uint32_t*>(h + r.ctl_off + 8)) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
   }
-  stats.groups = n_groups_host;
+  for (Slot& s : slot) { s.add_rows_bound = 0; s.add_bytes_bound = 0; }
+}
+// upper bounds of the device counters given what has been enqueued since the host last saw them
+uint32_t dnz_window::groups_bound() const {
+  return (uint32_t)std::min<uint64_t>(gcap, (uint64_t)n_groups_host + (uint64_t)std::max<int64_t>(rows_since_known, 0) + 1);   // + the NULL key
+}
+uint64_t dnz_window::key_bytes_bound() const {
+  const uint64_t fresh = groups_bound() - std::min<uint32_t>(groups_bound(), n_groups_host);
+  return key_bytes_total_host + fresh * INLINE_KEY + (arena_cap - std::min<uint64_t>(arena_used_host, arena_cap));
 }
 
 std::unique_ptr<Pane> dnz_window::new_pane(int64_t id) {
   std::unique_ptr<Pane> p;
-  if (!pane_pool.empty()) { p = std::move(pane_pool.back()); pane_pool.pop_back(); }
-  else { p.reset(new Pane()); p->st.alloc((size_t)gcap * sizeof(GroupState)); }
+  while (!pane_pool.empty() && !p) {
+    p = std::move(pane_pool.back()); pane_pool.pop_back();
+    if (p->st.bytes < (size_t)gcap * sizeof(GroupState)) p.reset();      // never reuse a pane sized for a smaller dictionary
+  }
+  if (!p) { p.reset(new Pane()); p->st.alloc((size_t)gcap * sizeof(GroupState)); }
+  if (p->nullrows.p && p->nullrows.bytes < (size_t)gcap * 8) p->nullrows.release();
+  if (p->fz.p && p->fz.bytes < (size_t)gcap * 8) p->fz.release();
   p->id = id;
   if (next_tag >= (1ull << 31)) {     // tags live in [1, 2^31) so that "newer" is a signed 32-bit difference: drop every hint, restart
     CK(launch_clear_hints(slots.as<DictSlot>(), dict_cap, stream)); stats.total_launches++;
@@ -523,13 +630,31 @@ Pane* dnz_window::get_pane(int64_t id, bool create) {
   panes[id] = std::move(p);
   return r;
 }
-// a pane is dropped once the last window that covers it (start == pane start) has been emitted
-void dnz_window::retire_panes() {
+// A pane is dropped once the last window that covers it (start == pane start) has been emitted.  Behind a speculative launch the
+// pane is parked in the slot until the launch has been verified (its emission may have to be re-issued); otherwise stream order
+// alone makes the reuse safe.
+void dnz_window::retire_panes(Slot* sl) {
   if (!has_wm) return;
   for (auto it = panes.begin(); it != panes.end();) {
-    if (it->first * pane_ms + L <= wm) { if (pane_pool.size() < 16) pane_pool.push_back(std::move(it->second)); it = panes.erase(it); }
-    else ++it;
+    if (it->first * pane_ms + L <= wm) {
+      if (sl) sl->retired.push_back(std::move(it->second));
+      else if (pane_pool.size() < 16) pane_pool.push_back(std::move(it->second));
+      it = panes.erase(it);
+    } else ++it;
   }
+}
+// an open pane, or one that was retired behind a launch that has not been verified yet (a replay of deferred rows still needs it)
+Pane* dnz_window::find_pane(int64_t id) {
+  auto it = panes.find(id);
+  if (it != panes.end()) return it->second.get();
+  for (Slot& s : slot) for (auto& p : s.retired) if (p->id == id) return p.get();
+  return nullptr;
+}
+std::map<int64_t, Pane*> dnz_window::pane_sources() {
+  std::map<int64_t, Pane*> src;
+  for (Slot& s : slot) for (auto& p : s.retired) src[p->id] = p.get();
+  for (auto& kv : panes) src[kv.first] = kv.second.get();
+  return src;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -540,9 +665,11 @@ void dnz_window::push_host(ArrowArray* batch) {
   if (!batch || !batch->release) fail(DNZ_ERR_INVALID, "released or null ArrowArray");
   if (batch->n_children != n_input_cols) fail(DNZ_ERR_INVALID, "batch has %lld columns, schema has %d", (long long)batch->n_children, n_input_cols);
   int64_t n = batch->length;
+  if (n < 0) fail(DNZ_ERR_INVALID, "negative batch length");
   if (n >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
-  if (cur.rows > 0 && cur.rows + n > max_rows) seal_current();
-  Arena& arena_in = in_arena[cur.arena];
+  if (cur().rows > 0 && cur().rows + n > max_rows) seal_current();
+  Slot& c = cur();
+  Arena& arena_in = c.arena;
   PendingBatch pb;
   pb.d.n_rows = n; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
   if (n > 0) {
@@ -560,10 +687,10 @@ void dnz_window::push_host(ArrowArray* batch) {
       bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer;
       if (!pinned) cudaGetLastError();
       if (pinned && bytes >= 4096) {
-        uint64_t fp = cur.gather.empty() ? 0 : cur.gather.back().first_piece + (cur.gather.back().bytes + COPY_PIECE - 1) / COPY_PIECE;
-        cur.gather.push_back(CopyDesc{at.devicePointer, d, (uint64_t)bytes, fp});
+        uint64_t fp = c.gather.empty() ? 0 : c.gather.back().first_piece + (c.gather.back().bytes + COPY_PIECE - 1) / COPY_PIECE;
+        c.gather.push_back(CopyDesc{at.devicePointer, d, (uint64_t)bytes, fp});
       }
-      else CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream));
+      else { CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, copy_stream)); if (!pinned) stats.h2d_pageable_bytes += (int64_t)bytes; }
       stats.h2d_bytes += (int64_t)bytes;
     };
     auto copy_in = [&](const void* src, size_t bytes) -> void* {
@@ -600,331 +727,448 @@ void dnz_window::push_host(ArrowArray* batch) {
     if (o1 > a0) enqueue_copy(db, hb + a0, (size_t)(o1 - a0));
     pb.d.bytes = db - a0;     // only [o0, o1) is ever dereferenced
     copy_bitmap(key, ko, pb.d.key_valid, pb.d.key_vbit);
-    cur.copies = true;
+    c.copies = true;
   }
   pb.has_moved = true; pb.moved = *batch; batch->release = nullptr;   // moved
-  cur.batches.push_back(pb);
-  cur.rows += n;
+  c.batches.push_back(pb);
+  c.rows += n;
   stats.batches_in++; stats.rows_in += n;
-  if (cur.rows >= max_rows) seal_current();      // full: its transfer starts now, not when the next batch happens to arrive
+  if (c.rows >= max_rows) seal_current();      // full: its transfer starts now, not when the next batch happens to arrive
 }
 
 void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
   for (int64_t i = 0; i < nb; i++) {
     const dnz_device_batch& s = b[i];
+    if (s.n_rows < 0) fail(DNZ_ERR_INVALID, "device batch %lld: negative row count", (long long)i);
     if (s.n_rows >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
-    if (cur.rows > 0 && cur.rows + s.n_rows > max_rows) seal_current();
+    if (s.n_rows > 0 && (!s.ts || !s.val || !s.key_off || !s.key_bytes)) fail(DNZ_ERR_INVALID, "device batch %lld: null column pointer", (long long)i);
+    if (cur().rows > 0 && cur().rows + s.n_rows > max_rows) seal_current();
+    Slot& c = cur();
     PendingBatch pb;
     pb.d.ts = s.ts; pb.d.val = s.val; pb.d.off = s.key_off; pb.d.bytes = s.key_bytes;
     pb.d.ts_valid = s.ts_valid; pb.d.val_valid = s.val_valid; pb.d.key_valid = s.key_valid;
     pb.d.n_rows = s.n_rows; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
     pb.key_bytes = -1;
-    cur.batches.push_back(pb);
-    cur.rows += s.n_rows;
+    c.batches.push_back(pb);
+    c.rows += s.n_rows;
     stats.batches_in++; stats.rows_in += s.n_rows;
+    if (c.rows >= max_rows) seal_current();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// The current superbatch is full: aggregate the previously sealed one (its successor's copies are already in flight on the
-// copy stream, so they overlap this work), then seal the current one and start filling the other arena.
+// pipeline
 // launch the gather copy of a superbatch's pinned sources and mark the point where all its bytes are on the device
-void dnz_window::finish_copies(Superbatch& sb) {
-  if (!sb.copies) return;
-  if (!sb.gather.empty()) {
-    size_t nbytes = sb.gather.size() * sizeof(CopyDesc);
-    h_copy_descs[sb.arena].reserve(nbytes); d_copy_descs[sb.arena].reserve(nbytes);
-    memcpy(h_copy_descs[sb.arena].p, sb.gather.data(), nbytes);
-    CK(cudaMemcpyAsync(d_copy_descs[sb.arena].p, h_copy_descs[sb.arena].p, nbytes, cudaMemcpyHostToDevice, copy_stream));
+void dnz_window::finish_copies(Slot& s) {
+  if (!s.copies) return;
+  if (!s.gather.empty()) {
+    size_t nbytes = s.gather.size() * sizeof(CopyDesc);
+    s.h_copy_descs.reserve(nbytes); s.d_copy_descs.reserve(nbytes);
+    memcpy(s.h_copy_descs.p, s.gather.data(), nbytes);
+    CK(cudaMemcpyAsync(s.d_copy_descs.p, s.h_copy_descs.p, nbytes, cudaMemcpyHostToDevice, copy_stream));
     CK(cudaMemsetAsync(d_copy_cursor.p, 0, 4, copy_stream));
-    CK(launch_gather_copy(d_copy_descs[sb.arena].as<CopyDesc>(), (uint32_t)sb.gather.size(), d_copy_cursor.as<unsigned int>(), copy_stream));
+    CK(launch_gather_copy(s.d_copy_descs.as<CopyDesc>(), (uint32_t)s.gather.size(), d_copy_cursor.as<unsigned int>(), copy_stream));
     stats.total_launches++;
-    sb.gather.clear();
+    s.gather.clear();
   }
-  CK(cudaEventRecord(copy_done[sb.arena], copy_stream));
+  CK(cudaEventRecord(s.copy_done, copy_stream));
 }
 
+// The filling superbatch is complete: start its transfer and its tile scan, enqueue the aggregation of the superbatch sealed
+// before it (whose scan results are on the host by now, so nothing waits), and move on to the next slot -- which must have been
+// verified: that is the only place where the host may wait for the device, two aggregate launches behind the one it just queued.
 void dnz_window::seal_current() {
-  finish_copies(cur);                                 // this superbatch's host->device transfer starts now ...
-  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }   // ... and overlaps the aggregation of the previous one
-  launch_scan(cur);                                   // queued behind that aggregation; waits for the transfer on the device
-  std::swap(sealed, cur); has_sealed = true;
-  cur.batches.clear(); cur.rows = 0; cur.copies = false; cur.arena = sealed.arena ^ 1;
+  Slot& f = cur();
+  if (f.batches.empty()) return;
+  struct Guard { dnz_window* w; bool prev; ~Guard() { w->in_process = prev; } } guard{this, in_process};
+  in_process = true;
+  finish_copies(f);
+  launch_scan(f);
+  f.state = Slot::SEALED; sealed_order.push_back(f.idx);
+  while (sealed_order.size() > 1) launch_slot(slot[sealed_order.front()]);
+  if (world > 1 || (cfg.flags & DNZ_FLAG_SYNCHRONOUS)) while (!sealed_order.empty()) launch_slot(slot[sealed_order.front()]);
+  const int next = (fill + 1) % NSLOT;
+  if (slot[next].state == Slot::SEALED) launch_slot(slot[next]);
+  if (slot[next].state == Slot::LAUNCHED) { while (!launched_order.empty() && slot[next].state == Slot::LAUNCHED) verify(slot[launched_order.front()]); }
+  fill = next; slot[next].state = Slot::FILLING;
 }
 
+// enqueue everything that has been pushed (no host wait for the results)
 void dnz_window::process_pending() {
-  if (has_sealed) { process_superbatch(sealed); has_sealed = false; }
-  if (!cur.batches.empty()) {
-    finish_copies(cur);
-    launch_scan(cur);
-    process_superbatch(cur);
-  }
+  struct Guard { dnz_window* w; bool prev; ~Guard() { w->in_process = prev; } } guard{this, in_process};
+  in_process = true;
+  if (!cur().batches.empty()) seal_current();
+  while (!sealed_order.empty()) launch_slot(slot[sealed_order.front()]);
+}
+// ... and make the host view exact: every launch verified, deferred rows replayed, input batches released
+void dnz_window::drain() {
+  struct Guard { dnz_window* w; bool prev; ~Guard() { w->in_process = prev; } } guard{this, in_process};
+  in_process = true;
+  while (!sealed_order.empty()) launch_slot(slot[sealed_order.front()]);
+  while (!launched_order.empty()) verify(slot[launched_order.front()]);
 }
 
 // Batch descriptors + tile scan (RecordBatchWatermark::try_from per batch, byte ranges per tile), asynchronously: the
-// results land in this arena's pinned buffers and `done` fires when they are readable.
-void dnz_window::launch_scan(Superbatch& sb) {
-  Scan& sc = scan[sb.arena];
-  const size_t nb = sb.batches.size();
-  sc.bds.resize(nb); sc.n_tiles = 0; sc.launched = true;
-  for (size_t i = 0; i < nb; i++) { sc.bds[i] = sb.batches[i].d; sc.bds[i].tile0 = sc.n_tiles; sc.n_tiles += (sc.bds[i].n_rows + TILE - 1) / TILE; }
-  if (sc.n_tiles == 0) return;            // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
+// results land in the slot's pinned buffers and `scan_done` fires when they are readable.
+void dnz_window::launch_scan(Slot& s) {
+  const size_t nb = s.batches.size();
+  s.bds.resize(nb); s.n_tiles = 0; s.scanned = true;
+  for (size_t i = 0; i < nb; i++) { s.bds[i] = s.batches[i].d; s.bds[i].tile0 = s.n_tiles; s.n_tiles += (s.bds[i].n_rows + TILE - 1) / TILE; }
+  if (s.n_tiles == 0) return;            // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
   // the scan picks the LAST batch with tile0 <= t: empty batches in the middle share their successor's tile0 and are
   // never chosen; trailing empties get a tile0 past the end
-  for (size_t i = nb; i-- > 0;) { if (sc.bds[i].n_rows == 0) sc.bds[i].tile0 = sc.n_tiles + 1; else break; }
-  sc.d_batches.reserve(nb * sizeof(BatchDesc)); sc.d_tiles.reserve((size_t)sc.n_tiles * sizeof(TileDesc)); sc.d_minmax.reserve(nb * sizeof(BatchMinMax));
-  sc.h_batches.reserve(nb * sizeof(BatchDesc)); sc.h_minmax.reserve(nb * sizeof(BatchMinMax));
-  memcpy(sc.h_batches.p, sc.bds.data(), nb * sizeof(BatchDesc));
-  if (sb.copies) CK(cudaStreamWaitEvent(stream, copy_done[sb.arena], 0));
-  CK(cudaMemcpyAsync(sc.d_batches.p, sc.h_batches.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
+  for (size_t i = nb; i-- > 0;) { if (s.bds[i].n_rows == 0) s.bds[i].tile0 = s.n_tiles + 1; else break; }
+  s.d_batches.reserve(nb * sizeof(BatchDesc)); s.d_tiles.reserve((size_t)s.n_tiles * sizeof(TileDesc)); s.d_minmax.reserve(nb * sizeof(BatchMinMax));
+  s.h_batches.reserve(nb * sizeof(BatchDesc)); s.h_minmax.reserve(nb * sizeof(BatchMinMax));
+  memcpy(s.h_batches.p, s.bds.data(), nb * sizeof(BatchDesc));
+  if (s.copies) CK(cudaStreamWaitEvent(stream, s.copy_done, 0));
+  CK(cudaMemcpyAsync(s.d_batches.p, s.h_batches.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
   bool allow_fast = !(cfg.flags & DNZ_FLAG_FORCE_GENERIC);
-  CK(launch_tile_scan(sc.d_batches.as<BatchDesc>(), (int64_t)nb, sc.n_tiles, pane_ms, sc.d_tiles.as<TileDesc>(), sc.d_minmax.as<BatchMinMax>(), allow_fast, stream));
+  CK(launch_tile_scan(s.d_batches.as<BatchDesc>(), (int64_t)nb, s.n_tiles, pane_ms, s.d_tiles.as<TileDesc>(), s.d_minmax.as<BatchMinMax>(), allow_fast, stream));
   stats.total_launches += 2;
-  CK(cudaMemcpyAsync(sc.h_minmax.p, sc.d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
-  CK(cudaEventRecord(sc.done, stream));
-}
-
-void dnz_window::process_superbatch(Superbatch& sb) {
-  if (sb.batches.empty()) return;
-  if (res_consumed) reset_results();
-  rotate_result_sets();
-  struct Cleanup {
-    dnz_window* w; Superbatch* sb;
-    ~Cleanup() {
-      if (sb->copies) cudaEventSynchronize(w->copy_done[sb->arena]);
-      for (auto& pb : sb->batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
-      sb->batches.clear(); sb->gather.clear(); sb->rows = 0; sb->copies = false; w->in_arena[sb->arena].reset(); w->active = nullptr;
-      w->scan[sb->arena].launched = false;
-    }
-  } cleanup{this, &sb};
-  active = &sb.batches;
-  if (!scan[sb.arena].launched) launch_scan(sb);
-  process_chunk(sb);
+  CK(cudaMemcpyAsync(s.h_minmax.p, s.d_minmax.p, nb * sizeof(BatchMinMax), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(s.scan_done, stream));
 }
 
 // Everything a steady-state pass needs is allocated when the operator is created (cudaMalloc / cudaMallocHost cost
 // milliseconds and must stay out of the per-batch path).
 void dnz_window::prealloc() {
   const size_t nb_max = 4096 + (size_t)(max_rows / 8192), nt_max = (size_t)(max_rows / TILE) + nb_max;
-  for (Scan& sc : scan) {
-    CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
-    sc.d_batches.reserve(nb_max * sizeof(BatchDesc)); sc.d_tiles.reserve(nt_max * sizeof(TileDesc)); sc.d_minmax.reserve(nb_max * sizeof(BatchMinMax));
-    sc.h_batches.reserve(nb_max * sizeof(BatchDesc)); sc.h_minmax.reserve(nb_max * sizeof(BatchMinMax));
+  for (Slot& s : slot) {
+    s.d_batches.reserve(nb_max * sizeof(BatchDesc)); s.d_tiles.reserve(nt_max * sizeof(TileDesc)); s.d_minmax.reserve(nb_max * sizeof(BatchMinMax));
+    s.h_batches.reserve(nb_max * sizeof(BatchDesc)); s.h_minmax.reserve(nb_max * sizeof(BatchMinMax));
+    s.d_copy_descs.reserve(8192 * sizeof(CopyDesc)); s.h_copy_descs.reserve(8192 * sizeof(CopyDesc));
+    s.d_ptrs.reserve(7 * 1024 * sizeof(void*)); s.h_ptrs.reserve((size_t)7 * 1024 * sizeof(void*));
+    s.d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
   }
   d_copy_cursor.alloc(64);
-  for (int i = 0; i < 2; i++) { d_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); h_copy_descs[i].reserve(8192 * sizeof(CopyDesc)); }
-  d_ptrs.reserve(7 * 1024 * sizeof(void*)); d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
-  h_stage.reserve((size_t)7 * 1024 * sizeof(void*)); h_small.reserve(256);
+  h_small.reserve(CTL_BYTES);
   for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
   {   // room for a few windows' worth of rows; grows on demand (one poll is limited to 2 GiB of key bytes by the 32-bit Utf8 offsets)
-    const uint64_t rows0 = std::min<uint64_t>((uint64_t)gcap * 8, 64ull << 20);
-    ensure_result_capacity(rows0, std::min<uint64_t>(rows0 * 16, (1ull << 31) - (1ull << 20)));
+    // (upper bounds are reserved per emission: windows x group capacity, for every launch in flight and every unconsumed window)
+    const uint64_t rows0 = std::min<uint64_t>((uint64_t)gcap * 24, 96ull << 20);
+    for (wr = 1; wr >= 0; wr--) ensure_result_capacity(rows0, std::min<uint64_t>(rows0 * 16, (1ull << 31) - (1ull << 20)));
+    wr = 0;
   }
 }
 
-void dnz_window::process_chunk(Superbatch& sb) {
-  Scan& sc = scan[sb.arena];
-  cur_scan = &sc;
-  const size_t nb = sb.batches.size(); const size_t b0 = 0;
-  const int64_t n_tiles = sc.n_tiles;
-  if (n_tiles == 0) return;
-  g_tr.mark("pre");
-  CK(cudaEventSynchronize(sc.done));
-  g_tr.mark("scan_wait");
-  const std::vector<BatchDesc>& bds = sc.bds;
-  std::vector<BatchMinMax> mm(sc.h_minmax.as<BatchMinMax>(), sc.h_minmax.as<BatchMinMax>() + nb);
-
-  // ---- validation: inputs the reference panics on
-  for (size_t i = 0; i < nb; i++) {
-    if (bds[i].n_rows == 0) continue;
-    if (mm[i].n_valid == 0) fail(DNZ_ERR_DATA, "batch %lld: all-null canonical_timestamp (the reference unwraps None and panics)", (long long)bds[i].seq);
-    if (mm[i].ts_min < 0 || (S > 0 && mm[i].ts_min - L < 0)) fail(DNZ_ERR_DATA, "batch %lld: timestamp before epoch (+window): the reference panics in duration_since(UNIX_EPOCH)", (long long)bds[i].seq);
-  }
-
-  // ---- runs: maximal sequences of batches without late rows are aggregated by ONE launch; a batch that contains rows
-  // for an already emitted window ("dirty") is aggregated alone so that the re-opened windows hold exactly its rows.
+// ---- runs: maximal sequences of batches without late rows are aggregated by ONE launch; a batch that contains rows for an
+// already emitted window ("dirty") is aggregated alone so that the re-opened windows hold exactly its rows.  A run is also cut
+// where its pane span would exceed the pane table (an idle gap in the stream), so the limit applies per batch, not per launch.
+constexpr int64_t MAX_RUN_PANES = 1 << 16;
+void dnz_window::plan_runs(Slot& s, const std::vector<BatchMinMax>& mm, std::vector<Run>& runs) {
+  const size_t nb = s.batches.size();
   bool cur_has_wm = world > 1 ? has_lwm : has_wm; int64_t cur_wm = world > 1 ? lwm : wm;
-  size_t run_start = nb; int64_t run_wm_after = 0;
+  size_t run_start = nb; int64_t run_wm_after = 0, run_pmin = 0, run_pmax = 0;
   for (size_t i = 0; i < nb; i++) {
-    if (bds[i].n_rows == 0) continue;
-    int64_t mn = mm[i].ts_min;
-    int64_t first_pane_end = (floor_div(mn, pane_ms) + 1) * pane_ms;
+    if (s.bds[i].n_rows == 0) continue;
+    const int64_t mn = mm[i].ts_min;
+    const int64_t bp0 = floor_div(mn, pane_ms), bp1 = floor_div(mm[i].ts_max, pane_ms);
+    if (bp1 - bp0 + 1 > MAX_RUN_PANES) fail(DNZ_ERR_UNSUPPORTED, "batch %lld spans %lld panes (timestamps too sparse); limit %lld", (long long)s.bds[i].seq, (long long)(bp1 - bp0 + 1), (long long)MAX_RUN_PANES);
+    const int64_t first_pane_end = (bp0 + 1) * pane_ms;
     bool dirty = cur_has_wm && first_pane_end <= cur_wm;
-    int64_t new_wm = (!cur_has_wm || cur_wm <= mn) ? mn : cur_wm;     // process_watermark (:255-266)
+    const int64_t new_wm = (!cur_has_wm || cur_wm <= mn) ? mn : cur_wm;     // process_watermark (:255-266)
     if (dirty && world > 1 && first_pane_end <= (exported_pane_upto == INT64_MIN ? INT64_MIN : (exported_pane_upto + 1) * pane_ms))
-      fail(DNZ_ERR_UNSUPPORTED, "batch %lld is late for a pane that was already exchanged (exchange mode needs in-order input)", (long long)bds[i].seq);
+      fail(DNZ_ERR_UNSUPPORTED, "batch %lld is late for a pane that was already exchanged (exchange mode needs in-order input)", (long long)s.bds[i].seq);
     if (world > 1) dirty = false;      // nothing has been emitted locally: late rows simply join their (still local) panes
     if (dirty) {
-      if (run_start != nb) { execute_run(mm, b0, run_start, i, false, 0, run_wm_after); run_start = nb; }
-      execute_run(mm, b0, i, i + 1, true, cur_wm, new_wm);
+      if (run_start != nb) { runs.push_back(Run{run_start, i, false, 0, run_wm_after}); run_start = nb; }
+      runs.push_back(Run{i, i + 1, true, cur_wm, new_wm});
       stats.late_batches++;
     } else {
-      if (run_start == nb) run_start = i;
+      if (run_start != nb && std::max(run_pmax, bp1) - std::min(run_pmin, bp0) + 1 > MAX_RUN_PANES) {
+        runs.push_back(Run{run_start, i, false, 0, run_wm_after}); run_start = nb;
+      }
+      if (run_start == nb) { run_start = i; run_pmin = bp0; run_pmax = bp1; }
+      else { run_pmin = std::min(run_pmin, bp0); run_pmax = std::max(run_pmax, bp1); }
       run_wm_after = new_wm;
     }
     cur_has_wm = true; cur_wm = new_wm;
   }
-  if (run_start != nb) execute_run(mm, b0, run_start, nb, false, 0, run_wm_after);
-  g_tr.flush("superbatch");
+  if (run_start != nb) runs.push_back(Run{run_start, nb, false, 0, run_wm_after});
 }
 
-// Aggregates batches [rb0, rb1) of the chunk (indices relative to the chunk) and triggers.
-void dnz_window::execute_run(const std::vector<BatchMinMax>& mm, size_t chunk_b0, size_t rb0,
-                             size_t rb1, bool dirty, int64_t horizon, int64_t wm_after) {
-  // tile range of the run
-  int64_t t0 = -1, t1 = -1; int64_t rows = 0; double alg_bytes = 0;
-  {
-    int64_t acc = 0;
-    for (size_t i = 0; i < rb1; i++) {
-      int64_t nt = ((*active)[chunk_b0 + i].d.n_rows + TILE - 1) / TILE;
-      if (i == rb0) t0 = acc;
-      acc += nt;
-    }
-    t1 = acc;
+dnz_window::RunGeom dnz_window::run_geometry(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r) {
+  RunGeom g;
+  int64_t acc = 0; int64_t fast = 0, generic = 0;
+  for (size_t i = 0; i < r.b1; i++) {
+    if (i == r.b0) g.t0 = acc;
+    acc += (s.bds[i].n_rows + TILE - 1) / TILE;
   }
-  if (t1 <= t0) { return; }
-  // ---- panes touched by the run (from the per-batch timestamp ranges of the tile scan)
-  int64_t pmin = INT64_MAX, pmax = INT64_MIN; int64_t fast = 0, generic = 0;
-  for (size_t i = rb0; i < rb1; i++) {
+  g.t1 = acc;
+  for (size_t i = r.b0; i < r.b1; i++) {
     const BatchMinMax& b = mm[i];
-    const int64_t nr = (*active)[chunk_b0 + i].d.n_rows;
+    const int64_t nr = s.bds[i].n_rows;
     if (nr == 0) continue;
-    rows += nr; alg_bytes += 20.0 * nr + (double)b.key_bytes;
+    g.rows += nr; g.alg_bytes += 20.0 * nr + (double)b.key_bytes;
     fast += b.n_fast; generic += b.n_tiles - b.n_fast;
+    if (s.bds[i].val_valid) g.val_nulls = true;
     if (b.n_valid == 0) continue;
-    pmin = std::min(pmin, floor_div(b.ts_min, pane_ms)); pmax = std::max(pmax, floor_div(b.ts_max, pane_ms));
+    g.pmin = std::min(g.pmin, floor_div(b.ts_min, pane_ms)); g.pmax = std::max(g.pmax, floor_div(b.ts_max, pane_ms));
   }
   stats.fast_tiles += fast; stats.generic_tiles += generic;
-  std::map<int64_t, std::unique_ptr<Pane>> late_panes;
-  if (pmin <= pmax) {
-    int64_t np = pmax - pmin + 1;
-    if (np > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one launch spans %lld panes (timestamps too sparse); limit 65536", (long long)np);
-    bool val_nulls = false;
-    for (size_t i = rb0; i < rb1; i++) if ((*active)[chunk_b0 + i].d.val_valid) val_nulls = true;
-    if (val_nulls && !need_nullrows) { need_nullrows = true; for (auto& kv : panes) ensure_side_arrays(kv.second.get()); }
-    std::vector<uint8_t> touched((size_t)np, 0);
-    for (size_t i = rb0; i < rb1; i++) {
-      const BatchMinMax& b = mm[i];
-      if ((*active)[chunk_b0 + i].d.n_rows == 0 || b.n_valid == 0) continue;
-      for (int64_t p = floor_div(b.ts_min, pane_ms); p <= floor_div(b.ts_max, pane_ms); p++) touched[(size_t)(p - pmin)] = 1;
+  return g;
+}
+
+// panes touched by the run (from the per-batch timestamp ranges of the tile scan)
+void dnz_window::prepare_panes(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r, const RunGeom& g) {
+  if (g.pmin > g.pmax) return;
+  const int64_t np = g.pmax - g.pmin + 1;
+  if (g.val_nulls && !need_nullrows) { need_nullrows = true; for_each_live_pane([&](Pane* p) { ensure_side_arrays(p); }); }
+  std::vector<uint8_t> touched((size_t)np, 0);
+  for (size_t i = r.b0; i < r.b1; i++) {
+    const BatchMinMax& b = mm[i];
+    if (s.bds[i].n_rows == 0 || b.n_valid == 0) continue;
+    for (int64_t p = floor_div(b.ts_min, pane_ms); p <= floor_div(b.ts_max, pane_ms); p++) touched[(size_t)(p - g.pmin)] = 1;
+  }
+  for (int64_t p = g.pmin; p <= g.pmax; p++) {
+    if (!touched[(size_t)(p - g.pmin)]) continue;
+    const bool need_main = !r.dirty || p * pane_ms + L > r.horizon;             // some covering window is still open
+    const bool need_late = r.dirty && (p + 1) * pane_ms <= r.horizon;           // some covering window was already emitted
+    if (need_main) get_pane(p, true);
+    if (need_late) late_panes[p] = new_pane(p);
+  }
+}
+
+// pane pointer table + launch parameters of one aggregate / replay pass over the run
+AggParams dnz_window::build_agg_params(Slot& s, const RunGeom& g, bool dirty, int64_t horizon, int out_list) {
+  const int64_t np = g.pmax - g.pmin + 1;
+  const size_t pb = (size_t)np * sizeof(void*);
+  s.h_ptrs.reserve(7 * pb); s.d_ptrs.reserve(7 * pb);
+  void** hp = s.h_ptrs.as<void*>();
+  for (int64_t p = g.pmin; p <= g.pmax; p++) {
+    const size_t k = (size_t)(p - g.pmin);
+    Pane* m = (!dirty || p * pane_ms + L > horizon) ? find_pane(p) : nullptr;
+    auto lit = late_panes.find(p); Pane* l = lit == late_panes.end() ? nullptr : lit->second.get();
+    if (m) ensure_side_arrays(m);
+    if (l) ensure_side_arrays(l);
+    hp[0 * np + k] = m ? m->st.p : nullptr; hp[1 * np + k] = l ? l->st.p : nullptr;
+    hp[2 * np + k] = m ? m->nullrows.p : nullptr; hp[3 * np + k] = l ? l->nullrows.p : nullptr;
+    hp[4 * np + k] = m ? m->fz.p : nullptr; hp[5 * np + k] = l ? l->fz.p : nullptr;
+    hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m ? (m->tag & 0xFFFFFFFFull) : 0));
+  }
+  CK(cudaMemcpyAsync(s.d_ptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(ctl(s.ctl_off()), 0, 16, stream));        // deferred-row counter, flags, tile counter (not the emit-blocked flag)
+  AggParams P;
+  P.batches = s.d_batches.as<BatchDesc>(); P.tiles = s.d_tiles.as<TileDesc>(); P.tile_begin = g.t0; P.tile_end = g.t1;
+  P.dict = dict_view();
+  P.flags = ((cfg.flags & DNZ_FLAG_NO_HINTS) ? AGG_NO_HINTS : 0) | ((cfg.flags & DNZ_FLAG_NO_QUEUE) ? AGG_NO_QUEUE : 0);
+  char* dp = s.d_ptrs.as<char>();
+  P.panes.pane0 = g.pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
+  P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
+  P.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); P.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
+  P.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); P.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+  P.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
+  const size_t defer_cap = (size_t)std::max<int64_t>(g.rows, 1);
+  s.d_defer[out_list].reserve(defer_cap * sizeof(DeferEntry));
+  P.defer.entries = s.d_defer[out_list].as<DeferEntry>();
+  P.defer.count = reinterpret_cast<unsigned long long*>(ctl(s.ctl_off())); P.defer.cap = defer_cap;
+  P.defer.flags = reinterpret_cast<uint32_t*>(ctl(s.ctl_off() + 8));
+  P.tile_counter = reinterpret_cast<uint32_t*>(ctl(s.ctl_off() + 12));
+  P.priv = nullptr; P.priv_groups = 0;
+  return P;
+}
+
+void dnz_window::launch_aggregate_pass(Slot& s, const RunGeom& g, AggParams& P, bool dirty) {
+  // low cardinality: private pane copies per CTA (see AggParams::priv)
+  const int64_t np = g.pmax - g.pmin + 1;
+  const int agg_grid = aggregate_grid(g.t1 - g.t0, sm_count);
+  const size_t priv_bytes = (size_t)agg_grid * (size_t)np * gcap * sizeof(GroupState);
+  const bool use_priv = !dirty && gcap <= 8192 && priv_bytes <= (256ull << 20) && !(cfg.flags & (DNZ_FLAG_FORCE_GENERIC | DNZ_FLAG_NO_PRIVATE));
+  if (use_priv) {
+    d_priv.reserve(priv_bytes);
+    CK(cudaMemsetAsync(d_priv.p, 0, priv_bytes, stream));
+    P.priv = d_priv.as<GroupState>(); P.priv_groups = gcap;
+  }
+  s.timed = (cfg.flags & DNZ_FLAG_KERNEL_TIMING) != 0; s.alg_bytes = g.alg_bytes;
+  if (s.timed) CK(cudaEventRecord(s.ev0, stream));
+  if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
+  else CK(launch_aggregate(P, sm_count, stream));
+  if (use_priv) { CK(launch_merge_private(P, agg_grid, stream)); stats.total_launches++; }
+  if (s.timed) CK(cudaEventRecord(s.ev1, stream));
+  stats.agg_launches++; stats.total_launches++;
+  rows_since_known += g.rows;
+}
+
+// Rows the aggregate pass could not apply (a table was full, a side array was missing) sit in the slot's deferred-row list.
+// Grow what was too small and replay exactly those rows until none is left.  Called with the stream idle and
+// defer_count_host / defer_flags_host describing the slot's list 0.
+void dnz_window::resolve_deferred(Slot& s, const RunGeom& g, bool dirty, int64_t horizon) {
+  int in_list = 0; uint64_t n_in = defer_count_host; uint32_t flags = defer_flags_host;
+  for (int iter = 0; n_in > 0; iter++) {
+    if (iter > 64) fail(DNZ_ERR_NOMEM, "deferred rows did not converge");
+    if (flags & DEFER_LIST_OVERFLOW) fail(DNZ_ERR_NOMEM, "deferred-row list overflow");
+    stats.deferred_rows += (int64_t)n_in;
+    if (flags & DEFER_GROUPS_FULL) {
+      uint32_t clamp = gcap;       // the device counter ran past gcap; ids >= gcap were never handed out
+      CK(cudaMemcpyAsync(ctl(0), &clamp, 4, cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));
+      dict_grow();
     }
-    for (int64_t p = pmin; p <= pmax; p++) {
-      if (!touched[(size_t)(p - pmin)]) continue;
-      bool need_main = !dirty || p * pane_ms + L > horizon;             // some covering window is still open
-      bool need_late = dirty && (p + 1) * pane_ms <= horizon;           // some covering window was already emitted
-      if (need_main) get_pane(p, true);
-      if (need_late) late_panes[p] = new_pane(p);
+    if (flags & DEFER_ARENA_FULL) {
+      // the counter ran past the capacity by the bytes of every failed reservation (>= what the deferred rows need, and
+      // never more than the key bytes of the run): pull it back to the capacity (the tail gap stays unused) and grow by that
+      const uint64_t over = arena_used_host > arena_cap ? arena_used_host - arena_cap : 0;
+      const uint64_t old_cap = arena_cap;
+      CK(cudaMemcpyAsync(ctl(8), &old_cap, 8, cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));
+      arena_grow(arena_cap + std::min<uint64_t>(over, (uint64_t)g.alg_bytes) + (1 << 20));
     }
+    if (flags & DEFER_NEED_FZ) need_fz = true;
+    if (flags & DEFER_NEED_NULLROWS) need_nullrows = true;
+    if (flags & (DEFER_NEED_FZ | DEFER_NEED_NULLROWS)) for_each_live_pane([&](Pane* p) { ensure_side_arrays(p); });
+    const int out_list = in_list ^ 1;
+    AggParams P = build_agg_params(s, g, dirty, horizon, out_list);
+    CK(launch_deferred(P, s.d_defer[in_list].as<DeferEntry>(), n_in, stream));   // replays the rows of the previous pass
+    stats.total_launches++;
+    fetch_ctl();
+    const char* h = h_small.as<char>() + s.ctl_off();
+    n_in = *reinterpret_cast<const uint64_t*>(h); flags = *reinterpret_cast<const uint32_t*>(h + 8);
+    in_list = out_list;
+  }
+}
+
+// Aggregates one run and triggers, waiting for the device after the launch (late batches, several runs in one superbatch,
+// exchange mode): the path the speculative one falls back to.
+void dnz_window::execute_run_sync(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r) {
+  RunGeom g = run_geometry(s, mm, r);
+  if (g.t1 <= g.t0) return;
+  if (g.pmin <= g.pmax) {
+    prepare_panes(s, mm, r, g);
     g_tr.mark("panes");
-    // ---- aggregate, replaying deferred rows until every table is large enough
-    const size_t defer_cap = (size_t)std::max<int64_t>(rows, 1);
-    d_defer[0].reserve(defer_cap * sizeof(DeferEntry));
-    int in_list = 0; uint64_t n_in = 0;
-    for (int iter = 0;; iter++) {
-      if (iter > 64) fail(DNZ_ERR_NOMEM, "deferred rows did not converge");
-      // pane pointer table
-      size_t pb = (size_t)np * sizeof(void*);
-      h_stage.reserve(7 * pb); d_ptrs.reserve(7 * pb);
-      void** hp = h_stage.as<void*>();
-      for (int64_t p = pmin; p <= pmax; p++) {
-        size_t k = (size_t)(p - pmin);
-        Pane* m = (!dirty || p * pane_ms + L > horizon) ? get_pane(p, false) : nullptr;
-        auto lit = late_panes.find(p); Pane* l = lit == late_panes.end() ? nullptr : lit->second.get();
-        if (m) ensure_side_arrays(m);
-        if (l) ensure_side_arrays(l);
-        hp[0 * np + k] = m ? m->st.p : nullptr; hp[1 * np + k] = l ? l->st.p : nullptr;
-        hp[2 * np + k] = m ? m->nullrows.p : nullptr; hp[3 * np + k] = l ? l->nullrows.p : nullptr;
-        hp[4 * np + k] = m ? m->fz.p : nullptr; hp[5 * np + k] = l ? l->fz.p : nullptr;
-        hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m ? (m->tag & 0xFFFFFFFFull) : 0));
-      }
-      CK(cudaMemcpyAsync(d_ptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
-      CK(cudaMemsetAsync(ctl(64), 0, 16, stream));
-      AggParams P;
-      P.batches = cur_scan->d_batches.as<BatchDesc>(); P.tiles = cur_scan->d_tiles.as<TileDesc>(); P.tile_begin = t0; P.tile_end = t1;
-      P.dict = dict_view();
-      P.flags = ((cfg.flags & DNZ_FLAG_NO_HINTS) ? AGG_NO_HINTS : 0) | ((cfg.flags & DNZ_FLAG_NO_QUEUE) ? AGG_NO_QUEUE : 0);
-      char* dp = d_ptrs.as<char>();
-      P.panes.pane0 = pmin; P.panes.n_panes = (int32_t)np; P.panes.pad = 0; P.panes.pane_ms = pane_ms;
-      P.panes.main = (GroupState* const*)(dp + 0 * pb); P.panes.late = (GroupState* const*)(dp + 1 * pb);
-      P.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); P.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
-      P.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); P.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
-      P.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
-      const int out_list = iter == 0 ? 0 : (in_list ^ 1);
-      d_defer[out_list].reserve(defer_cap * sizeof(DeferEntry));
-      P.defer.entries = d_defer[out_list].as<DeferEntry>();
-      P.defer.count = reinterpret_cast<unsigned long long*>(ctl(64)); P.defer.cap = defer_cap;
-      P.defer.flags = reinterpret_cast<uint32_t*>(ctl(72));
-      P.tile_counter = reinterpret_cast<uint32_t*>(ctl(76));     // zeroed with the deferred-row counters above
-      // low cardinality: private pane copies per CTA (see AggParams::priv)
-      P.priv = nullptr; P.priv_groups = 0;
-      const int agg_grid = aggregate_grid(t1 - t0, sm_count);
-      const size_t priv_bytes = (size_t)agg_grid * (size_t)np * gcap * sizeof(GroupState);
-      const bool use_priv = iter == 0 && !dirty && gcap <= 8192 && priv_bytes <= (256ull << 20) && !(cfg.flags & (DNZ_FLAG_FORCE_GENERIC | DNZ_FLAG_NO_PRIVATE));
-      if (use_priv) {
-        d_priv.reserve(priv_bytes);
-        CK(cudaMemsetAsync(d_priv.p, 0, priv_bytes, stream));
-        P.priv = d_priv.as<GroupState>(); P.priv_groups = gcap;
-      }
-      const bool timing = iter == 0 && (cfg.flags & DNZ_FLAG_KERNEL_TIMING);
-      if (iter == 0) {
-        if (timing) CK(cudaEventRecord(ev0, stream));
-        if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
-        else CK(launch_aggregate(P, sm_count, stream));
-        if (use_priv) { CK(launch_merge_private(P, agg_grid, stream)); stats.total_launches++; }
-        if (timing) CK(cudaEventRecord(ev1, stream));
-        stats.agg_launches++; stats.total_launches++;
-      } else {
-        CK(launch_deferred(P, d_defer[in_list].as<DeferEntry>(), n_in, stream));   // replays the rows of the previous pass
-        stats.total_launches++;
-      }
-      g_tr.mark("agg_launch");
-      fetch_ctl();
-      g_tr.mark("agg_wait");
-      if (timing) {
-        float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
-        stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += alg_bytes;
-      }
-      uint64_t cnt = defer_count_host; uint32_t flags = defer_flags_host;
-      if (cnt == 0) { ctl_fresh = true; break; }
-      if (flags & DEFER_LIST_OVERFLOW) fail(DNZ_ERR_NOMEM, "deferred-row list overflow");
-      stats.deferred_rows += (int64_t)cnt;
-      if (flags & DEFER_GROUPS_FULL) {
-        uint32_t clamp = gcap;       // the device counter ran past gcap; ids >= gcap were never handed out
-        CK(cudaMemcpyAsync(ctl(0), &clamp, 4, cudaMemcpyHostToDevice, stream));
-        CK(cudaStreamSynchronize(stream));
-        dict_grow();
-      }
-      if (flags & DEFER_ARENA_FULL) arena_grow();
-      if (flags & DEFER_NEED_FZ) need_fz = true;
-      if (flags & DEFER_NEED_NULLROWS) need_nullrows = true;
-      if (flags & (DEFER_NEED_FZ | DEFER_NEED_NULLROWS)) for (auto& kv : panes) ensure_side_arrays(kv.second.get());
-      in_list = out_list; n_in = cnt;
-    }
+    AggParams P = build_agg_params(s, g, r.dirty, r.horizon, 0);
+    launch_aggregate_pass(s, g, P, r.dirty);
+    g_tr.mark("agg_launch");
+    fetch_ctl();
+    g_tr.mark("agg_wait");
+    if (s.timed) { float ms = 0; CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1)); stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += s.alg_bytes; s.timed = false; }
+    const char* h = h_small.as<char>() + s.ctl_off();
+    defer_count_host = *reinterpret_cast<const uint64_t*>(h); defer_flags_host = *reinterpret_cast<const uint32_t*>(h + 8);
+    if (defer_count_host) resolve_deferred(s, g, r.dirty, r.horizon);
   }
   g_tr.mark("post_agg");
   // ---- process_watermark + trigger_windows
-  if (dirty) {
+  if (r.dirty) {
     // windows that were already emitted (end <= horizon) and received rows from this batch are re-opened and emitted
     // again immediately with ONLY this batch's rows (§8a-3)
     std::set<int64_t> starts;
     for (auto& kv : late_panes)
       for (int j = 0; j < panes_per_window; j++) {
-        int64_t s = (kv.first - j) * pane_ms;
-        if (s >= 0 && s + L <= horizon) starts.insert(s);
+        int64_t st = (kv.first - j) * pane_ms;
+        if (st >= 0 && st + L <= r.horizon) starts.insert(st);
       }
     std::map<int64_t, Pane*> src;
     for (auto& kv : late_panes) src[kv.first] = kv.second.get();
-    emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src);
+    emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src, false, nullptr);
     CK(cudaStreamSynchronize(stream));
     for (auto& kv : late_panes) if (pane_pool.size() < 16) pane_pool.push_back(std::move(kv.second));
     late_panes.clear();
   }
-  if (world > 1) { if (!has_lwm || lwm <= wm_after) lwm = wm_after; has_lwm = true; }   // emission waits for the global watermark
-  else emit_normal(wm_after);
+  if (world > 1) { if (!has_lwm || lwm <= r.wm_after) lwm = r.wm_after; has_lwm = true; }   // emission waits for the global watermark
+  else emit_normal(r.wm_after, false, nullptr);
   g_tr.mark("emit");
 }
 
-void dnz_window::emit_normal(int64_t wm_new) {
+// The host has the scan results of a sealed superbatch: replay the reference's per-batch watermark rule over its batches, enqueue
+// the aggregation and the emission of every window it closes.  The common case -- one run, nothing late -- is enqueued without
+// waiting for anything: emission is gated ON THE DEVICE by the deferred-row counters, and verify() inspects the outcome later.
+void dnz_window::launch_slot(Slot& s) {
+  if (s.state != Slot::SEALED) return;
+  sealed_order.erase(std::find(sealed_order.begin(), sealed_order.end(), s.idx));
+  s.speculative = false; s.emit_starts.clear(); s.add_rows_bound = s.add_bytes_bound = 0; s.rows_launched = 0; s.timed = false;
+  g_tr.mark("pre");
+  if (s.n_tiles > 0) {
+    CK(cudaEventSynchronize(s.scan_done));
+    g_tr.mark("scan_wait");
+    const size_t nb = s.batches.size();
+    std::vector<BatchMinMax> mm(s.h_minmax.as<BatchMinMax>(), s.h_minmax.as<BatchMinMax>() + nb);
+    // ---- validation: inputs the reference panics on
+    for (size_t i = 0; i < nb; i++) {
+      if (s.bds[i].n_rows == 0) continue;
+      if (mm[i].n_valid == 0) fail(DNZ_ERR_DATA, "batch %lld: all-null canonical_timestamp (the reference unwraps None and panics)", (long long)s.bds[i].seq);
+      if (mm[i].ts_min < 0 || (S > 0 && mm[i].ts_min - L < 0)) fail(DNZ_ERR_DATA, "batch %lld: timestamp before epoch (+window): the reference panics in duration_since(UNIX_EPOCH)", (long long)s.bds[i].seq);
+    }
+    std::vector<Run> runs;
+    plan_runs(s, mm, runs);
+    const bool speculative = world == 1 && runs.size() == 1 && !runs[0].dirty && !(cfg.flags & DNZ_FLAG_SYNCHRONOUS);
+    if (!speculative) while (!launched_order.empty()) verify(slot[launched_order.front()]);
+    if (res_consumed) reset_results();
+    rotate_result_sets();
+    if (speculative) {
+      const Run& r = runs[0];
+      RunGeom g = run_geometry(s, mm, r);
+      if (g.t1 > g.t0) {
+        if (g.pmin <= g.pmax) {
+          prepare_panes(s, mm, r, g);
+          g_tr.mark("panes");
+          AggParams P = build_agg_params(s, g, false, 0, 0);
+          launch_aggregate_pass(s, g, P, false);
+          g_tr.mark("agg_launch");
+          s.speculative = true; s.t0 = g.t0; s.t1 = g.t1; s.pmin = g.pmin; s.pmax = g.pmax; s.rows_launched = g.rows;
+        }
+        emit_normal(r.wm_after, true, &s);
+        g_tr.mark("emit");
+      }
+    } else {
+      for (const Run& r : runs) execute_run_sync(s, mm, r);
+    }
+  }
+  CK(cudaMemcpyAsync(s.snap.p, d_ctl.p, CTL_BYTES, cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(s.done, stream));
+  s.state = Slot::LAUNCHED; launched_order.push_back(s.idx);
+  g_tr.flush("superbatch");
+}
+
+// Inspect the snapshot taken behind a slot's launches (waits for it if it has not been written yet).
+void dnz_window::verify(Slot& s) {
+  if (s.state != Slot::LAUNCHED) return;
+  CK(cudaEventSynchronize(s.done));
+  const char* h = s.snap.as<char>();
+  parse_ctl(h);
+  // what later launches may have added on top of this snapshot
+  rows_since_known = 0;
+  bool later = false;
+  for (int i : launched_order) { if (i == s.idx) { later = true; continue; } if (later) rows_since_known += slot[i].rows_launched; }
+  for (int k = 0; k < 2; k++) {
+    uint64_t c = *reinterpret_cast<const uint64_t*>(h + rs[k].ctl_off);
+    uint64_t rows = c >> 32, bytes = c & 0xFFFFFFFFull;
+    later = false;
+    for (int i : launched_order) { if (i == s.idx) { later = true; continue; } if (later && slot[i].emit_set == k) { rows += slot[i].add_rows_bound; bytes += slot[i].add_bytes_bound; } }
+    rs[k].rows = rows; rs[k].bytes = bytes;
+  }
+  if (s.timed) { float ms = 0; CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1)); stats.agg_kernel_ms += ms; stats.agg_algorithmic_bytes += s.alg_bytes; s.timed = false; }
+  if (s.speculative) {
+    const char* hs = h + s.ctl_off();
+    defer_count_host = *reinterpret_cast<const uint64_t*>(hs); defer_flags_host = *reinterpret_cast<const uint32_t*>(hs + 8);
+    bool blocked = *reinterpret_cast<const uint32_t*>(hs + 16) != 0;
+    if (defer_count_host) {
+      // rare: a table was too small.  Let everything that is enqueued finish (emission behind this launch -- and behind later
+      // ones -- found the gate closed and did nothing), replay the deferred rows, then issue the emission again.
+      CK(cudaStreamSynchronize(stream));
+      RunGeom g; g.t0 = s.t0; g.t1 = s.t1; g.pmin = s.pmin; g.pmax = s.pmax; g.rows = s.rows_launched; g.alg_bytes = s.alg_bytes;
+      resolve_deferred(s, g, false, 0);
+      blocked = true;
+    }
+    if (blocked) {
+      CK(cudaMemsetAsync(ctl(s.ctl_off() + 16), 0, 4, stream));
+      if (!s.emit_starts.empty()) emit_windows(s.emit_starts, pane_sources(), false, nullptr);
+    }
+  }
+  release_slot(s);
+}
+
+void dnz_window::release_slot(Slot& s) {
+  if (s.copies) cudaEventSynchronize(s.copy_done);
+  for (auto& pb : s.batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
+  s.batches.clear(); s.gather.clear(); s.rows = 0; s.copies = false; s.arena.reset(); s.scanned = false; s.n_tiles = 0;
+  for (auto& p : s.retired) if (pane_pool.size() < 16) pane_pool.push_back(std::move(p));
+  s.retired.clear(); s.emit_starts.clear(); s.speculative = false; s.add_rows_bound = s.add_bytes_bound = 0; s.rows_launched = 0;
+  auto it = std::find(launched_order.begin(), launched_order.end(), s.idx);
+  if (it != launched_order.end()) launched_order.erase(it);
+  s.state = Slot::FREE;
+}
+
+void dnz_window::emit_normal(int64_t wm_new, bool gated, Slot* sl) {
   if (!has_wm || wm <= wm_new) { wm = wm_new; has_wm = true; }
   std::set<int64_t> starts;
   for (auto& kv : panes)
@@ -934,31 +1178,32 @@ void dnz_window::emit_normal(int64_t wm_new) {
     }
   std::map<int64_t, Pane*> src;
   for (auto& kv : panes) src[kv.first] = kv.second.get();
-  emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src);
+  emit_windows(std::vector<int64_t>(starts.begin(), starts.end()), src, gated, sl);
   emitted_upto = std::max(emitted_upto, wm);
-  retire_panes();
+  retire_panes(gated ? sl : nullptr);
 }
 
 void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
   uint64_t need_rows = R().rows + add_rows, need_bytes = R().bytes + add_bytes;
-  if (need_bytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes between polls (Utf8 offsets are 32-bit); poll more often");
+  if (need_bytes >= (1ull << 31) || need_rows >= (1ull << 32)) {
+    // the bound may be stale: make it exact before giving up
+    drain(); fetch_ctl();
+    need_rows = R().rows + add_rows; need_bytes = R().bytes + add_bytes;
+    if (need_bytes >= (1ull << 31)) fail(DNZ_ERR_UNSUPPORTED, "more than 2 GiB of key bytes between polls (Utf8 offsets are 32-bit); poll more often");
+  }
   if (need_rows <= R().row_cap && need_bytes <= R().byte_cap) return;
-  auto grow = [&](DevBuf& b, size_t elem, uint64_t used, uint64_t cap) {
-    DevBuf nb; nb.alloc((size_t)cap * elem + 64);
-    if (used && b.p) CK(cudaMemcpyAsync(nb.p, b.p, (size_t)used * elem, cudaMemcpyDeviceToDevice, stream));
-    CK(cudaStreamSynchronize(stream));
-    b = std::move(nb);
-  };
+  auto grow = [&](DevBuf& b, size_t elem, uint64_t used, uint64_t cap) { b.regrow_on(stream, (size_t)cap * elem + 64, b.p ? (size_t)used * elem : 0); };
   if (need_rows > R().row_cap) {
     uint64_t cap = std::max<uint64_t>(need_rows, R().row_cap * 2);
-    grow(R().key_off, 4, R().rows, cap + 1); grow(R().key_valid, 1, R().rows, cap); grow(R().count, 8, R().rows, cap);
-    grow(R().mn, 8, R().rows, cap); grow(R().mx, 8, R().rows, cap); grow(R().avg, 8, R().rows, cap); grow(R().sum, 8, R().rows, cap);
-    grow(R().agg_valid, 1, R().rows, cap); grow(R().wstart, 8, R().rows, cap); grow(R().wend, 8, R().rows, cap);
+    const uint64_t used = std::min(R().rows, R().row_cap);
+    grow(R().key_off, 4, used, cap + 1); grow(R().key_valid, 1, used, cap); grow(R().count, 8, used, cap);
+    grow(R().mn, 8, used, cap); grow(R().mx, 8, used, cap); grow(R().avg, 8, used, cap); grow(R().sum, 8, used, cap);
+    grow(R().agg_valid, 1, used, cap); grow(R().wstart, 8, used, cap); grow(R().wend, 8, used, cap);
     R().row_cap = cap;
   }
   if (need_bytes > R().byte_cap) {
     uint64_t cap = std::max<uint64_t>(need_bytes, R().byte_cap * 2);
-    grow(R().key_bytes, 1, R().bytes, cap);
+    grow(R().key_bytes, 1, std::min(R().bytes, R().byte_cap), cap);
     R().byte_cap = cap;
   }
 }
@@ -967,6 +1212,7 @@ void dnz_window::reset_set(int i) {
   ResultSet& r = rs[i];
   CK(cudaMemsetAsync(ctl(r.ctl_off), 0, 16, stream));
   r.rows = 0; r.bytes = 0; r.exp_rows = 0; r.exp_bytes = 0; r.snap_issued = false;
+  for (Slot& s : slot) if (s.emit_set == i) { s.add_rows_bound = 0; s.add_bytes_bound = 0; }
 }
 void dnz_window::reset_results() { reset_set(wr); res_consumed = false; }
 
@@ -992,13 +1238,14 @@ void dnz_window::rotate_result_sets() {
   if (set_drained(rs[wr ^ 1])) { if (rs[wr ^ 1].exp_rows || rs[wr ^ 1].rows) reset_set(wr ^ 1); wr ^= 1; }
 }
 
-// One k_emit launch per window: combine its panes, apply the fused FilterExec predicate, compact.
-void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src) {
+// One k_emit launch per window: combine its panes, apply the fused FilterExec predicate, compact.  `gated`: the launches do
+// nothing (and raise the slot's emit-blocked flag) when any pipeline slot holds deferred rows at the time they run.
+void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map<int64_t, Pane*>& src, bool gated, Slot* sl) {
   if (starts.empty()) return;
-  if (!ctl_fresh) fetch_ctl();        // group count + result cursor (already fetched after an aggregate launch)
-  ctl_fresh = false;
-  if (n_groups_host == 0) return;
-  ensure_result_capacity((uint64_t)starts.size() * n_groups_host, (uint64_t)starts.size() * key_bytes_total_host);
+  const uint32_t ng = groups_bound();
+  if (ng == 0) return;
+  const uint64_t add_rows = (uint64_t)starts.size() * ng, add_bytes = (uint64_t)starts.size() * key_bytes_bound();
+  ensure_result_capacity(add_rows, add_bytes);
   for (int64_t s : starts) {
     EmitParams E; memset(&E, 0, sizeof E);
     int64_t p0 = s / pane_ms; int k = 0;
@@ -1013,8 +1260,10 @@ void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map
     if (k == 0) continue;
     E.n_panes = k; E.has_filter = cfg.has_filter;
     E.filter_col = cfg.has_filter ? aggs[cfg.filter_agg].kind : 0; E.filter_op = cfg.filter_op; E.filter_lit = cfg.filter_literal;
-    E.wstart = s; E.wend = s + L; E.n_groups = n_groups_host; E.rank = rank; E.world = world;
+    E.wstart = s; E.wend = s + L; E.n_groups = ng; E.rank = rank; E.world = world;
     E.dict = dict_view();
+    E.gate = gated ? reinterpret_cast<const unsigned long long*>(ctl(64)) : nullptr;
+    E.blocked = gated && sl ? reinterpret_cast<uint32_t*>(ctl(sl->ctl_off() + 16)) : nullptr;
     E.out.key_off = R().key_off.as<int32_t>(); E.out.key_bytes = R().key_bytes.as<uint8_t>(); E.out.key_valid = R().key_valid.as<uint8_t>();
     E.out.count = R().count.as<int64_t>(); E.out.mn = R().mn.as<double>(); E.out.mx = R().mx.as<double>(); E.out.avg = R().avg.as<double>();
     E.out.sum = R().sum.as<double>(); E.out.agg_valid = R().agg_valid.as<uint8_t>(); E.out.wstart = R().wstart.as<int64_t>(); E.out.wend = R().wend.as<int64_t>();
@@ -1023,8 +1272,12 @@ void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map
     CK(launch_emit(E, stream));
     stats.total_launches++; stats.windows_emitted++;
   }
+  R().rows += add_rows; R().bytes += add_bytes;
+  if (sl && gated) {
+    sl->emit_starts.insert(sl->emit_starts.end(), starts.begin(), starts.end());
+    sl->add_rows_bound += add_rows; sl->add_bytes_bound += add_bytes; sl->emit_set = wr;
+  }
   snapshot_results();
-  ctl_fresh = false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1049,12 +1302,17 @@ void dnz_window::fill_schema(ArrowSchema* schema) {
   schema->release = release_schema; schema->private_data = sp;
 }
 
+
 // Hands out every emitted row that is COMPLETE on the device: per result set, the rows between what was exported before and
 // the newest snapshot whose event has fired (older set first).  `blocking` callers have synchronised the stream, so every
 // snapshot has fired; the non-blocking poll simply leaves rows of still-running emits for the next call.  The device->host
 // copies run on their own stream, never behind queued input.
 void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking) {
   if (blocking) { CK(cudaStreamSynchronize(stream)); }
+  else {
+    while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
+    cudaGetLastError();
+  }
   struct Range { ResultSet* r; uint64_t r0, r1, b0, b1; };
   std::vector<Range> ranges;
   for (int k = 0; k < 2; k++) {
@@ -1157,10 +1415,53 @@ void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has
   }
 }
 
+// Device-resident hand-over: the oldest range of emitted rows that has not been handed out yet, one result set per call (call
+// again until n_rows == 0 when both sets may hold rows).  blocking: everything has been aggregated and the stream is idle, so
+// every emitted row is eligible.  Non-blocking: only rows whose emission is COMPLETE on the device; nothing queued is forced.
+// key_off entries are offsets into `key_bytes` (the set's byte buffer); key_bytes_len is the offset at which the last returned
+// key ends.
+void dnz_window::export_device(dnz_device_result* out, bool blocking) {
+  memset(out, 0, sizeof *out);
+  ResultSet* r = nullptr; uint64_t r0 = 0, r1 = 0, b1 = 0;
+  if (blocking) fetch_ctl();
+  else {
+    // release the input of launches that have completed (never waits)
+    while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
+    cudaGetLastError();
+  }
+  for (int k = 0; k < 2 && !r; k++) {
+    ResultSet& c = rs[k == 0 ? (wr ^ 1) : wr];
+    uint64_t rows = c.rows, bytes = c.bytes;
+    if (!blocking) {
+      if (!c.snap_issued) continue;
+      if (cudaEventQuery(c.snap_ev) != cudaSuccess) { cudaGetLastError(); continue; }
+      const volatile uint64_t* sp = reinterpret_cast<volatile uint64_t*>(c.snap.p);
+      const uint64_t cur = sp[0];
+      if (static_cast<uint32_t>(sp[1])) fail(DNZ_ERR_NOMEM, "result buffer overflow (internal sizing error)");
+      rows = cur >> 32; bytes = cur & 0xFFFFFFFFull;
+    }
+    if (rows > c.exp_rows) { r = &c; r0 = c.exp_rows; r1 = rows; b1 = bytes; }
+  }
+  if (!r) return;
+  r->exp_rows = r1; r->exp_bytes = b1;
+  if (blocking) {          // stream idle: a set that has been handed out completely restarts at row 0 with the next emission
+    for (int i = 0; i < 2; i++) if (rs[i].exp_rows && rs[i].exp_rows == rs[i].rows) reset_set(i);
+  }
+  out->n_rows = (int64_t)(r1 - r0); out->key_bytes_len = (int64_t)b1;
+  out->key_off = r->key_off.as<int32_t>() + r0; out->key_bytes = r->key_bytes.as<uint8_t>(); out->key_valid = r->key_valid.as<uint8_t>() + r0;
+  out->count = r->count.as<int64_t>() + r0; out->min = r->mn.as<double>() + r0; out->max = r->mx.as<double>() + r0;
+  out->avg = r->avg.as<double>() + r0; out->sum = r->sum.as<double>() + r0; out->agg_valid = r->agg_valid.as<uint8_t>() + r0;
+  out->window_start_ms = r->wstart.as<int64_t>() + r0; out->window_end_ms = r->wend.as<int64_t>() + r0;
+  stats.rows_out += (int64_t)(r1 - r0);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+
 // ------------------------------------------------------------------------------------------------
 // pane exchange (see include/dnz_gpu.h)
 void dnz_window::export_partials(int64_t watermark, dnz_partials* out) {
-  process_pending();
+  process_pending(); drain();
   memset(out, 0, sizeof *out);
   h_owner_counts.assign((size_t)world, 0); h_owner_bytes.assign((size_t)world, 0);
   out->owner_counts = h_owner_counts.data(); out->owner_key_bytes = h_owner_bytes.data();
@@ -1174,7 +1475,7 @@ void dnz_window::export_partials(int64_t watermark, dnz_partials* out) {
   out->pane_lo = lo; out->pane_hi = hi;
   exported_pane_upto = hi;
   if (send.empty()) return;
-  fetch_ctl(); ctl_fresh = false;
+  fetch_ctl();
   if (n_groups_host == 0) return;
   d_owner_cursor.reserve((size_t)world * 8);
   h_small.reserve((size_t)std::max(256, world * 8));
@@ -1222,36 +1523,35 @@ void dnz_window::import_partials(const uint8_t* entries, const int64_t* src_coun
   if (!entries || (kb && !key_bytes)) fail(DNZ_ERR_INVALID, "null packet buffers");
   if (pane_hi < pane_lo || pane_hi - pane_lo >= (1 << 16)) fail(DNZ_ERR_INVALID, "bad pane range");
   // every received key may be new here: size the dictionary and the long-key arena first so that the merge cannot fail
-  fetch_ctl(); ctl_fresh = false;
+  fetch_ctl();
   while ((uint64_t)n_groups_host + (uint64_t)n > gcap) dict_grow();
   {
-    uint64_t arena_used = *reinterpret_cast<const uint64_t*>(h_small.as<char>() + 8);
-    while (arena_used + (uint64_t)kb + 64 > arena_cap) arena_grow();
+    if (arena_used_host + (uint64_t)kb + 64 > arena_cap) arena_grow(arena_used_host + (uint64_t)kb + 64);
   }
   const int64_t np = pane_hi - pane_lo + 1;
   for (int64_t p = pane_lo; p <= pane_hi; p++) ensure_side_arrays(get_pane(p, true));
   const size_t pb = (size_t)np * sizeof(void*);
-  h_stage.reserve(7 * pb); d_ptrs.reserve(7 * pb);
-  void** hp = h_stage.as<void*>();
+  h_xptrs.reserve(7 * pb); d_xptrs.reserve(7 * pb);
+  void** hp = h_xptrs.as<void*>();
   for (int64_t p = pane_lo; p <= pane_hi; p++) {
     const size_t k = (size_t)(p - pane_lo);
     Pane* m = get_pane(p, false);
     hp[0 * np + k] = m->st.p; hp[1 * np + k] = nullptr; hp[2 * np + k] = m->nullrows.p; hp[3 * np + k] = nullptr;
     hp[4 * np + k] = m->fz.p; hp[5 * np + k] = nullptr; hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m->tag & 0xFFFFFFFFull));
   }
-  CK(cudaMemcpyAsync(d_ptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemsetAsync(ctl(96), 0, 4, stream));
-  char* dp = d_ptrs.as<char>();
+  CK(cudaMemcpyAsync(d_xptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(ctl(CTL_MERGE_ERR), 0, 4, stream));
+  char* dp = d_xptrs.as<char>();
   M.panes.pane0 = pane_lo; M.panes.n_panes = (int32_t)np; M.panes.pane_ms = pane_ms;
   M.panes.main = (GroupState* const*)(dp + 0 * pb); M.panes.late = (GroupState* const*)(dp + 1 * pb);
   M.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); M.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
   M.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); M.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
   M.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
   M.entries = reinterpret_cast<const PartialEntry*>(entries); M.n_entries = n; M.key_bytes = key_bytes; M.world = world;
-  M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(96));
+  M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR));
   CK(launch_merge_partials(M, stream)); stats.total_launches++;
-  fetch_ctl(); ctl_fresh = false;
-  uint32_t err = *reinterpret_cast<const uint32_t*>(h_small.as<char>() + 96);
+  fetch_ctl();
+  uint32_t err = *reinterpret_cast<const uint32_t*>(h_small.as<char>() + CTL_MERGE_ERR);
   if (err) fail(DNZ_ERR_NOMEM, "pane merge failed (flags %u): table sizing error", err);
   stats.exchanged_in += n;
 }
@@ -1267,7 +1567,7 @@ void dnz_window::import_partials(const uint8_t* entries, const int64_t* src_coun
 #define DNZ_CATCH(w)                                                                \
   } catch (const DnzError& e) {                                                     \
     (w)->err = e.msg; g_last_error = e.msg;                                         \
-    if (e.code == DNZ_ERR_CUDA) (w)->sticky = e.code;                               \
+    if (e.code == DNZ_ERR_CUDA || (w)->in_process) (w)->sticky = e.code;            \
     return e.code;                                                                  \
   } catch (const std::exception& e) {                                               \
     (w)->err = e.what(); g_last_error = e.what(); return DNZ_ERR_NOMEM;             \
@@ -1308,7 +1608,7 @@ int32_t dnz_window_push_device(dnz_window* w, const dnz_device_batch* batches, i
 int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_output) {
   DNZ_TRY(w)
   if (!out) fail(DNZ_ERR_INVALID, "null out");
-  w->process_pending();
+  w->process_pending(); w->drain();
   if (w->res_consumed) w->reset_results();
   w->export_arrow(out, out_schema, has_output, true);
   DNZ_CATCH(w)
@@ -1326,26 +1626,26 @@ int32_t dnz_window_poll_ready(dnz_window* w, struct ArrowArray* out, struct Arro
 int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out) {
   DNZ_TRY(w)
   if (!out) fail(DNZ_ERR_INVALID, "null out");
-  w->process_pending();
+  w->process_pending(); w->drain();
   if (w->res_consumed) w->reset_results();
-  w->fetch_ctl(); w->ctl_fresh = false;
-  if (w->R().exp_rows || w->rs[w->wr ^ 1].rows > w->rs[w->wr ^ 1].exp_rows)
-    fail(DNZ_ERR_UNSUPPORTED, "poll_device after a partial Arrow poll: drain with dnz_window_poll first");
-  out->n_rows = (int64_t)w->R().rows; out->key_bytes_len = (int64_t)w->R().bytes;
-  out->key_off = w->R().key_off.as<int32_t>(); out->key_bytes = w->R().key_bytes.as<uint8_t>(); out->key_valid = w->R().key_valid.as<uint8_t>();
-  out->count = w->R().count.as<int64_t>(); out->min = w->R().mn.as<double>(); out->max = w->R().mx.as<double>();
-  out->avg = w->R().avg.as<double>(); out->sum = w->R().sum.as<double>(); out->agg_valid = w->R().agg_valid.as<uint8_t>();
-  out->window_start_ms = w->R().wstart.as<int64_t>(); out->window_end_ms = w->R().wend.as<int64_t>();
-  w->stats.rows_out += (int64_t)w->R().rows;
-  w->res_consumed = true;         // buffers stay valid until the next call that produces output
+  w->export_device(out, true);
+  DNZ_CATCH(w)
+}
+
+int32_t dnz_window_poll_device_ready(dnz_window* w, dnz_device_result* out) {
+  DNZ_TRY(w)
+  if (!out) fail(DNZ_ERR_INVALID, "null out");
+  w->async_polls = true;
+  w->export_device(out, false);
   DNZ_CATCH(w)
 }
 
 int32_t dnz_window_flush(dnz_window* w, int64_t watermark_ms) {
   DNZ_TRY(w)
-  w->process_pending();
+  w->process_pending(); w->drain();
   if (w->res_consumed) w->reset_results();
-  w->emit_normal(watermark_ms);
+  w->rotate_result_sets();
+  w->emit_normal(watermark_ms, false, nullptr);
   DNZ_CATCH(w)
 }
 
@@ -1381,15 +1681,16 @@ int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
 int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch) {
   DNZ_TRY(w)
   if (bytes_per_launch < 0) fail(DNZ_ERR_INVALID, "negative size");
-  for (Arena& a : w->in_arena) {
-    size_t have = 0; for (auto& s : a.slabs) have += s.bytes;
+  for (Slot& s : w->slot) {
+    Arena& a = s.arena;
+    size_t have = 0; for (auto& b : a.slabs) have += b.bytes;
     if (have < (size_t)bytes_per_launch) { DevBuf b; b.alloc(round_up((size_t)bytes_per_launch - have, Arena::SLAB)); a.slabs.push_back(std::move(b)); }
   }
   DNZ_CATCH(w)
 }
 int32_t dnz_window_process(dnz_window* w, int64_t* local_watermark_ms) {
   DNZ_TRY(w)
-  w->process_pending();
+  w->process_pending(); w->drain();
   if (local_watermark_ms) *local_watermark_ms = w->world > 1 ? (w->has_lwm ? w->lwm : INT64_MIN) : (w->has_wm ? w->wm : INT64_MIN);
   DNZ_CATCH(w)
 }
@@ -1408,6 +1709,7 @@ int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, const 
   w->import_partials(entries, src_counts, key_bytes, src_key_bytes, pane_lo, pane_hi);
   DNZ_CATCH(w)
 }
+
 
 void* dnz_host_alloc(int64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 64)) == cudaSuccess ? p : nullptr; }
 void dnz_host_free(void* p) { if (p) cudaFreeHost(p); }

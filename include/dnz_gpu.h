@@ -40,6 +40,7 @@ enum { DNZ_OP_GT = 0, DNZ_OP_GTE = 1, DNZ_OP_LT = 2, DNZ_OP_LTE = 3, DNZ_OP_EQ =
 #define DNZ_FLAG_NO_HINTS 4u        /* experiments: disable the per-group min/max reduction filter                 */
 #define DNZ_FLAG_NO_PRIVATE 16u     /* experiments: no per-CTA private pane copies for low-cardinality streams        */
 #define DNZ_FLAG_NO_QUEUE 8u        /* experiments: colliding probes loop in place instead of using the retry queue */
+#define DNZ_FLAG_SYNCHRONOUS 32u    /* testing / A-B: wait for every aggregate launch before emitting (no speculative pipeline) */
 
 typedef struct {
   int32_t kind;          /* DNZ_AGG_*                                            */
@@ -107,6 +108,7 @@ typedef struct {
   int64_t generic_tiles; int64_t fast_tiles;
   int64_t late_batches;         /* batches that contained late rows (exact re-open path) */
   int64_t exchanged_out; int64_t exchanged_in;   /* pane-exchange packets sent / merged   */
+  int64_t h2d_pageable_bytes;   /* part of h2d_bytes that came from pageable host memory (cudaMemcpyAsync, driver-staged) */
 } dnz_stats;
 
 /* replaces: StreamingWindowExec::try_new + ExecutionPlan::execute(partition, ctx)
@@ -139,6 +141,10 @@ int32_t dnz_window_poll_ready(dnz_window* w, struct ArrowArray* out, struct Arro
 
 /* As dnz_window_poll but leaves the emitted rows on the device. */
 int32_t dnz_window_poll_device(dnz_window* w, dnz_device_result* out);
+/* As dnz_window_poll_ready, device resident: the oldest range of emitted rows that is complete on the device and has not been
+ * handed out (n_rows = 0 when there is none); never waits for queued input.  key_off entries are offsets into key_bytes,
+ * key_bytes_len is where the last returned key ends.  Valid until the next call on the handle. */
+int32_t dnz_window_poll_device_ready(dnz_window* w, dnz_device_result* out);
 
 /* Test/bench only (the reference has no flush: open windows are never emitted, :348): advance the watermark
  * to watermark_ms as process_watermark would and trigger. */

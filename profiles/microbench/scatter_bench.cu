@@ -30,16 +30,17 @@ __device__ __forceinline__ void ld_slot_nc(const Slot* p, uint64_t& a, uint64_t&
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 enum Variant { V_RED4 = 0, V_RED2, V_PAIR, V_PAIR_ADD, V_PROBE, V_PROBE_NC, V_PROBE_RED4, V_PROBE_PAIR, V_PROBE_HINT, V_PROBE_HINT_SCALAR,
-               V_BULK, V_QUAD_ADD, V_RED1, V_PROBE_RED1, V_PROBE16, V_COUNT };
+               V_BULK, V_QUAD_ADD, V_RED1, V_PROBE_RED1, V_PROBE16, V_TEX32, V_TEX16, V_TEX32_HINT, V_PROBE_HINT_XOR, V_XOR_ADD, V_COUNT };
 static const char* NAMES[] = {"red4 (cnt,sum,min,max scalar REDs)", "red2 (cnt,sum scalar)", "pair (add.f64 x2 lanes + max.u64 x2 lanes, 16 rows/instr)",
                               "pair_add only", "probe only (ld.relaxed.gpu v4.u64)", "probe only (ld.global.nc v4.u64)", "probe + red4  [= round-1 kernel]",
                               "probe + pair", "probe + pair_add + 6% pair_max (hint)", "probe + red2 + 6% red max x2 (hint, scalar)",
                               "cp.reduce.async.bulk 16 B add.f64 + 16 B max.u64", "quad add.f64 (4 lanes/sector, 8 rows/instr)", "red1 (one scalar RED)",
-                              "probe + red1", "probe only 16 B (v2.u64)"};
+                              "probe + red1", "probe only 16 B (v2.u64)", "TEX probe 32 B (2 x tex1Dfetch<uint4>)", "TEX probe 16 B (1 x tex1Dfetch<uint4>)",
+                              "TEX probe 32 B + xor-pair add + 6% own-lane max", "LDG probe + xor-pair add + 6% own-lane max", "xor-pair add only (1 shuffle)"};
 
 template <int V>
 __global__ void __launch_bounds__(512) k_bench(State* __restrict__ st, const Slot* __restrict__ dict, uint32_t mask, uint64_t rows, uint32_t G,
-                                               unsigned long long* sink) {
+                                               unsigned long long* sink, cudaTextureObject_t tex) {
   const int lane = threadIdx.x & 31;
   uint64_t acc = 0;
   __shared__ __align__(16) unsigned long long stage[512 * 4];
@@ -63,6 +64,33 @@ __global__ void __launch_bounds__(512) k_bench(State* __restrict__ st, const Slo
       uint32_t idx = (uint32_t)splitmix(gid) & mask; uint64_t a, b;
       asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(dict + idx) : "memory");
       acc += a ^ b;
+    }
+
+    if (V == V_TEX32 || V == V_TEX16 || V == V_TEX32_HINT) {
+      uint32_t idx = (uint32_t)splitmix(gid) & mask;
+      uint4 a = tex1Dfetch<uint4>(tex, (int)(2u * idx));
+      acc += a.x ^ a.y ^ a.z ^ a.w;
+      if (V != V_TEX16) { uint4 b = tex1Dfetch<uint4>(tex, (int)(2u * idx + 1u)); acc += b.x ^ b.y ^ b.z ^ b.w; gid = (uint32_t)((gid + (b.x & 1)) % G); }
+      else gid = (uint32_t)((gid + (a.x & 1)) % G);
+      hint_pass = ((r >> 40) & 1023) < 61;
+    }
+    if (V == V_PROBE_HINT_XOR) {
+      uint32_t idx = (uint32_t)splitmix(gid) & mask;
+      uint64_t a, b, c, d; ld_slot(dict + idx, a, b, c, d);
+      acc += a ^ b ^ c ^ d; gid = (uint32_t)((gid + (a & 1)) % G); hint_pass = ((r >> 40) & 1023) < 61;
+    }
+    if (V == V_TEX32_HINT || V == V_PROBE_HINT_XOR || V == V_XOR_ADD) {
+      // lanes 2j / 2j+1 share one sector per instruction; ONE xor-shuffle of the group id serves both halves:
+      // half 0 = rows of even lanes (own lane adds the sum, the partner adds the count), half 1 = rows of odd lanes
+      const uint32_t g2 = __shfl_xor_sync(0xffffffffu, gid, 1);
+      const int odd = lane & 1;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const bool own = (odd == half);
+        State* s2 = st + (own ? gid : g2);
+        red_add_f64(reinterpret_cast<double*>(s2) + (own ? 1 : 0), own ? v : 1.0);
+      }
+      if (V != V_XOR_ADD && hint_pass) { red_max_u64(&st[gid].mnk, mnk); }
     }
     State* s = st + gid;
     if (V == V_RED4 || V == V_PROBE_RED4) { red_add_u64(&s->cnt, 1ull); red_add_f64(&s->sum, v); red_max_u64(&s->mnk, mnk); red_max_u64(&s->mxk, mxk); }
@@ -114,6 +142,7 @@ __global__ void __launch_bounds__(512) k_bench(State* __restrict__ st, const Slo
   if (acc == 0x1234567ull) *sink = acc;
 }
 
+static cudaTextureObject_t g_tex;
 template <int V>
 float run(State* st, Slot* dict, uint32_t mask, uint64_t rows, uint32_t G, unsigned long long* sink, int ctas_per_sm) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -121,7 +150,7 @@ float run(State* st, Slot* dict, uint32_t mask, uint64_t rows, uint32_t G, unsig
   for (int rep = 0; rep < 4; rep++) {
     CK(cudaMemsetAsync(st, 0, (size_t)G * sizeof(State)));
     CK(cudaEventRecord(e0));
-    k_bench<V><<<148 * ctas_per_sm, 512>>>(st, dict, mask, rows, G, sink);
+    k_bench<V><<<148 * ctas_per_sm, 512>>>(st, dict, mask, rows, G, sink, g_tex);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep && ms < best) best = ms;
   }
@@ -135,6 +164,12 @@ int main(int argc, char** argv) {
   State* st; Slot* dict; unsigned long long* sink;
   CK(cudaMalloc(&st, (size_t)G * sizeof(State))); CK(cudaMalloc(&dict, (size_t)cap * sizeof(Slot))); CK(cudaMalloc(&sink, 8));
   CK(cudaMemset(dict, 0, (size_t)cap * sizeof(Slot)));
+  {
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = dict; rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = (size_t)cap * sizeof(Slot);
+    cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+    CK(cudaCreateTextureObject(&g_tex, &rd, &td, nullptr));
+  }
   printf("rows=2^%d groups=%u dict_slots=%u (%.1f MB) state=%.1f MB\n", lg, G, cap, cap * 32.0 / 1e6, G * 32.0 / 1e6);
   for (int cps = 1; cps <= 4; cps *= 2) {
     printf("--- %d CTA(s) of 512 threads per SM\n", cps);
@@ -154,6 +189,11 @@ int main(int argc, char** argv) {
     ms[V_RED1] = run<V_RED1>(st, dict, cap - 1, rows, G, sink, cps);
     ms[V_PROBE_RED1] = run<V_PROBE_RED1>(st, dict, cap - 1, rows, G, sink, cps);
     ms[V_PROBE16] = run<V_PROBE16>(st, dict, cap - 1, rows, G, sink, cps);
+    ms[V_TEX32] = run<V_TEX32>(st, dict, cap - 1, rows, G, sink, cps);
+    ms[V_TEX16] = run<V_TEX16>(st, dict, cap - 1, rows, G, sink, cps);
+    ms[V_TEX32_HINT] = run<V_TEX32_HINT>(st, dict, cap - 1, rows, G, sink, cps);
+    ms[V_PROBE_HINT_XOR] = run<V_PROBE_HINT_XOR>(st, dict, cap - 1, rows, G, sink, cps);
+    ms[V_XOR_ADD] = run<V_XOR_ADD>(st, dict, cap - 1, rows, G, sink, cps);
     for (int v = 0; v < V_COUNT; v++)
       printf("%-62s %8.3f ms  %7.1f G rows/s  %5.2f cyc/row/SM @1.9GHz\n", NAMES[v], ms[v], rows / ms[v] * 1e-6, ms[v] * 1e-3 * 1.9e9 * 148 / rows);
   }

@@ -210,3 +210,118 @@ def test_device_resident_path_equals_host_path():
     assert st["agg_kernel_ms"] > 0 and st["agg_algorithmic_bytes"] == dev.algorithmic_bytes
     w.close()
     dev.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# round 2: the speculative three-slot pipeline (scan k+1 | aggregate + gated emission k | verify k-1) and the growth paths
+def _stream(seed, n_batches, rows, n_keys, span_ms=300, long_keys=False, late_every=0, late_shift_ms=0):
+    rng = np.random.default_rng(seed)
+    out, t = [], T0
+    for b in range(n_batches):
+        back = late_shift_ms if (late_every and b % late_every == late_every - 1) else 0
+        k = rng.integers(0, n_keys, rows)
+        ts = t - back + rng.integers(0, span_ms, rows)
+        v = rng.random(rows) * 115.0
+        if long_keys:
+            keys = [(b"key-%06d-" % int(x)) * 3 for x in k]         # 33 B: arena keys
+        else:
+            keys = [b"sensor_%d" % int(x) for x in k]
+        out.append(rows_to_batch([(int(ts[i]), float(v[i]), keys[i]) for i in range(rows)]))
+        t += span_ms
+    return out, t
+
+
+@pytest.mark.parametrize("L,S", [(1000, 0), (3000, 1000)])
+@pytest.mark.parametrize("expected_groups", [0, 16])
+def test_speculative_pipeline_matches_oracle_and_synchronous_mode(L, S, expected_groups):
+    """Many small superbatches (max_rows_per_launch = 3 batches) so that the three pipeline slots rotate; non-forcing polls in
+    between; expected_groups=16 makes the dictionary overflow INSIDE the pipeline: emission behind the launch finds the gate
+    closed, the deferred rows are replayed at verification and the emission is issued again."""
+    from tests.helpers import gpu_window, to_record_batch, record_batch_rows
+    batches, t_end = _stream(77 + L + expected_groups, 40, 2500, 3000)
+    batches.append(sentinel(t_end + 3 * L))
+    want = run_oracle_batches(batches, L, S)
+    res = {}
+    for flags in (0, 32):                       # 32 = DNZ_FLAG_SYNCHRONOUS
+        w = gpu_window(L, S, None, expected_groups=expected_groups, max_rows_per_launch=7500, flags=flags)
+        rows = []
+        for b in batches:
+            w.push(to_record_batch(b))
+            rows += record_batch_rows(w.poll_ready())
+        rows += record_batch_rows(w.poll())
+        st = w.stats()
+        w.close()
+        assert st["agg_launches"] >= 13
+        if expected_groups:
+            assert st["deferred_rows"] > 0
+        assert_rows_equal(rows, want)
+        res[flags] = st
+    assert res[0]["rows_out"] == res[32]["rows_out"] == len(want)
+
+
+def test_late_batch_while_the_dictionary_grows():
+    """a late (dirty) batch that also overflows the dictionary -- the one-batch late panes must grow with it."""
+    batches, t_end = _stream(5, 12, 1500, 40)
+    rng = np.random.default_rng(6)
+    late = [(T0 + int(rng.integers(0, 900)), float(rng.random()), b"newkey_%d" % i) for i in range(3000)]     # 3000 unseen keys, all late
+    batches.append(rows_to_batch(late))
+    more, t_end2 = _stream(7, 4, 1500, 40)
+    batches.append(sentinel(t_end + 9000))
+    for L, S in [(1000, 0), (2000, 1000)]:
+        want = run_oracle_batches(batches, L, S)
+        got, st = run_gpu(batches, L, S, expected_groups=16)
+        assert st["late_batches"] >= 1 and st["deferred_rows"] > 0
+        assert_rows_equal(got, want, check_seq=True)
+
+
+def test_long_key_arena_growth_in_one_launch():
+    """more than 1 MiB of long keys inserted by ONE launch (the arena starts at 1 MiB)."""
+    n_keys = 45_000
+    rows = [(T0 + (i % 900), float(i % 97), (b"long-key-%08d-" % (i % n_keys)) * 2 + b"x" * 6) for i in range(90_000)]   # 40 B keys
+    batches = [rows_to_batch(rows[i:i + 30_000]) for i in range(0, len(rows), 30_000)] + [sentinel(T0 + 5000)]
+    want = run_oracle_batches(batches, 1000)
+    got, st = run_gpu(batches, 1000, per_batch_poll=False, expected_groups=n_keys)
+    assert st["deferred_rows"] > 0 and len(want) == n_keys + 0
+    assert_rows_equal(got, want)
+
+
+def test_idle_gap_between_queued_batches():
+    """two batches 30 h apart queued into one launch: the pane span limit applies per run, not per launch."""
+    a = rows_to_batch([(T0 + i, 1.0 + i, b"a") for i in range(50)])
+    b = rows_to_batch([(T0 + 30 * 3600 * 1000 + i, 2.0 + i, b"b") for i in range(50)])
+    batches = [a, b, sentinel(T0 + 31 * 3600 * 1000)]
+    want = run_oracle_batches(batches, 1000)
+    got, _ = run_gpu(batches, 1000, per_batch_poll=False)
+    assert len(want) == 2
+    assert_rows_equal(got, want)
+
+
+def test_device_ready_poll_hands_out_every_row_once():
+    from denormalized_b200 import DeviceBatches
+    from tests.helpers import gpu_window
+    import ctypes as C
+    from denormalized_b200 import capi
+    n, G, rpm = 2_000_000, 5000, 400
+    dev = DeviceBatches(n, 65536, groups=G, rows_per_ms=rpm)
+    w = gpu_window(1000, 0, None, expected_groups=G, max_rows_per_launch=4 * 65536)
+    got = []
+
+    def take(r):
+        if r.n_rows:
+            f = w.fetch_device_result(r)
+            got.extend((int(f["window_start"][i]), int(f["window_end"][i]), f["key"][i], int(f["count"][i]), float(f["min"][i]),
+                        float(f["max"][i]), float(f["avg"][i]), 0) for i in range(r.n_rows))
+        return r.n_rows
+    for g0 in range(0, dev.n_batches, 4):
+        k = min(4, dev.n_batches - g0)
+        w.push_device(array=C.cast(C.byref(dev.array, g0 * C.sizeof(capi.DeviceBatchC)), C.POINTER(capi.DeviceBatchC)), n=k)
+        while take(w.poll_device_ready()):
+            pass
+    w.flush(T0 + n // rpm + 5000)
+    while take(w.poll_device()):
+        pass
+    hb = [synth_batch(i, min(65536, n - i), groups=G, rows_per_ms=rpm) for i in range(0, n, 65536)]
+    hb.append(sentinel(T0 + n // rpm + 5000))
+    want = run_oracle_batches(hb, 1000)
+    assert_rows_equal(got, want)
+    w.close(); dev.free()
