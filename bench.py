@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exchange", action="store_true", help="N>1: skip the extra leg with un-partitioned input + pane all-to-all")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the legs' output (outside the timed regions)")
     ap.add_argument("--flags", type=int, default=0, help="extra DNZ_FLAG_* bits for the operator (experiments)")
     return ap.parse_args()
 
@@ -239,7 +240,7 @@ def pinned_host_batches(d, wl, rows, rank, world):
         meta = pa.StructArray.from_arrays([barrier, ts], fields=meta_fields)
         batches.append(pa.RecordBatch.from_arrays([occ, val, key, meta], schema=schema))
         in_bytes += 20 * BATCH_ROWS + 4 + used
-    return batches, in_bytes, base
+    return batches, in_bytes, base, addrs
 
 
 def export_all(d, batches):
@@ -248,6 +249,110 @@ def export_all(d, batches):
     for i, b in enumerate(batches):
         b._export_to_c(C.addressof(arr[i]))
     return arr
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of the timed legs (outside the timed regions): the rows a leg emitted for the windows that lie completely inside the
+# first `sample` rows of its stream are compared, row by row, with the CPU oracle run over exactly those rows
+def parity_sample_rows(wl, world):
+    n = min(200_000_000 if world == 1 else 100_000_000, wl["rows"])
+    return max(BATCH_ROWS, n // BATCH_ROWS * BATCH_ROWS)
+
+
+def batches_from_addresses(addrs, n_batches):
+    """oracle.Batch views over the page-locked buffers the e2e leg feeds to the operator (no copy)."""
+    from oracle import Batch
+
+    def view(addr, dt, n):
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt)
+    out = []
+    for a_ts, a_val, a_off, a_kb, used in addrs[:n_batches]:
+        out.append(Batch(ts=view(a_ts, np.int64, BATCH_ROWS), val=view(a_val, np.float64, BATCH_ROWS), key_off=view(a_off, np.int32, BATCH_ROWS + 1),
+                         key_bytes=view(a_kb, np.uint8, max(used, 1))))
+    return out
+
+
+def oracle_sample(wl, batches, sample_rows):
+    """Oracle rows (pyarrow Table) of the windows that end at or before the last full millisecond of the sample."""
+    import pyarrow.compute as pc
+    from tests.helpers import oracle_mt_arrays, result_table, rows_to_batch
+    span_ms = sample_rows // wl["rows_per_ms"]                      # rows [0, span_ms * rows_per_ms) carry ts < T0 + span_ms
+    cut = T0 + span_ms
+    feed = list(batches) + [rows_to_batch([(cut + 2 * wl["window_ms"] + 1000, 1.0, b"sentinel")])]
+    t = time.perf_counter()
+    arr = oracle_mt_arrays(feed, wl["window_ms"], wl["slide_ms"], wl["filt"])
+    dt = time.perf_counter() - t
+    tab = result_table(arr, "w")
+    tab = tab.filter(pc.less_equal(pc.add(tab["ws"], wl["window_ms"]), cut))
+    return tab, cut, dt
+
+
+class Capture(list):
+    """Collects a leg's emitted results, keeping only the polls that contain rows of windows ending at or before `cut`."""
+
+    def __init__(self, cut, window_ms):
+        super().__init__()
+        self.cut, self.window_ms = cut, window_ms
+
+    def append(self, part):
+        if isinstance(part, dict):
+            ws = np.asarray(part["window_start"])
+            keep = len(ws) and int(ws.min()) + self.window_ms <= self.cut
+        else:
+            import pyarrow.compute as pc
+            keep = part.num_rows and pc.min(part.column("window_start_time").cast("int64")).as_py() + self.window_ms <= self.cut
+        if keep:
+            super().append(part)
+
+
+def leg_checksum(parts, cut, window_ms):
+    """Order-independent checksum of the emitted rows of the windows that end at or before `cut`:
+    (rows, sum of counts, xor of min bit patterns, xor of max bit patterns, sum of averages)."""
+    n, sc, xmn, xmx, sa = 0, 0, 0, 0, 0.0
+    for p in parts:
+        if not len(p["count"]):
+            continue
+        m = (np.asarray(p["window_start"]) + window_ms) <= cut
+        ok = m & ((np.asarray(p["agg_isnull"]) == 0) if "agg_isnull" in p else (np.asarray(p["agg_valid"]) != 0))
+        n += int(m.sum()); sc += int(np.asarray(p["count"])[m].sum())
+        xmn ^= int(np.bitwise_xor.reduce(np.asarray(p["min"], np.float64)[ok].view(np.uint64))) if ok.any() else 0
+        xmx ^= int(np.bitwise_xor.reduce(np.asarray(p["max"], np.float64)[ok].view(np.uint64))) if ok.any() else 0
+        sa += float(np.asarray(p["avg"], np.float64)[ok].sum())
+    return (n, sc, xmn, xmx, sa)
+
+
+def combine_checksums(cs):
+    n = sum(c[0] for c in cs); sc = sum(c[1] for c in cs); sa = sum(c[4] for c in cs)
+    xmn = xmx = 0
+    for c in cs:
+        xmn ^= c[2]; xmx ^= c[3]
+    return (n, sc, xmn, xmx, sa)
+
+
+def compare_with_oracle(got_parts, want, cut, wl, what):
+    """got_parts: column-array dicts (device results) or pyarrow RecordBatches (Arrow results) of a leg."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from tests.helpers import assert_tables_equal, concat_arrays, result_table
+    tabs = []
+    for p in got_parts:
+        if isinstance(p, dict):
+            if not len(p["count"]):
+                continue
+            t = result_table(concat_arrays([p]), "g")
+        else:
+            if p.num_rows == 0:
+                continue
+            nulls = pc.is_null(p.column("min"))
+            t = pa.table({"ws": p.column("window_start_time").cast(pa.int64()), "key": p.column(0).cast(pa.binary()),
+                          "count_g": p.column("count"),
+                          "min_g": pa.array(p.column("min").fill_null(0.0).to_numpy(zero_copy_only=False).view(np.int64)),
+                          "max_g": pa.array(p.column("max").fill_null(0.0).to_numpy(zero_copy_only=False).view(np.int64)),
+                          "avg_g": p.column("average").fill_null(0.0), "null_g": nulls})
+        tabs.append(t.filter(pc.less_equal(pc.add(t["ws"], wl["window_ms"]), cut)))
+    got = pa.concat_tables(tabs) if tabs else want.slice(0, 0).rename_columns(["ws", "key", "count_g", "min_g", "max_g", "avg_g", "null_g"])
+    n = assert_tables_equal(got, want)
+    return {"leg": what, "rows_compared": int(n)}
 
 
 _JSON_OUT = None
@@ -304,7 +409,7 @@ def main():
 
     GROUP = int(os.environ.get('DNZ_BENCH_GROUP', '1024'))       # batches (64 Mi rows) pushed between polls: emitted windows are consumed as the stream advances
 
-    def step_device(w):
+    def step_device(w, capture=None):
         """One pass over the device-resident stream.  Batches are pushed 64 Mi rows at a time; the operator pipelines them (tile scan
         of group g+1 | aggregate + emission of group g | verification of group g-1) and the emitted windows are consumed as the
         stream advances with the non-forcing poll, so the host never waits between two kernels."""
@@ -317,6 +422,8 @@ def main():
                 if r.n_rows == 0:
                     break
                 n_out += r.n_rows
+                if capture is not None:
+                    capture.append(w.fetch_device_result(r, max_keys=0))
         # close the remaining windows a few at a time: one poll must stay below 2 GiB of key bytes (Utf8 offsets are 32-bit),
         # which 10 M 36-byte keys x 12 open sliding windows (cfg 5) would exceed
         step_ms = max(wl["slide_ms"] or wl["window_ms"], 1000) * (1 if G >= 4_000_000 else 64)
@@ -329,6 +436,8 @@ def main():
                 if r.n_rows == 0:
                     break
                 n_out += r.n_rows
+                if capture is not None:
+                    capture.append(w.fetch_device_result(r, max_keys=0))
         return n_out
 
     def barrier():
@@ -343,26 +452,49 @@ def main():
     out_rows = 0
     for _ in range(args.warmup):
         w = new_window(); out_rows = step_device(w); w.close()
-    wins = [new_window(d.capi.FLAG_KERNEL_TIMING) for _ in range(args.steps)]
+    # operators are created before the timed region (creation = allocation); huge tables (>= 4 M groups: tens of GB per
+    # operator) are created one at a time instead, from the memory the previous one returned to the pool
+    lazy = G >= 4_000_000
+    wins = [None if lazy else new_window(d.capi.FLAG_KERNEL_TIMING) for _ in range(args.steps)]
+    stats = []
     sampler = ClockSampler(local); sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for w in wins:
+        if lazy:
+            w = new_window(d.capi.FLAG_KERNEL_TIMING)
         step_device(w)
+        if lazy:
+            stats.append(w.stats()); w.close()
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     log(f"device-resident: {ms / args.steps:.2f} ms/step")
-    stats = [w.stats() for w in wins]
-    for w in wins:
-        w.close()
+    if not lazy:
+        stats = [w.stats() for w in wins]
+        for w in wins:
+            w.close()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = rows * world * args.steps / (ms * 1e-3)
+    parity = []
+    want = cut = None
+    if not args.no_parity:
+        from tests.helpers import host_stream
+        ps = parity_sample_rows(wl, world)
+        hs = host_stream(ps, groups=G, rows_per_ms=wl["rows_per_ms"], uuid_keys=wl["uuid"], seed=42 + rank, key_mul=world, key_add=rank)
+        want, cut, odt = oracle_sample(wl, hs, ps)
+        del hs
+        log(f"oracle over the first {ps} rows of this rank's stream: {odt:.1f} s, {want.num_rows} rows in complete windows")
+        capd = Capture(cut, wl["window_ms"])
+        wv = new_window(); step_device(wv, capd); wv.close()
+        parity.append(compare_with_oracle(capd, want, cut, wl, "value"))
+        del capd
+        log("value leg: emitted rows equal the oracle's")
     agg_ms = sum(s["agg_kernel_ms"] for s in stats); agg_bytes = sum(s["agg_algorithmic_bytes"] for s in stats)
     agg_launches = sum(s["agg_launches"] for s in stats); launches = sum(s["total_launches"] for s in stats)
     peak, peak_src = measured_peak()
@@ -385,14 +517,19 @@ def main():
         endm = d.DeviceBatches(1, 1, seed=7, groups=1, rows_per_ms=1, t0_ms=close_wm, device=local)     # end-of-stream marker row
         tr = TorchTransport(device=f"cuda:{local}")
 
-        def step_exchange(w):
+        def step_exchange(w, capture=None):
             n_out = 0
+
+            def take(r):
+                if capture is not None and r.n_rows:
+                    capture.append(w.fetch_device_result(r, max_keys=0))
+                return r.n_rows
             for g0 in range(0, devx.n_batches, GROUP):
                 n = min(GROUP, devx.n_batches - g0)
                 w.push_device(array=C.cast(C.byref(devx.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
-                n_out += exchange_step(w, tr, emit="device").n_rows
+                n_out += take(exchange_step(w, tr, emit="device"))
             w.push_device(endm)
-            return n_out + exchange_step(w, tr, emit="device").n_rows
+            return n_out + take(exchange_step(w, tr, emit="device"))
 
         def xwindow():
             w = new_window(); w.set_exchange(rank, world); return w
@@ -419,6 +556,30 @@ def main():
                     "nvlink_bytes_per_step": int(tp.item()) // args.steps * 80,
                     "what": f"{rows} rows/GPU of ONE {G}-key stream dealt to {world} GPUs (not key-partitioned); per 64 Mi rows: "
                             "watermark all-reduce(min), one all-to-all of 64 B pane packets + key bytes, owner merge, owners emit"}
+        if not args.no_parity:
+            # every rank owns a share of the keys: order-independent checksums of the rows each rank emitted for the windows inside
+            # the sample are combined on rank 0 and compared with the oracle run over the interleaved sample streams of ALL ranks
+            psx = max(BATCH_ROWS, min(rows, 200_000_000 // world) // BATCH_ROWS * BATCH_ROWS)
+            cutx = T0 + psx // wl["rows_per_ms"]
+            capx = Capture(cutx, wl["window_ms"])
+            w = xwindow(); step_exchange(w, capx); w.close()
+            mine = leg_checksum(capx, cutx, wl["window_ms"])
+            del capx
+            allsums = [None] * world
+            dist.all_gather_object(allsums, mine)
+            if rank == 0:
+                from tests.helpers import host_stream, oracle_mt_arrays, rows_to_batch
+                per_rank = [host_stream(psx, groups=G, rows_per_ms=wl["rows_per_ms"], uuid_keys=wl["uuid"], seed=42 + r) for r in range(world)]
+                feed = [per_rank[r][i] for i in range(len(per_rank[0])) for r in range(world)]      # batch i of every rank, then batch i+1 ...
+                feed.append(rows_to_batch([(cutx + 2 * wl["window_ms"] + 1000, 1.0, b"sentinel")]))
+                oarr = oracle_mt_arrays(feed, wl["window_ms"], wl["slide_ms"], wl["filt"])
+                del feed, per_rank
+                ref = leg_checksum([oarr], cutx, wl["window_ms"])
+                got = combine_checksums(allsums)
+                assert got[:4] == ref[:4], f"exchange leg differs from the oracle: {got} != {ref}"
+                assert abs(got[4] - ref[4]) <= 1e-9 * abs(ref[4]), f"exchange leg: sum of averages {got[4]} != {ref[4]}"
+                parity.append({"leg": "exchange", "rows_compared": int(ref[0]), "how": "checksums: rows, sum(count), xor(min bits), xor(max bits), sum(avg) 1e-9"})
+                log("exchange leg: checksums of the emitted rows equal the oracle's")
         devx.free(); endm.free()
         log(f"exchange leg: {xms / args.steps:.2f} ms/step")
 
@@ -435,12 +596,13 @@ def main():
         cap = rows if free_gb / world > 6 * rows * 40 / 2**30 else 268_435_456
         e2e_rows = args.e2e_rows or int(min(rows, cap, max(BATCH_ROWS, (free_gb / 4 / world) * 2**30 / 40)))
         e2e_rows = max(BATCH_ROWS, e2e_rows // BATCH_ROWS * BATCH_ROWS)
-        hb, in_bytes, base = pinned_host_batches(d, wl, e2e_rows, rank, world)
+        hb, in_bytes, base, hb_addrs = pinned_host_batches(d, wl, e2e_rows, rank, world)
         e_last = T0 + (e2e_rows - 1) // wl["rows_per_ms"]
         e_close = (e_last // 1000 + 1) * 1000 + 2 * wl["window_ms"]
         n_e2e_steps = args.warmup + args.steps
-        exported = [export_all(d, hb) for _ in range(n_e2e_steps)]
-        e_wins = [new_window() for _ in range(n_e2e_steps)]
+        n_e2e_total = n_e2e_steps + (0 if args.no_parity else 1)      # + one untimed pass whose output is compared with the oracle
+        exported = [export_all(d, hb) for _ in range(n_e2e_total)]
+        e_wins = [new_window() for _ in range(n_e2e_total)]
         launch_rows = args.max_rows_per_launch or (64 << 20)
         for w_ in e_wins:       # operator start-up (device staging for host batches) belongs to creation, not to the stream
             w_.reserve_input(int(min(launch_rows, e2e_rows) * (in_bytes / e2e_rows) * 1.05) + (64 << 20))
@@ -448,7 +610,7 @@ def main():
         push, poll, poll_ready, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_poll_ready, L.dnz_window_flush
         rel = C.CFUNCTYPE(None, C.c_void_p)
 
-        def step_host(i):
+        def step_host(i, capture=None):
             h = e_wins[i]._h
             arr = exported[i]
             n_out = 0
@@ -465,7 +627,11 @@ def main():
                     if rc:
                         raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
                     n_out += ca.length
-                    rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
+                    if capture is not None:      # takes ownership of both structs
+                        import pyarrow as pa
+                        capture.append(pa.RecordBatch._import_from_c(C.addressof(ca), C.addressof(cs)))
+                    else:
+                        rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
             return n_out
         log(f"e2e host batches ready: {e2e_rows} rows")
         for i in range(args.warmup):
@@ -485,8 +651,17 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ems, wall_ms = float(te[0].item()), float(te[1].item())
-        d2h = (sum(w.stats()["d2h_bytes"] for w in e_wins) - d2h0) // args.steps
-        h2d = e_wins[-1].stats()["h2d_bytes"]
+        d2h = (sum(w.stats()["d2h_bytes"] for w in e_wins[:n_e2e_steps]) - d2h0) // args.steps
+        h2d = e_wins[n_e2e_steps - 1].stats()["h2d_bytes"]
+        pageable = e_wins[n_e2e_steps - 1].stats()["h2d_pageable_bytes"]
+        if not args.no_parity:
+            if e2e_rows < parity_sample_rows(wl, world):     # shorter host stream than the oracle sample: its own oracle run
+                want, cut, odt = oracle_sample(wl, batches_from_addresses(hb_addrs, e2e_rows // BATCH_ROWS), e2e_rows)
+            cap = Capture(cut, wl["window_ms"])
+            step_host(n_e2e_total - 1, cap)
+            parity.append(compare_with_oracle(cap, want, cut, wl, "e2e"))
+            del cap
+            log("e2e leg: emitted rows equal the oracle's")
         for w in e_wins:
             w.close()
         e2e = {"value": e2e_rows * world * args.steps / (ems * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
@@ -515,7 +690,8 @@ def main():
                              "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                              "launches": int(agg_launches), "avg_launch_ms": agg_ms / max(agg_launches, 1),
                              "algorithmic_bytes_per_row": agg_bytes / max(rows * args.steps, 1)},
-                "e2e": e2e, "cpu_baseline": cpu}
+                "e2e": e2e, "cpu_baseline": cpu,
+                "parity_checked": bool(parity) and not args.no_parity, "parity": parity}
         if exchange:
             line["exchange"] = exchange
         print(json.dumps(line), file=claim_stdout(), flush=True)

@@ -304,11 +304,12 @@ class GpuStreamingWindow:
                     raise DnzError(rc, "memcpy")
             return a
         off = np.concatenate([get(r.key_off, np.int32, n), np.array([r.key_bytes_len], np.int32)])
-        kb = get(r.key_bytes, np.uint8, r.key_bytes_len).tobytes()
+        kb_arr = get(r.key_bytes, np.uint8, r.key_bytes_len)
+        kb = kb_arr.tobytes() if (max_keys is None or max_keys > 0) else b""
         kv = get(r.key_valid, np.uint8, n)
         av = get(r.agg_valid, np.uint8, n)
         nk = n if max_keys is None else min(n, max_keys)
-        return {"key": [kb[off[i]:off[i + 1]] if kv[i] else None for i in range(nk)], "key_off": off,
+        return {"key": [kb[off[i]:off[i + 1]] if kv[i] else None for i in range(nk)], "key_off": off, "key_bytes": kb_arr, "key_valid": kv,
                 "count": get(r.count, np.int64, n), "min": get(r.min, np.float64, n), "max": get(r.max, np.float64, n),
                 "avg": get(r.avg, np.float64, n), "sum": get(r.sum, np.float64, n), "agg_valid": av,
                 "window_start": get(r.window_start_ms, np.int64, n), "window_end": get(r.window_end_ms, np.int64, n)}

@@ -7,10 +7,10 @@ namespace dnz {
 
 // ------------------------------------------------------------------------------------------------
 // Tiling of the input.  One tile = up to TILE consecutive rows of ONE RecordBatch.
-constexpr int TILE = 416;             // rows per tile = consumer threads of one CTA (a multiple of 4: 16 B aligned column slices)
-constexpr int STAGES = 4;             // TMA ring depth per CTA
-constexpr int BCAP = 6656;            // staged key bytes per tile (16 B/row average); longer tiles take the generic path (a 16 KB budget with 3 stages was tried: cfg 2 -1.5 %, cfg 5 no gain)
-constexpr int CONSUMER_WARPS = 13;    // 416 consumer threads x 1 row = TILE; + 1 producer warp = 448 threads; two CTAs per SM at 72 registers (no spills)
+constexpr int TILE = 288;             // rows per tile = consumer threads of one CTA (a multiple of 4: 16 B aligned column slices)
+constexpr int STAGES = 5;             // TMA ring depth per CTA (the consumers hold two stages: the tile being probed and the one being reduced)
+constexpr int BCAP = 4608;            // staged key bytes per tile (16 B/row average); longer tiles take the generic path (a 16 KB budget with 3 stages was tried: cfg 2 -1.5 %, cfg 5 no gain)
+constexpr int CONSUMER_WARPS = 9;    // 416 consumer threads x 1 row = TILE; + 1 producer warp = 448 threads; two CTAs per SM at 72 registers (no spills)
 constexpr int AGG_THREADS = (CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 constexpr int INLINE_KEY = 16;        // key bytes stored inline in a dictionary slot
 

@@ -843,10 +843,12 @@ void dnz_window::prealloc() {
   }
   d_copy_cursor.alloc(64);
   h_small.reserve(CTL_BYTES);
+  // low cardinality: the per-CTA private pane copies (AggParams::priv) are needed by the first launch already
+  if (gcap <= 8192) d_priv.reserve(std::min<size_t>(256ull << 20, (size_t)2 * sm_count * 8 * gcap * sizeof(GroupState)));
   for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
   {   // room for a few windows' worth of rows; grows on demand (one poll is limited to 2 GiB of key bytes by the 32-bit Utf8 offsets)
     // (upper bounds are reserved per emission: windows x group capacity, for every launch in flight and every unconsumed window)
-    const uint64_t rows0 = std::min<uint64_t>((uint64_t)gcap * 24, 96ull << 20);
+    const uint64_t rows0 = std::min<uint64_t>((uint64_t)gcap * 24, 48ull << 20);
     for (wr = 1; wr >= 0; wr--) ensure_result_capacity(rows0, std::min<uint64_t>(rows0 * 16, (1ull << 31) - (1ull << 20)));
     wr = 0;
   }

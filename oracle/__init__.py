@@ -146,6 +146,22 @@ def _rows(res: _Result):
     return out
 
 
+def _arrays(res: _Result) -> dict:
+    """Result set as numpy arrays (copies): key_off[n+1], key_bytes, key_isnull, count, min, max, avg, agg_isnull, window_start,
+    window_end.  For large outputs (millions of rows), where the tuple list of _rows() would take minutes."""
+    n = int(res.n)
+
+    def arr(ptr, dt, m):
+        if m == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(m * np.dtype(dt).itemsize,)).view(dt).copy()
+    off = arr(res.key_off, np.int32, n + 1) if n else np.zeros(1, np.int32)
+    return {"n": n, "key_off": off, "key_bytes": arr(res.key_bytes, np.uint8, int(off[-1])), "key_isnull": arr(res.key_isnull, np.uint8, n),
+            "count": arr(res.count, np.int64, n), "min": arr(res.min, np.float64, n), "max": arr(res.max, np.float64, n),
+            "avg": arr(res.avg, np.float64, n), "agg_isnull": arr(res.agg_isnull, np.uint8, n),
+            "window_start": arr(res.window_start_ms, np.int64, n), "window_end": arr(res.window_end_ms, np.int64, n)}
+
+
 class OracleWindow:
     """Single-partition GroupedWindowAggStream (+ FilterExec) -- the ground truth."""
 
@@ -218,6 +234,17 @@ class OracleMT:
         if clear:
             self._L.orc_mt_clear_results(self._h)
         return rows
+
+    def results_arrays(self, clear=True):
+        """One dict of numpy arrays per partition (see _arrays)."""
+        out = []
+        for p in range(self.partitions):
+            res = _Result()
+            self._L.orc_mt_get_results(self._h, p, C.byref(res))
+            out.append(_arrays(res))
+        if clear:
+            self._L.orc_mt_clear_results(self._h)
+        return out
 
     def clear(self):
         self._L.orc_mt_clear_results(self._h)

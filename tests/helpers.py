@@ -149,3 +149,107 @@ def run_oracle_batches(batches, L, S=0, filt=None):
     for b in batches:
         o.push(b)
     return o.results()
+
+
+# ---------------------------------------------------------------------------------------------
+# large results: sort-free comparison (hash join on (window_start, key)) of column arrays instead of Python row tuples
+def _binary_array(key_off, key_bytes, key_isnull=None):
+    import pyarrow as pa
+    n = len(key_off) - 1
+    off = np.ascontiguousarray(key_off, np.int32)
+    kb = np.ascontiguousarray(key_bytes, np.uint8)
+    if len(kb) == 0:
+        kb = np.zeros(1, np.uint8)
+    arr = pa.Array.from_buffers(pa.binary(), n, [None, pa.py_buffer(off), pa.py_buffer(kb)])
+    if key_isnull is not None and np.any(key_isnull):
+        arr = pa.array([None if key_isnull[i] else arr[i].as_py() for i in range(n)], pa.binary()) if n < 100_000 else \
+            pa.compute.if_else(pa.array(np.asarray(key_isnull, bool)), pa.scalar(None, pa.binary()), arr)
+    return arr
+
+
+def result_table(a, tag):
+    """dict of column arrays (oracle._arrays or fetch_device_result layout) -> pyarrow Table with columns suffixed by `tag`."""
+    import pyarrow as pa
+    n = len(a["count"])
+    if "key_isnull" in a:
+        knull, anull = a["key_isnull"], a["agg_isnull"]
+        ws = a["window_start"]
+    else:
+        knull, anull = (np.asarray(a["key_valid"]) == 0), (np.asarray(a["agg_valid"]) == 0)
+        ws = a["window_start"]
+    key = _binary_array(a["key_off"][: n + 1], a["key_bytes"], knull)
+    anull = np.asarray(anull, bool)
+    return pa.table({"ws": pa.array(np.asarray(ws, np.int64)), "key": key,
+                     "count_" + tag: pa.array(np.asarray(a["count"], np.int64)),
+                     "min_" + tag: pa.array(np.asarray(a["min"], np.float64).view(np.int64)),      # bit patterns: compared exactly
+                     "max_" + tag: pa.array(np.asarray(a["max"], np.float64).view(np.int64)),
+                     "avg_" + tag: pa.array(np.asarray(a["avg"], np.float64)),
+                     "null_" + tag: pa.array(anull)})
+
+
+def assert_tables_equal(got, want, rel=1e-9):
+    """got / want: pyarrow Tables from result_table(.., "g") / (.., "w").  Rows must match one to one on (window_start, key)
+    [valid for in-order streams: every (window, key) is emitted once]; count/min/max bit-exact, avg within `rel`."""
+    assert got.num_rows == want.num_rows, f"row count {got.num_rows} != {want.num_rows}"
+    if got.num_rows == 0:
+        return 0
+    j = got.join(want, keys=["ws", "key"], join_type="inner")
+    assert j.num_rows == got.num_rows, f"only {j.num_rows} of {got.num_rows} (window, key) pairs match"
+    c = {name: j.column(name).to_numpy(zero_copy_only=False) for name in j.column_names if name not in ("ws", "key")}
+    assert np.array_equal(c["count_g"], c["count_w"]), "count differs"
+    assert np.array_equal(c["null_g"], c["null_w"]), "null aggregates differ"
+    ok = ~c["null_w"].astype(bool)
+    assert np.array_equal(c["min_g"][ok], c["min_w"][ok]), "min differs (bit pattern)"
+    assert np.array_equal(c["max_g"][ok], c["max_w"][ok]), "max differs (bit pattern)"
+    ag, aw = c["avg_g"][ok], c["avg_w"][ok]
+    fin = np.isfinite(aw)
+    assert np.all(np.abs(ag[fin] - aw[fin]) <= rel * np.maximum(np.abs(aw[fin]), 1e-300)), "avg differs beyond the tolerance"
+    assert np.array_equal(np.isnan(ag[~fin]), np.isnan(aw[~fin])) and np.array_equal(ag[~fin][~np.isnan(ag[~fin])], aw[~fin][~np.isnan(aw[~fin])])
+    return j.num_rows
+
+
+def concat_arrays(parts):
+    """Concatenate several column-array dicts (e.g. the oracle's partitions, or several polls) into one."""
+    parts = [p for p in parts if len(p["count"])]
+    if not parts:
+        z = np.zeros(0)
+        return {"key_off": np.zeros(1, np.int32), "key_bytes": np.zeros(0, np.uint8), "key_isnull": np.zeros(0, np.uint8), "count": z.astype(np.int64),
+                "min": z, "max": z, "avg": z, "agg_isnull": np.zeros(0, np.uint8), "window_start": z.astype(np.int64)}
+    out = {}
+    offs, base = [np.zeros(1, np.int64)], 0
+    for p in parts:
+        n = len(p["count"])
+        o = np.asarray(p["key_off"][: n + 1], np.int64)
+        offs.append(o[1:] - o[0] + base)
+        base += int(o[-1] - o[0])
+    tot = np.concatenate(offs)
+    assert tot[-1] < 2 ** 31, "concatenated key bytes exceed 2 GiB: compare in pieces"
+    out["key_off"] = tot.astype(np.int32)
+    out["key_bytes"] = np.concatenate([np.asarray(p["key_bytes"], np.uint8)[int(p["key_off"][0]): int(p["key_off"][len(p["count"])])] for p in parts])
+    for k_out, k_a, k_b in [("key_isnull", "key_isnull", "key_valid"), ("agg_isnull", "agg_isnull", "agg_valid")]:
+        out[k_out] = np.concatenate([np.asarray(p[k_a], np.uint8) if k_a in p else (np.asarray(p[k_b]) == 0).astype(np.uint8) for p in parts])
+    for k in ("count", "min", "max", "avg", "window_start"):
+        out[k] = np.concatenate([np.asarray(p[k]) for p in parts])
+    return out
+
+
+def host_stream(n_rows, *, groups, rows_per_ms, uuid_keys=False, batch_rows=65536, seed=42, key_mul=1, key_add=0, threads=None, extra_columns=False):
+    """Batches [0, n_rows) of the synthetic sensor stream, generated with a thread pool (ctypes releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import synth_batch
+    starts = list(range(0, n_rows, batch_rows))
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda r0: synth_batch(r0, min(batch_rows, n_rows - r0), seed=seed, groups=groups, rows_per_ms=rows_per_ms, uuid_keys=uuid_keys,
+                                                  key_mul=key_mul, key_add=key_add, extra_columns=extra_columns), starts))
+
+
+def oracle_mt_arrays(batches, L, S=0, filt=None, partitions=None):
+    """Run the multi-threaded oracle over `batches`; returns one concatenated column-array dict."""
+    import os
+    from oracle import OracleMT
+    m = OracleMT(L, S, filt, partitions=partitions or min(32, os.cpu_count() or 1))
+    m.push_many(batches)
+    parts = m.results_arrays()
+    m.close()
+    return concat_arrays(parts)
