@@ -79,6 +79,14 @@ class PartialsC(C.Structure):
                 ("pane_lo", C.c_int64), ("pane_hi", C.c_int64)]
 
 
+class GroupConfigC(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
+                ("ring_entries", C.c_int64), ("ring_key_bytes", C.c_int64)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
 class StatsC(C.Structure):
     _fields_ = [("rows_in", C.c_int64), ("batches_in", C.c_int64), ("rows_out", C.c_int64), ("windows_emitted", C.c_int64),
                 ("groups", C.c_int64), ("agg_launches", C.c_int64), ("total_launches", C.c_int64),
@@ -96,7 +104,9 @@ EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dn
            "dnz_window_flush", "dnz_window_stats", "dnz_window_reset_stats", "dnz_window_watermark",
            "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_process", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
-           "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free"]
+           "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free",
+           "dnz_group_create", "dnz_group_create_local", "dnz_group_destroy", "dnz_group_attach", "dnz_group_step_begin",
+           "dnz_group_step_pack", "dnz_group_step_finish", "dnz_group_step"]
 
 _lib = None
 
@@ -161,6 +171,19 @@ def lib():
         L.dnz_synth_generate.restype = C.c_int32
         L.dnz_synth_generate.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(DeviceBatchC), C.c_int64]
+        L.dnz_group_create.restype = C.c_int32
+        L.dnz_group_create.argtypes = [C.POINTER(GroupConfigC), ALLGATHER_FN, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.dnz_group_create_local.restype = C.c_int32
+        L.dnz_group_create_local.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        L.dnz_group_destroy.argtypes = [C.c_void_p]
+        L.dnz_group_attach.restype = C.c_int32
+        L.dnz_group_attach.argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("dnz_group_step_begin", "dnz_group_step_pack"):
+            getattr(L, name).restype = C.c_int32
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("dnz_group_step_finish", "dnz_group_step"):
+            getattr(L, name).restype = C.c_int32
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.dnz_synth_bytes.restype = C.c_int64
         L.dnz_synth_bytes.argtypes = [C.c_void_p]
         L.dnz_synth_free.argtypes = [C.c_void_p]
@@ -360,6 +383,84 @@ class GpuStreamingWindow:
     def close(self):
         if getattr(self, "_h", None):
             self._L.dnz_window_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ExchangeGroup:
+    """One rank of the fused pane exchange (dnz_group): the library owns the communicator -- peer mappings of every rank's receive
+    ring (CUDA IPC), remote-atomic reservations, P2P stores over NVLink, flag signalling; see include/dnz_gpu.h.
+
+    ExchangeGroup.create(rank, world, device, allgather)  one rank per process; `allgather(bytes) -> list of bytes` is the
+                                                          rendezvous helper (e.g. torch.distributed), used at creation only
+    ExchangeGroup.create_local(devices)                   all ranks in this process (tests)"""
+
+    def __init__(self, handle, rank, world, keep=None):
+        self._L, self._h, self.rank, self.world, self._keep = lib(), C.c_void_p(handle), rank, world, keep
+
+    @staticmethod
+    def create(rank, world, device, allgather, ring_entries=0, ring_key_bytes=0):
+        L = lib()
+
+        def cb(_ctx, send, recv, nbytes):
+            try:
+                parts = allgather(C.string_at(send, nbytes))
+                C.memmove(recv, b"".join(parts), nbytes * len(parts))
+                return 0
+            except Exception:          # noqa: BLE001 -- reported as a failed rendezvous by the library
+                return 1
+        fn = ALLGATHER_FN(cb)
+        cfg = GroupConfigC(1, rank, world, device, ring_entries, ring_key_bytes)
+        h = C.c_void_p()
+        rc = L.dnz_group_create(C.byref(cfg), fn, None, C.byref(h))
+        if rc != 0:
+            raise DnzError(rc, L.dnz_window_last_error(None).decode())
+        return ExchangeGroup(h.value, rank, world, keep=fn)
+
+    @staticmethod
+    def create_local(devices, ring_entries=0, ring_key_bytes=0):
+        L = lib()
+        n = len(devices)
+        dv = (C.c_int32 * n)(*devices)
+        out = (C.c_void_p * n)()
+        rc = L.dnz_group_create_local(n, dv, ring_entries, ring_key_bytes, out)
+        if rc != 0:
+            raise DnzError(rc, L.dnz_window_last_error(None).decode())
+        return [ExchangeGroup(out[r], r, n) for r in range(n)]
+
+    def _check(self, rc, w):
+        if rc != 0:
+            raise DnzError(rc, self._L.dnz_window_last_error(w._h).decode())
+
+    def attach(self, w: GpuStreamingWindow):
+        self._check(self._L.dnz_group_attach(self._h, w._h), w)
+        w._world = self.world
+
+    def step_begin(self, w):
+        self._check(self._L.dnz_group_step_begin(self._h, w._h), w)
+
+    def step_pack(self, w):
+        self._check(self._L.dnz_group_step_pack(self._h, w._h), w)
+
+    def step_finish(self, w):
+        v = C.c_int64(0)
+        self._check(self._L.dnz_group_step_finish(self._h, w._h, C.byref(v)), w)
+        return None if v.value == -(2 ** 63) else v.value
+
+    def step(self, w):
+        """One collective exchange step; returns the global watermark (None before every rank has one)."""
+        v = C.c_int64(0)
+        self._check(self._L.dnz_group_step(self._h, w._h, C.byref(v)), w)
+        return None if v.value == -(2 ** 63) else v.value
+
+    def close(self):
+        if self._h:
+            self._L.dnz_group_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -76,4 +76,119 @@ cudaError_t launch_merge_partials(const MergeParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+
+// =================================================================================================
+// Fused pane exchange over peer memory (NVLink / NVSwitch): no host copy and no library collective in the data path.
+//
+// Every rank owns a RECEIVE region in its HBM (mapped into every peer with CUDA IPC): a cursor block, a ring of 64 B packets
+// and a ring of key bytes, each split into two halves (step parity).  One exchange step of a rank, all on its own stream:
+//
+//   [wait: owners have merged step-2]      interprocess CUDA events, no spinning kernel
+//   k_pack_partials (pass 0)   per-owner packet / key-byte counts of the panes that closed under the global watermark
+//   k_xchg_reserve             one thread per owner: reserve the counted range in the OWNER'S ring with one remote atomicAdd
+//   k_pack_write_peer          write the packets and their key bytes straight into the owners' rings with P2P stores
+//   [record: my packets of this step are written]  /  [wait: every peer's packets are written]
+//   k_merge_ring               intern unknown keys, merge the received partial states into the owner's panes
+//   [reset the ring half; record: merged]
+//   k_emit ...                 the owner emits the closed windows of ITS keys
+// =================================================================================================
+__global__ void k_xchg_reserve(XchgView X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total) {
+  const int o = threadIdx.x;
+  if (o >= X.world || o == X.rank) return;
+  const unsigned long long c = owner_cursor[o];
+  unsigned long long base = 0;
+  if (c) {
+    base = atomicAdd_system(&X.peer[o].ctl->cursor[X.step & 1], c);
+    if ((base >> 32) + (c >> 32) > X.ring_entries || (base & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) > X.ring_key_bytes) {
+      atomicOr(&X.self.ctl->error, 1u);          // the owner's ring is too small for this step: nothing of it is written
+      base = ~0ull;
+    }
+  }
+  owner_base[o] = base;
+  owner_cursor[o] = 0ull;
+  atomicAdd(sent_total, c >> 32);
+}
+cudaError_t launch_xchg_reserve(const XchgView& X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total, cudaStream_t s) {
+  k_xchg_reserve<<<1, MAX_WORLD, 0, s>>>(X, owner_cursor, owner_base, sent_total);
+  return cudaGetLastError();
+}
+
+// pass 1 of the fused path: like k_pack_partials' write pass, but the destination is the owner's ring and key_off is absolute
+__global__ void __launch_bounds__(256) k_pack_write_peer(const __grid_constant__ PackParams P, const __grid_constant__ XchgView X, const unsigned long long* __restrict__ owner_base) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.n_groups) return;
+  const GroupState s = P.st[g];
+  const unsigned long long nr = P.nullrows ? P.nullrows[g] : 0ull;
+  if (s.cnt == 0.0 && nr == 0ull) return;
+  const GidKey gk = P.dict.gid_key[g];
+  const bool null_key = gk.len == 0xFFFFFFFFu;
+  const uint32_t klen = null_key ? 0u : gk.len;
+  const int owner = null_key ? 0 : (int)((klen <= (uint32_t)INLINE_KEY ? hash_inline(gk.k0, gk.k1, klen) : gk.k0) % (uint64_t)P.world);
+  if (owner == P.rank) return;
+  const unsigned long long base = owner_base[owner];
+  if (base == ~0ull) return;
+  const uint32_t kpad = (klen + 7u) & ~7u;
+  const unsigned long long c = atomicAdd(P.owner_cursor + owner, (1ull << 32) | kpad);
+  const uint64_t row = (base >> 32) + (c >> 32);
+  const uint64_t boff = (base & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull);      // inside the owner's key half
+  PartialEntry e;
+  e.pane = P.pane; e.cnt = (unsigned long long)s.cnt; e.sum = s.sum; e.minkey = s.minkey; e.maxkey = s.maxkey;
+  e.nullrows = nr; e.fz = P.fz ? P.fz[g] : ~0ull;
+  e.key_off = (uint32_t)boff; e.key_len = null_key ? 0xFFFFFFFFu : klen;
+  const int half = (int)(X.step & 1);
+  X.peer[owner].entries[(uint64_t)half * X.ring_entries + row] = e;
+  if (!null_key) {
+    uint8_t* dst = X.peer[owner].keys + (uint64_t)half * X.ring_key_bytes + boff;
+    if (klen <= (uint32_t)INLINE_KEY) {
+      const uint64_t w[2] = {gk.k0, gk.k1};
+      for (uint32_t i = 0; i < kpad; i += 8) *reinterpret_cast<uint64_t*>(dst + i) = w[i >> 3];     // 8 B aligned: key ranges are padded to 8
+    } else {
+      const uint8_t* src = P.dict.arena + gk.k1;                                                    // arena entries are 8 B aligned and padded
+      for (uint32_t i = 0; i < kpad; i += 8) *reinterpret_cast<uint64_t*>(dst + i) = *reinterpret_cast<const uint64_t*>(src + i);
+    }
+  }
+}
+cudaError_t launch_pack_write_peer(const PackParams& p, const XchgView& X, const unsigned long long* owner_base, cudaStream_t s) {
+  if (!p.n_groups) return cudaSuccess;
+  k_pack_write_peer<<<(p.n_groups + 255) / 256, 256, 0, s>>>(p, X, owner_base);
+  return cudaGetLastError();
+}
+
+// merge everything the peers wrote into this rank's ring half of the step: grid-stride, the packet count is read on the device
+__global__ void __launch_bounds__(256) k_merge_ring(const __grid_constant__ MergeParams P, const __grid_constant__ XchgView X, unsigned long long* merged_total) {
+  const int half = (int)(X.step & 1);
+  const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&X.self.ctl->cursor[half]);
+  const uint64_t n = cur >> 32;
+  const PartialEntry* ring = X.self.entries + (uint64_t)half * X.ring_entries;
+  const uint8_t* keys = X.self.keys + (uint64_t)half * X.ring_key_bytes;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(merged_total, n);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    PartialEntry e;
+    {   // packets were written by peers while this kernel may already have been resident: bypass L1
+      const uint4* p4 = reinterpret_cast<const uint4*>(ring + i);
+      uint4 a = __ldcg(p4), b = __ldcg(p4 + 1), c = __ldcg(p4 + 2), d = __ldcg(p4 + 3);
+      memcpy(&e, &a, 16); memcpy(reinterpret_cast<char*>(&e) + 16, &b, 16); memcpy(reinterpret_cast<char*>(&e) + 32, &c, 16); memcpy(reinterpret_cast<char*>(&e) + 48, &d, 16);
+    }
+    uint32_t gid;
+    if (e.key_len == 0xFFFFFFFFu) gid = dict_lookup_null(P.dict);
+    else {
+      KeyRef k; load_key<false>(keys + e.key_off, e.key_len, k);
+      gid = dict_lookup(P.dict, k, false);
+    }
+    const int64_t pi = e.pane - P.panes.pane0;
+    if (gid >= GID_DEFER_ARENA || pi < 0 || pi >= P.panes.n_panes || P.panes.main[pi] == nullptr) { atomicOr(P.error, 1u); continue; }
+    GroupState* s = P.panes.main[pi] + gid;
+    if (e.cnt) {
+      red_add_f64(&s->cnt, (double)e.cnt); red_add_f64(&s->sum, e.sum);
+      red_max_u64(&s->minkey, e.minkey); red_max_u64(&s->maxkey, e.maxkey);
+    }
+    if (e.nullrows) { if (P.panes.nullrows_main[pi]) red_add_u64(P.panes.nullrows_main[pi] + gid, e.nullrows); else atomicOr(P.error, 2u); }
+    if (e.fz != ~0ull) { if (P.panes.fz_main[pi]) red_min_u64(P.panes.fz_main[pi] + gid, e.fz); else atomicOr(P.error, 4u); }
+  }
+}
+cudaError_t launch_merge_ring(const MergeParams& p, const XchgView& X, unsigned long long* merged_total, int sm_count, cudaStream_t s) {
+  k_merge_ring<<<sm_count * 4, 256, 0, s>>>(p, X, merged_total);
+  return cudaGetLastError();
+}
+
 }  // namespace dnz

@@ -359,7 +359,7 @@ __device__ __noinline__ uint32_t agg_queue_round(const AggParams& P, WarpQueue& 
   return base + __popc(bal);
 }
 
-__global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P) {
+__global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_constant__ AggParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   AggSmem& S = *reinterpret_cast<AggSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -445,13 +445,7 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
     return;
   }
 
-  // -------------------------------------------------------------- consumer warps: one row per thread, two tiles in flight
-  // Software pipeline over the tiles of the ring.  Phase A of tile t+1 (wait for the stage, build the row's key words, hash,
-  // ISSUE the dictionary probe) runs before phase B of tile t (compare the probed slot, hints, reductions), so a warp never
-  // waits for the L2 round trip of its own probe: by the time B(t) looks at the slot, A(t+1) -- some hundred instructions -- and
-  // the other warps have been issued in between.  Carried from A to B per thread: the four key words, length + flags, the slot
-  // index and the 32 B slot; everything else (value, header) is read from the stage again, which stays allocated until B(t) has
-  // finished.
+  // -------------------------------------------------------------- consumer warps: one row per thread
   const DictSlot* const slots = P.dict.slots;
   const uint32_t dmask = P.dict.mask;
   // hints are switched off together with the private pane copies (low cardinality): the copies make every reduction cheap, and
@@ -459,48 +453,16 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
   // partitions (ncu on cfg 1: 57 % of the samples waiting for the probe, LSU pipe 6 % busy)
   const bool use_hints = !(P.flags & AGG_NO_HINTS) && P.priv == nullptr, use_queue = !(P.flags & AGG_NO_QUEUE);
   uint32_t qcount = 0;                 // warp-uniform
-  struct Pend { uint32_t w0, w1, w2, w3, meta, idx; uint64_t sa, sb, sc, sd; };
-  constexpr uint32_t M_LIVE = 1u << 8, M_SLOW = 1u << 9, M_PROBED = 1u << 10, M_END = 1u << 11;
-
-  auto phase_a = [&](uint32_t it, Pend& p) {
+  for (uint32_t it = 0;; it++) {
     const int s = it % STAGES;
     mbar_wait(&S.full[s], (it / STAGES) & 1u);
     const Stage& st = S.st[s];
-    const int4 h0 = *reinterpret_cast<const int4*>(&st.hdr.n_rows);            // n_rows, flags, a0, tag
-    p.meta = 0u;
-    if (h0.y & TILE_END) { p.meta = M_END; return; }
-    if (!(h0.y & TILE_FAST)) return;
-    uint32_t tix = (uint32_t)tid; asm volatile("" : "+r"(tix));
-    const uint32_t r = tix;
-    const bool live = r < (uint32_t)h0.x;
-    const int32_t o0 = st.off[r], o1 = st.off[r + 1];
-    const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - h0.z) : 0u;
-    const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, mis = addr & 3u, sh = mis * 8u;
-    uint32_t a[5];
-#pragma unroll
-    for (int j = 0; j < 4; j++) a[j] = lds32(q + 4u * j);
-    a[4] = (mis + klen > 16u) ? lds32(q + 16u) : 0u;                    // a 5th word only when the key straddles it
-    // byte mask of word i of a klen-byte key: 0xFFFFFFFF >> clamp(32 - 8 * (klen - 4 i), 0, 32)  (shf.r.clamp saturates at 32)
-    const int mb = 32 - 8 * (int)min(klen, (uint32_t)INLINE_KEY);
-    p.w0 = __funnelshift_r(a[0], a[1], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb, 0));
-    p.w1 = __funnelshift_r(a[1], a[2], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 32, 0));
-    p.w2 = __funnelshift_r(a[2], a[3], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 64, 0));
-    p.w3 = __funnelshift_r(a[3], a[4], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 96, 0));
-    p.idx = hash_words(p.w0, p.w1, p.w2, p.w3, klen) & dmask;
-    const bool slow = live && klen > (uint32_t)INLINE_KEY;
-    p.meta = (klen & 0xFFu) | (live ? M_LIVE : 0u) | (slow ? M_SLOW : 0u) | M_PROBED;
-    // ONE dictionary probe (32 B sector, carries the group's min/max hint)
-    if (live && !slow) ld_slot(slots + p.idx, p.sa, p.sb, p.sc, p.sd);
-  };
-
-  auto phase_b = [&](uint32_t it, const Pend& p) {
-    const int s = it % STAGES;
-    const Stage& st = S.st[s];
     const StageHdr& H = st.hdr;
     const int4 h0 = *reinterpret_cast<const int4*>(&H.n_rows);            // n_rows, flags, a0, tag
+    if (h0.y & TILE_END) break;
     // Everything derived from the thread index is recomputed per tile behind an opaque barrier: hoisted out of the loop
-    // these values (lane masks, shuffle sources, queue address) cost registers the budget does not have, and a spill is a
-    // local-memory access that queues behind the scattered traffic in the L1TEX FIFO.
+    // these values (lane masks, shuffle sources, queue address) cost registers the 64-register budget does not have, and
+    // a spill is a local-memory access that queues behind the scattered traffic in the L1TEX FIFO.
     uint32_t tix = (uint32_t)tid; asm volatile("" : "+r"(tix));
     const int lane = (int)(tix & 31u), odd = (int)(tix & 1u);
     WarpQueue& Q = S.q[tix >> 5];
@@ -509,21 +471,36 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
     } else {
       const uint4 h1 = *reinterpret_cast<const uint4*>(&H.mbase);         // mbase, tile_rel, pane_rel
       const uint32_t r = tix;
-      const bool live = (p.meta & M_LIVE) != 0u;
-      const uint32_t klen = p.meta & 0xFFu;
+      const bool live = r < (uint32_t)h0.x;
       GroupState* const mbase = reinterpret_cast<GroupState*>(((uint64_t)h1.y << 32) | h1.x);
       const double v = st.val[r];
-      uint32_t idx = p.idx;
+      const int32_t o0 = st.off[r], o1 = st.off[r + 1];
+      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - h0.z) : 0u;
+      const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, mis = addr & 3u, sh = mis * 8u;
+      uint32_t a[5];
+#pragma unroll
+      for (int j = 0; j < 4; j++) a[j] = lds32(q + 4u * j);
+      a[4] = (mis + klen > 16u) ? lds32(q + 16u) : 0u;                    // a 5th word only when the key straddles it
+      // byte mask of word i of a klen-byte key: 0xFFFFFFFF >> clamp(32 - 8 * (klen - 4 i), 0, 32)  (shf.r.clamp saturates at 32)
+      const int mb = 32 - 8 * (int)min(klen, (uint32_t)INLINE_KEY);
+      const uint32_t w0 = __funnelshift_r(a[0], a[1], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb, 0));
+      const uint32_t w1 = __funnelshift_r(a[1], a[2], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 32, 0));
+      const uint32_t w2 = __funnelshift_r(a[2], a[3], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 64, 0));
+      const uint32_t w3 = __funnelshift_r(a[3], a[4], sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(mb + 96, 0));
+      uint32_t idx = hash_words(w0, w1, w2, w3, klen) & dmask;
       // paired-path row: finite and not +-0.0 (everything else goes through the general per-row path)
       const uint32_t bhi = (uint32_t)__double2hiint(v), blo = (uint32_t)__double2loint(v);
       const bool plain = mbase != nullptr && (bhi & 0x7FF00000u) != 0x7FF00000u && ((bhi << 1) | blo) != 0u;
       uint32_t gid = 0; uint64_t hint = 0;
-      bool need_slow = (p.meta & M_SLOW) != 0u, park = false, hit = false;
+      bool need_slow = live && klen > (uint32_t)INLINE_KEY, park = false, hit = false;
+      // ONE dictionary probe (32 B sector, carries the group's min/max hint)
       if (live && !need_slow) {
-        const uint32_t state = (uint32_t)(p.sd >> 32);
+        uint64_t sa, sb, sc, sd;
+        ld_slot(slots + idx, sa, sb, sc, sd);
+        const uint32_t state = (uint32_t)(sd >> 32);
         if (state - 1u < 0xFFFFFFFEu) {                   // occupied and published
-          if ((uint32_t)p.sd == klen && (uint32_t)p.sa == p.w0 && (uint32_t)(p.sa >> 32) == p.w1 && (uint32_t)p.sb == p.w2 && (uint32_t)(p.sb >> 32) == p.w3) {
-            gid = state - 1u; hint = p.sc; hit = true;
+          if ((uint32_t)sd == klen && (uint32_t)sa == w0 && (uint32_t)(sa >> 32) == w1 && (uint32_t)sb == w2 && (uint32_t)(sb >> 32) == w3) {
+            gid = state - 1u; hint = sc; hit = true;
           } else if (use_queue && plain) { idx = (idx + 1u) & dmask; park = true; }   // chain continues: park, re-probe 32 at a time
           else need_slow = true;
         } else need_slow = true;                          // empty (insert) or locked (insert in flight)
@@ -532,18 +509,14 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
       if (bal) {
         if (park) {
           const uint32_t pos = qcount + __popc(bal & ((1u << lane) - 1u));
-          Q.key[pos] = make_uint4(p.w0, p.w1, p.w2, p.w3);
+          Q.key[pos] = make_uint4(w0, w1, w2, w3);
           Q.meta[pos] = make_uint2(idx, klen | (h1.w << 8));
           Q.val[pos] = v;
           Q.row[pos] = (h1.z << 10) | r;
         }
         qcount += __popc(bal);
       }
-      if (need_slow) {
-        const int32_t o0 = st.off[r], o1 = st.off[r + 1];
-        const uint64_t gs = agg_probe_slow(P, st.bytes + (uint32_t)(o0 - h0.z), (uint32_t)(o1 - o0));
-        gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true;
-      }
+      if (need_slow) { const uint64_t gs = agg_probe_slow(P, st.bytes + kb, klen); gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true; }
       uint32_t pk = 0;
       if (hit) {
         if (gid >= GID_DEFER_ARENA) defer_row(P.defer, h1.z, r, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
@@ -559,7 +532,9 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
           // the OLDER pane (smaller tag; tags live in [1, 2^31)) never replaces the newer pane's hint -- it just reduces
           if (use_hints && (int32_t)(htag - tag) <= 0 && (tmin > hmin || tmax > hmax))
             st_relaxed_u64(const_cast<uint64_t*>(&slots[idx].hint), ((uint64_t)tag << 32) | ((uint64_t)max(hmin, tmin) << 16) | (uint64_t)max(hmax, tmax));
-          // min / max: the hint lets ~7 % of the rows through; they are reduced here, by the row's own lane
+          // min / max: the hint lets ~7 % of the rows through; they are reduced here, by the row's own lane.  (Parking them in a
+          // per-warp queue and reducing 32 at a time was tried in round 2: 0.96 ms instead of 0.92 ms per launch -- the queue
+          // bookkeeping costs more than the sparse instructions it saves.)
           const uint32_t olo = (bhi & 0x80000000u) ? ~blo : blo;
           if (tmin >= hmin) red_max_u64(&mbase[gid].minkey, ((unsigned long long)(0xFFEFFFFFu - ohi) << 32) | (uint32_t)~olo);
           if (tmax >= hmax) red_max_u64(&mbase[gid].maxkey, ((unsigned long long)(ohi - 0x00100000u) << 32) | olo);
@@ -577,9 +552,9 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           const bool own = (odd == half);
-          const uint32_t pp = own ? pk : pk2;
-          if (pp & (1u << 29)) {
-            GroupState* s2 = mbase + (pp & 0x1FFFFFFFu);
+          const uint32_t p = own ? pk : pk2;
+          if (p & (1u << 29)) {
+            GroupState* s2 = mbase + (p & 0x1FFFFFFFu);
             red_add_f64(own ? &s2->sum : &s2->cnt, own ? v : 1.0);
           }
         }
@@ -588,17 +563,6 @@ __global__ void __maxnreg__(96) k_aggregate(const __grid_constant__ AggParams P)
     __syncwarp();
     if (lane == 0) mbar_arrive_relaxed(&S.empty[s]);
     while (qcount >= 32u) qcount = agg_queue_round(P, Q, qcount, lane, use_hints);
-  };
-
-  Pend pa, pb;
-  phase_a(0u, pa);
-  for (uint32_t it = 0;; it += 2) {                 // unrolled by two: the carried state ping-pongs between pa and pb without moves
-    if (pa.meta & M_END) break;
-    phase_a(it + 1u, pb);
-    phase_b(it, pa);
-    if (pb.meta & M_END) break;
-    phase_a(it + 2u, pa);
-    phase_b(it + 1u, pb);
   }
   while (qcount > 0u) qcount = agg_queue_round(P, S.q[warp], qcount, lane, use_hints);
 }

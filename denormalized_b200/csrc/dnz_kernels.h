@@ -7,10 +7,10 @@ namespace dnz {
 
 // ------------------------------------------------------------------------------------------------
 // Tiling of the input.  One tile = up to TILE consecutive rows of ONE RecordBatch.
-constexpr int TILE = 288;             // rows per tile = consumer threads of one CTA (a multiple of 4: 16 B aligned column slices)
-constexpr int STAGES = 5;             // TMA ring depth per CTA (the consumers hold two stages: the tile being probed and the one being reduced)
-constexpr int BCAP = 4608;            // staged key bytes per tile (16 B/row average); longer tiles take the generic path (a 16 KB budget with 3 stages was tried: cfg 2 -1.5 %, cfg 5 no gain)
-constexpr int CONSUMER_WARPS = 9;    // 416 consumer threads x 1 row = TILE; + 1 producer warp = 448 threads; two CTAs per SM at 72 registers (no spills)
+constexpr int TILE = 416;             // rows per tile = consumer threads of one CTA (a multiple of 4: 16 B aligned column slices)
+constexpr int STAGES = 4;             // TMA ring depth per CTA
+constexpr int BCAP = 6656;            // staged key bytes per tile (16 B/row average); longer tiles take the generic path (a 16 KB budget with 3 stages was tried: cfg 2 -1.5 %, cfg 5 no gain)
+constexpr int CONSUMER_WARPS = 13;   // 416 consumer threads x 1 row = TILE; + 1 producer warp = 448 threads; two CTAs per SM at 72 registers (no spills)
 constexpr int AGG_THREADS = (CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 constexpr int INLINE_KEY = 16;        // key bytes stored inline in a dictionary slot
 
@@ -144,7 +144,7 @@ struct __align__(16) PartialEntry {
   uint32_t key_off, key_len;     // bytes at key_off inside the sender's key segment FOR THIS OWNER; key_len == 0xFFFFFFFF: NULL key
 };
 static_assert(sizeof(PartialEntry) == 64, "packet size");
-constexpr int MAX_WORLD = 64;
+constexpr int MAX_WORLD = 32;
 struct PackParams {
   const GroupState* st; const unsigned long long* nullrows; const unsigned long long* fz;   // one pane
   int64_t pane; uint32_t n_groups; int32_t rank, world;
@@ -181,6 +181,22 @@ cudaError_t agg_kernel_setup();
 // exchange (multi-GPU, dnz_exchange.cu)
 cudaError_t launch_pack_partials(const PackParams& p, cudaStream_t s);
 cudaError_t launch_merge_partials(const MergeParams& p, cudaStream_t s);
+
+// fused exchange over peer memory: a rank's receive region (device memory of that rank, mapped into every peer)
+struct XchgCtl {
+  unsigned long long cursor[2];               // per ring half: (packets << 32) | key bytes reserved so far (remote atomicAdd by the senders)
+  unsigned int error; unsigned int pad;
+};
+struct XchgRegion { XchgCtl* ctl; PartialEntry* entries; uint8_t* keys; };      // entries: 2 x ring_entries, keys: 2 x ring_key_bytes
+struct XchgView {
+  XchgRegion self; XchgRegion peer[MAX_WORLD];
+  uint64_t ring_entries, ring_key_bytes;
+  unsigned long long step;                    // 1, 2, ... (same on every rank)
+  int32_t rank, world;
+};
+cudaError_t launch_xchg_reserve(const XchgView& X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total, cudaStream_t s);
+cudaError_t launch_pack_write_peer(const PackParams& p, const XchgView& X, const unsigned long long* owner_base, cudaStream_t s);
+cudaError_t launch_merge_ring(const MergeParams& p, const XchgView& X, unsigned long long* merged_total, int sm_count, cudaStream_t s);
 
 // Arrow<->device buffer manager: one launch pulls every pinned host buffer of a superbatch over PCIe with 128-bit loads
 // (hundreds of 0.5 MiB cudaMemcpyAsync calls reach only ~25 GB/s on this platform; see profiles/h2d_probe.py)

@@ -230,6 +230,7 @@ constexpr size_t CTL_BYTES = 256, CTL_MERGE_ERR = 224;
 
 }  // namespace
 
+struct dnz_group;
 struct dnz_window {
   dnz_window_config cfg{};
   std::vector<dnz_agg> aggs; std::vector<std::string> aliases;
@@ -287,6 +288,9 @@ struct dnz_window {
   int64_t exported_pane_upto = INT64_MIN;
   DevBuf d_part_entries, d_part_keys, d_owner_cursor, d_xptrs; PinnedBuf h_xptrs;
   std::vector<int64_t> h_owner_counts, h_owner_bytes;
+  void group_begin(struct dnz_group* g);
+  void group_pack(struct dnz_group* g);
+  void group_finish(struct dnz_group* g, int64_t* gwm_out);
   void export_partials(int64_t watermark, dnz_partials* out);
   void import_partials(const uint8_t* entries, const int64_t* src_counts, const uint8_t* key_bytes, const int64_t* src_key_bytes,
                        int64_t pane_lo, int64_t pane_hi);
@@ -589,6 +593,7 @@ void dnz_window::fetch_ctl() {
 }
 // upper bounds of the device counters given what has been enqueued since the host last saw them
 uint32_t dnz_window::groups_bound() const {
+  if (world > 1) return gcap;      // the owner's merge interns keys the host has not seen
   return (uint32_t)std::min<uint64_t>(gcap, (uint64_t)n_groups_host + (uint64_t)std::max<int64_t>(rows_since_known, 0) + 1);   // + the NULL key
 }
 uint64_t dnz_window::key_bytes_bound() const {
@@ -842,9 +847,9 @@ void dnz_window::prealloc() {
     s.d_defer[0].reserve((size_t)std::max<int64_t>(max_rows, 1) * sizeof(DeferEntry));
   }
   d_copy_cursor.alloc(64);
-  h_small.reserve(CTL_BYTES);
+  h_small.reserve(CTL_BYTES + 64);
   // low cardinality: the per-CTA private pane copies (AggParams::priv) are needed by the first launch already
-  if (gcap <= 8192) d_priv.reserve(std::min<size_t>(256ull << 20, (size_t)2 * sm_count * 8 * gcap * sizeof(GroupState)));
+  if (gcap <= 8192) d_priv.reserve(256ull << 20);
   for (int i = 0; i < std::max(panes_per_window + 2, 8) && i < 16; i++) pane_pool.push_back(new_pane(0));
   {   // room for a few windows' worth of rows; grows on demand (one poll is limited to 2 GiB of key bytes by the 32-bit Utf8 offsets)
     // (upper bounds are reserved per emission: windows x group capacity, for every launch in flight and every unconsumed window)
@@ -1677,7 +1682,12 @@ int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
   if (world > MAX_WORLD) fail(DNZ_ERR_UNSUPPORTED, "world > %d", MAX_WORLD);
   if (w->stats.rows_in > 0 && world != w->world) fail(DNZ_ERR_INVALID, "set_exchange must precede the first batch");
   w->rank = rank; w->world = world;
-  if (world > 1) { w->need_nullrows = true; w->need_fz = true; for (auto& kv : w->panes) w->ensure_side_arrays(kv.second.get()); }
+  if (world > 1) {
+    w->need_nullrows = true; w->need_fz = true; for (auto& kv : w->panes) w->ensure_side_arrays(kv.second.get());
+    // staging of the merge's pane table for the largest pane range of one step: page-locked allocations synchronise the device,
+    // which must not happen while a peer rank of the same process spins in a wait kernel (dnz_group, local groups)
+    w->h_xptrs.reserve((size_t)7 * (1 << 16) * sizeof(void*)); w->d_xptrs.reserve((size_t)7 * (1 << 16) * sizeof(void*));
+  }
   DNZ_CATCH(w)
 }
 int32_t dnz_window_reserve_input(dnz_window* w, int64_t bytes_per_launch) {
@@ -1778,6 +1788,359 @@ void dnz_synth_free(dnz_synth* a) {
   cudaSetDevice(a->dev);
   cudaFree(a->ts); cudaFree(a->val); cudaFree(a->off); cudaFree(a->bytes);
   delete a;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// dnz_group: the library-owned communicator of the fused pane exchange (SURVEY.md §8b "dnz_group_create"; §8e).
+// One rank per GPU.  Multi-process groups (one process per GPU, the production shape) map every rank's receive region into every
+// peer with CUDA IPC, order the streams of different ranks with INTERPROCESS CUDA EVENTS (no kernel ever spins) and exchange the
+// per-step host scalars (local watermark, first pane) through a POSIX shared-memory block; the rendezvous needs two all-gathers
+// of a few hundred bytes at creation, which the host application supplies as a callback (the role the ncclUniqueId broadcast
+// plays for NCCL).  Local groups put all ranks into one process (tests; several GPUs driven by one process): same kernels,
+// same protocol, plain events.
+// =================================================================================================
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
+
+namespace {
+struct HostCtl {          // shared by all ranks (POSIX shm or heap); two slots by step parity
+  std::atomic<int64_t> arrived[2][MAX_WORLD];     // phase 1: the local watermark of the step is published
+  std::atomic<int64_t> packed[2][MAX_WORLD];      // phase 2: the "my packets are written" event of the step is recorded
+  std::atomic<int64_t> lwm[2][MAX_WORLD];
+  std::atomic<int64_t> first_pane[2][MAX_WORLD];
+  std::atomic<int32_t> failed;
+};
+struct GroupShared { HostCtl ctl; };
+}  // namespace
+
+struct dnz_group {
+  int rank = 0, world = 1, dev = 0;
+  uint64_t ring_entries = 0, ring_key_bytes = 0;
+  size_t region_bytes = 0;
+  void* region = nullptr;                       // this rank's receive region (cudaMalloc: IPC-exportable)
+  std::vector<void*> peer_base;                 // mapped peers (nullptr for self)
+  bool ipc = false;
+  HostCtl* hctl = nullptr; size_t shm_bytes = 0; std::string shm_name; bool shm_owner = false;
+  std::shared_ptr<GroupShared> local_shared;
+  // ev_packed[r][p] / ev_merged[r][p]: rank r's events of step parity p (own rank: created here; peers: opened / shared)
+  cudaEvent_t ev_packed[MAX_WORLD][2] = {}, ev_merged[MAX_WORLD][2] = {};
+  XchgView view{};
+  unsigned long long step = 0;
+  DevBuf d_owner_cursor, d_owner_base, d_totals;   // totals: [0] packets sent, [1] packets merged
+  int phase = 0;                                 // 0 idle, 1 begun, 2 packed
+  int64_t my_lwm = INT64_MIN, my_first = INT64_MAX, gwm = INT64_MIN, gfirst = INT64_MAX;
+
+  static XchgRegion carve(void* base, uint64_t ring_entries) {
+    XchgRegion r;
+    char* p = static_cast<char*>(base);
+    r.ctl = reinterpret_cast<XchgCtl*>(p);
+    r.entries = reinterpret_cast<PartialEntry*>(p + 4096);
+    r.keys = reinterpret_cast<uint8_t*>(p + 4096 + 2 * ring_entries * sizeof(PartialEntry));
+    return r;
+  }
+  ~dnz_group() {
+    cudaSetDevice(dev);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < 2; p++) { if (ev_packed[rank][p]) cudaEventDestroy(ev_packed[rank][p]); if (ev_merged[rank][p]) cudaEventDestroy(ev_merged[rank][p]); }
+    if (ipc) {
+      for (int r = 0; r < world; r++) if (r != rank) for (int p = 0; p < 2; p++) { if (ev_packed[r][p]) cudaEventDestroy(ev_packed[r][p]); if (ev_merged[r][p]) cudaEventDestroy(ev_merged[r][p]); }
+      for (size_t r = 0; r < peer_base.size(); r++) if (peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+    }
+    if (region) cudaFree(region);
+    if (hctl && !local_shared) { munmap(hctl, shm_bytes); if (shm_owner) shm_unlink(shm_name.c_str()); }
+  }
+};
+
+namespace {
+
+void group_alloc_region(dnz_group* g, unsigned event_flags) {
+  if (g->ring_entries < 1024) g->ring_entries = 1024;
+  if (g->ring_key_bytes < 65536) g->ring_key_bytes = 65536;
+  g->ring_key_bytes = round_up(g->ring_key_bytes, 256);
+  if (g->ring_entries >= (1ull << 31) || g->ring_key_bytes >= (1ull << 31)) fail(DNZ_ERR_INVALID, "exchange ring larger than 2^31 packets / key bytes per step");
+  g->region_bytes = 4096 + 2 * g->ring_entries * sizeof(PartialEntry) + 2 * g->ring_key_bytes;
+  CK(cudaSetDevice(g->dev));
+  CK(cudaMalloc(&g->region, g->region_bytes));
+  CK(cudaMemset(g->region, 0, 4096));
+  g->d_owner_cursor.alloc(MAX_WORLD * 8); g->d_owner_base.alloc(MAX_WORLD * 8); g->d_totals.alloc(64);
+  CK(cudaMemset(g->d_totals.p, 0, 64));
+  for (int p = 0; p < 2; p++) {
+    CK(cudaEventCreateWithFlags(&g->ev_packed[g->rank][p], cudaEventDisableTiming | event_flags));
+    CK(cudaEventCreateWithFlags(&g->ev_merged[g->rank][p], cudaEventDisableTiming | event_flags));
+  }
+  CK(cudaDeviceSynchronize());
+}
+
+void group_finish_view(dnz_group* g) {
+  XchgView& v = g->view;
+  memset(&v, 0, sizeof v);
+  v.rank = g->rank; v.world = g->world; v.ring_entries = g->ring_entries; v.ring_key_bytes = g->ring_key_bytes;
+  v.self = dnz_group::carve(g->region, g->ring_entries);
+  for (int r = 0; r < g->world; r++) v.peer[r] = dnz_group::carve(r == g->rank ? g->region : g->peer_base[(size_t)r], g->ring_entries);
+}
+
+// host barrier on one of the per-step counters.  A process that drives all ranks itself must call the phases in order for
+// ALL ranks (begin x world, pack x world, finish x world): waiting would never end there, so it is an error instead.
+void group_wait(dnz_group* g, std::atomic<int64_t> (*ctr)[MAX_WORLD], unsigned long long step, const char* what) {
+  const int s = (int)(step & 1);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < g->world; r++) {
+    int spins = 0;
+    while (ctr[s][r].load(std::memory_order_acquire) != (int64_t)step) {
+      if (g->local_shared) fail(DNZ_ERR_INVALID, "exchange group: rank %d has not reached '%s' of step %llu (a process driving several ranks calls each phase for all ranks before the next phase)", r, what, step);
+      if (g->hctl->failed.load(std::memory_order_relaxed)) fail(DNZ_ERR_INVALID, "exchange group: another rank failed or left");
+      if (++spins > 2000) {
+        usleep(50);
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(300)) fail(DNZ_ERR_INVALID, "exchange group: rank %d did not reach '%s' of step %llu within 300 s", r, what, step);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ---- phase 1: aggregate what is queued, publish the local watermark of the step
+void dnz_window::group_begin(dnz_group* g) {
+  if (world != g->world || rank != g->rank) fail(DNZ_ERR_INVALID, "operator is not attached to this group");
+  if (g->phase != 0) fail(DNZ_ERR_INVALID, "dnz_group_step_begin: the previous step of this rank is not finished");
+  process_pending(); drain();
+  fetch_ctl();
+  if (*reinterpret_cast<const uint32_t*>(h_small.as<char>() + CTL_MERGE_ERR)) fail(DNZ_ERR_NOMEM, "pane merge failed: the dictionary / key arena of this rank is too small for the keys it owns (in exchange mode expected_groups must cover the GLOBAL key set)");
+  {
+    h_small.reserve(CTL_BYTES + 64);
+    char* hb = h_small.as<char>() + CTL_BYTES;
+    CK(cudaMemcpyAsync(hb, &g->view.self.ctl->error, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hb + 8, g->d_totals.p, 16, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (*reinterpret_cast<uint32_t*>(hb)) fail(DNZ_ERR_NOMEM, "exchange ring overflow: an owner's ring is smaller than one step's packets (dnz_group_config.ring_entries / ring_key_bytes)");
+    stats.exchanged_out = (int64_t)reinterpret_cast<unsigned long long*>(hb + 8)[0]; stats.exchanged_in = (int64_t)reinterpret_cast<unsigned long long*>(hb + 8)[1];
+  }
+  g->my_lwm = has_lwm ? lwm : INT64_MIN;
+  g->my_first = exported_pane_upto != INT64_MIN ? exported_pane_upto + 1 : (panes.empty() ? INT64_MAX : panes.begin()->first);
+  const unsigned long long step = g->step + 1;
+  HostCtl* h = g->hctl; const int s = (int)(step & 1);
+  h->lwm[s][g->rank].store(g->my_lwm, std::memory_order_relaxed);
+  h->first_pane[s][g->rank].store(g->my_first, std::memory_order_relaxed);
+  h->arrived[s][g->rank].store((int64_t)step, std::memory_order_release);
+  g->phase = 1;
+}
+
+// ---- phase 2: global watermark; pack the closed panes' partial states of the keys owned elsewhere straight into the owners' rings
+void dnz_window::group_pack(dnz_group* g) {
+  if (g->phase != 1) fail(DNZ_ERR_INVALID, "dnz_group_step_pack without dnz_group_step_begin");
+  const unsigned long long step = g->step + 1;
+  const int par = (int)(step & 1);
+  group_wait(g, g->hctl->arrived, step, "begin");
+  int64_t gwm = INT64_MAX, gfirst = INT64_MAX;
+  for (int r = 0; r < world; r++) { gwm = std::min(gwm, g->hctl->lwm[par][r].load(std::memory_order_relaxed)); gfirst = std::min(gfirst, g->hctl->first_pane[par][r].load(std::memory_order_relaxed)); }
+  g->gwm = gwm; g->gfirst = gfirst;
+  XchgView X = g->view; X.step = step;
+  const int64_t hi = gwm == INT64_MIN ? INT64_MIN : floor_div(gwm, pane_ms) - 1;          // panes with end <= global watermark
+  std::vector<Pane*> send;
+  if (gwm != INT64_MIN) for (auto& kv : panes) if (kv.first >= g->my_first && kv.first <= hi) send.push_back(kv.second.get());
+  // the owners must have merged step-2, which used the same half of their rings
+  if (step > 2) for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_merged[r][par], 0));
+  CK(cudaMemsetAsync(g->d_owner_cursor.p, 0, MAX_WORLD * 8, stream));
+  PackParams P; memset(&P, 0, sizeof P);
+  P.n_groups = n_groups_host; P.rank = rank; P.world = world; P.dict = dict_view();
+  P.owner_cursor = g->d_owner_cursor.as<unsigned long long>();
+  if (n_groups_host) {
+    P.pass = 0;
+    for (Pane* p : send) {
+      P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
+      CK(launch_pack_partials(P, stream)); stats.total_launches++;
+    }
+  }
+  CK(launch_xchg_reserve(X, g->d_owner_cursor.as<unsigned long long>(), g->d_owner_base.as<unsigned long long>(), g->d_totals.as<unsigned long long>(), stream));
+  stats.total_launches++;
+  if (n_groups_host) {
+    for (Pane* p : send) {
+      P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
+      CK(launch_pack_write_peer(P, X, g->d_owner_base.as<unsigned long long>(), stream)); stats.total_launches++;
+    }
+  }
+  CK(cudaEventRecord(g->ev_packed[rank][par], stream));                    // "all my packets of this step are in the owners' rings"
+  g->hctl->packed[par][g->rank].store((int64_t)step, std::memory_order_release);
+  g->phase = 2;
+}
+
+// ---- phase 3: merge what the peers sent, emit the closed windows of this rank's keys
+void dnz_window::group_finish(dnz_group* g, int64_t* gwm_out) {
+  if (g->phase != 2) fail(DNZ_ERR_INVALID, "dnz_group_step_finish without dnz_group_step_pack");
+  const unsigned long long step = ++g->step;
+  const int par = (int)(step & 1);
+  g->phase = 0;
+  group_wait(g, g->hctl->packed, step, "pack");
+  const int64_t gwm = g->gwm, gfirst = g->gfirst;
+  if (gwm_out) *gwm_out = gwm;
+  XchgView X = g->view; X.step = step;
+  const int64_t hi = gwm == INT64_MIN ? INT64_MIN : floor_div(gwm, pane_ms) - 1;
+  for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_packed[r][par], 0));
+  if (gwm != INT64_MIN && gfirst != INT64_MAX && hi >= gfirst) {
+    exported_pane_upto = std::max(exported_pane_upto, hi);                 // the same on every rank
+    const int64_t np = hi - gfirst + 1;
+    if (np > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one exchange step spans %lld panes", (long long)np);
+    for (int64_t p = gfirst; p <= hi; p++) ensure_side_arrays(get_pane(p, true));
+    const size_t pb = (size_t)np * sizeof(void*);
+    h_xptrs.reserve(7 * pb); d_xptrs.reserve(7 * pb);
+    void** hp = h_xptrs.as<void*>();      // (the previous step's table is no longer in use: group_begin drained the stream)
+    for (int64_t p = gfirst; p <= hi; p++) {
+      const size_t k = (size_t)(p - gfirst);
+      Pane* m = get_pane(p, false);
+      hp[0 * np + k] = m->st.p; hp[1 * np + k] = nullptr; hp[2 * np + k] = m->nullrows.p; hp[3 * np + k] = nullptr;
+      hp[4 * np + k] = m->fz.p; hp[5 * np + k] = nullptr; hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m->tag & 0xFFFFFFFFull));
+    }
+    CK(cudaMemcpyAsync(d_xptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
+    MergeParams M; memset(&M, 0, sizeof M);
+    char* dp = d_xptrs.as<char>();
+    M.panes.pane0 = gfirst; M.panes.n_panes = (int32_t)np; M.panes.pane_ms = pane_ms;
+    M.panes.main = (GroupState* const*)(dp + 0 * pb); M.panes.late = (GroupState* const*)(dp + 1 * pb);
+    M.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); M.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
+    M.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); M.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+    M.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
+    M.world = world; M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR));
+    CK(launch_merge_ring(M, X, g->d_totals.as<unsigned long long>() + 1, sm_count, stream)); stats.total_launches++;
+  }
+  CK(cudaMemsetAsync(&g->view.self.ctl->cursor[par], 0, 8, stream));       // the ring half is free again ...
+  CK(cudaEventRecord(g->ev_merged[rank][par], stream));                    // ... once this has happened
+  // ---- every rank emits the windows of ITS keys that closed under the global watermark
+  if (gwm != INT64_MIN) {
+    if (res_consumed) reset_results();
+    rotate_result_sets();
+    emit_normal(gwm, false, nullptr);
+  }
+}
+
+namespace {
+struct GroupHello { cudaIpcMemHandle_t mem; cudaIpcEventHandle_t packed[2], merged[2]; char shm[64]; int64_t ring_entries, ring_key_bytes; int32_t dev, pad; };
+}
+
+extern "C" {
+
+int32_t dnz_group_create(const dnz_group_config* cfg, dnz_allgather_fn allgather, void* ctx, dnz_group** out) {
+  if (!out) { g_last_error = "null out"; return DNZ_ERR_INVALID; }
+  *out = nullptr;
+  dnz_group* g = nullptr;
+  try {
+    if (!cfg || !allgather) fail(DNZ_ERR_INVALID, "null config or all-gather callback");
+    if (cfg->abi_version != DNZ_ABI_VERSION) fail(DNZ_ERR_INVALID, "abi_version %u != %u", cfg->abi_version, DNZ_ABI_VERSION);
+    if (cfg->world < 1 || cfg->world > MAX_WORLD || cfg->rank < 0 || cfg->rank >= cfg->world) fail(DNZ_ERR_INVALID, "bad rank/world (world <= %d)", MAX_WORLD);
+    g = new dnz_group();
+    g->rank = cfg->rank; g->world = cfg->world; g->dev = cfg->device; g->ipc = true;
+    g->ring_entries = (uint64_t)std::max<int64_t>(cfg->ring_entries, 0); g->ring_key_bytes = (uint64_t)std::max<int64_t>(cfg->ring_key_bytes, 0);
+    if (!g->ring_entries) g->ring_entries = 8ull << 20;
+    if (!g->ring_key_bytes) g->ring_key_bytes = 256ull << 20;
+    group_alloc_region(g, cudaEventInterprocess);
+    GroupHello mine; memset(&mine, 0, sizeof mine);
+    CK(cudaIpcGetMemHandle(&mine.mem, g->region));
+    for (int p = 0; p < 2; p++) { CK(cudaIpcGetEventHandle(&mine.packed[p], g->ev_packed[g->rank][p])); CK(cudaIpcGetEventHandle(&mine.merged[p], g->ev_merged[g->rank][p])); }
+    mine.ring_entries = (int64_t)g->ring_entries; mine.ring_key_bytes = (int64_t)g->ring_key_bytes; mine.dev = g->dev;
+    g->shm_bytes = round_up(sizeof(HostCtl), 4096);
+    if (g->rank == 0) {       // the block of per-step scalars shared by all ranks
+      snprintf(mine.shm, sizeof mine.shm, "/dnz_group_%d_%lld", (int)getpid(), (long long)std::chrono::steady_clock::now().time_since_epoch().count());
+      int fd = shm_open(mine.shm, O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd < 0 || ftruncate(fd, (off_t)g->shm_bytes) != 0) fail(DNZ_ERR_NOMEM, "shm_open(%s) failed", mine.shm);
+      void* p = mmap(nullptr, g->shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0); close(fd);
+      if (p == MAP_FAILED) fail(DNZ_ERR_NOMEM, "mmap of the group control block failed");
+      g->hctl = static_cast<HostCtl*>(p); g->shm_name = mine.shm; g->shm_owner = true;
+    }
+    std::vector<GroupHello> all((size_t)g->world);
+    if (allgather(ctx, &mine, all.data(), (int64_t)sizeof(GroupHello)) != 0) fail(DNZ_ERR_INVALID, "the rendezvous all-gather failed");
+    if (g->rank != 0) {
+      int fd = shm_open(all[0].shm, O_RDWR, 0600);
+      if (fd < 0) fail(DNZ_ERR_INVALID, "cannot open the group control block %s (ranks must share one node)", all[0].shm);
+      void* p = mmap(nullptr, g->shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0); close(fd);
+      if (p == MAP_FAILED) fail(DNZ_ERR_NOMEM, "mmap of the group control block failed");
+      g->hctl = static_cast<HostCtl*>(p); g->shm_name = all[0].shm;
+    }
+    g->peer_base.assign((size_t)g->world, nullptr);
+    for (int r = 0; r < g->world; r++) {
+      const GroupHello& o = all[(size_t)r];
+      if (o.ring_entries != mine.ring_entries || o.ring_key_bytes != mine.ring_key_bytes) fail(DNZ_ERR_INVALID, "ranks disagree on the ring size");
+      if (r == g->rank) continue;
+      int can = 0; CK(cudaDeviceCanAccessPeer(&can, g->dev, o.dev));
+      if (!can && o.dev != g->dev) fail(DNZ_ERR_UNSUPPORTED, "GPU %d cannot access GPU %d directly (the fused exchange needs NVLink / P2P)", g->dev, o.dev);
+      CK(cudaIpcOpenMemHandle(&g->peer_base[(size_t)r], o.mem, cudaIpcMemLazyEnablePeerAccess));
+      for (int p = 0; p < 2; p++) { CK(cudaIpcOpenEventHandle(&g->ev_packed[r][p], o.packed[p])); CK(cudaIpcOpenEventHandle(&g->ev_merged[r][p], o.merged[p])); }
+    }
+    group_finish_view(g);
+    GroupHello again = mine; std::vector<GroupHello> all2((size_t)g->world);          // barrier: everybody has mapped everything
+    if (allgather(ctx, &again, all2.data(), (int64_t)sizeof(GroupHello)) != 0) fail(DNZ_ERR_INVALID, "the rendezvous all-gather failed");
+    if (g->shm_owner) { shm_unlink(g->shm_name.c_str()); g->shm_owner = false; }      // the mappings stay; the name is gone
+    *out = g;
+    return DNZ_OK;
+  } catch (const DnzError& e) {
+    g_last_error = e.msg; delete g; return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what(); delete g; return DNZ_ERR_NOMEM;
+  }
+}
+
+int32_t dnz_group_create_local(int32_t world, const int32_t* devices, int64_t ring_entries, int64_t ring_key_bytes, dnz_group** out) {
+  if (!out || !devices) { g_last_error = "null argument"; return DNZ_ERR_INVALID; }
+  std::vector<dnz_group*> gs;
+  try {
+    if (world < 1 || world > MAX_WORLD) fail(DNZ_ERR_INVALID, "bad world (<= %d)", MAX_WORLD);
+    auto shared = std::make_shared<GroupShared>();
+    memset(static_cast<void*>(&shared->ctl), 0, sizeof(HostCtl));
+    for (int r = 0; r < world; r++) {
+      dnz_group* g = new dnz_group(); gs.push_back(g);
+      g->rank = r; g->world = world; g->dev = devices[r];
+      g->ring_entries = ring_entries > 0 ? (uint64_t)ring_entries : (1ull << 20); g->ring_key_bytes = ring_key_bytes > 0 ? (uint64_t)ring_key_bytes : (32ull << 20);
+      g->local_shared = shared; g->hctl = &shared->ctl;
+      group_alloc_region(g, 0);
+    }
+    for (int r = 0; r < world; r++) {
+      dnz_group* g = gs[(size_t)r];
+      g->peer_base.assign((size_t)world, nullptr);
+      for (int q = 0; q < world; q++) {
+        if (q == r) continue;
+        g->peer_base[(size_t)q] = gs[(size_t)q]->region;
+        for (int p = 0; p < 2; p++) { g->ev_packed[q][p] = gs[(size_t)q]->ev_packed[q][p]; g->ev_merged[q][p] = gs[(size_t)q]->ev_merged[q][p]; }
+        if (devices[q] != devices[r]) { CK(cudaSetDevice(devices[r])); cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
+      }
+      group_finish_view(g);
+    }
+    for (int r = 0; r < world; r++) out[r] = gs[(size_t)r];
+    return DNZ_OK;
+  } catch (const DnzError& e) {
+    g_last_error = e.msg; for (auto* g : gs) delete g; return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what(); for (auto* g : gs) delete g; return DNZ_ERR_NOMEM;
+  }
+}
+
+void dnz_group_destroy(dnz_group* g) {
+  if (!g) return;
+  if (g->hctl && !g->local_shared) g->hctl->failed.store(1);
+  delete g;
+}
+
+int32_t dnz_group_attach(dnz_group* g, dnz_window* w) {
+  if (!g) { g_last_error = "null group"; return DNZ_ERR_INVALID; }
+  return dnz_window_set_exchange(w, g->rank, g->world);
+}
+
+#define DNZ_GROUP_PHASE(call)                                                       \
+  DNZ_TRY(w)                                                                        \
+  if (!g) fail(DNZ_ERR_INVALID, "null group");                                      \
+  struct Guard { dnz_window* w; bool prev; ~Guard() { w->in_process = prev; } } guard{w, w->in_process};   \
+  w->in_process = true;                                                             \
+  call;                                                                             \
+  DNZ_CATCH(w)
+
+int32_t dnz_group_step_begin(dnz_group* g, dnz_window* w) { DNZ_GROUP_PHASE(w->group_begin(g)) }
+int32_t dnz_group_step_pack(dnz_group* g, dnz_window* w) { DNZ_GROUP_PHASE(w->group_pack(g)) }
+int32_t dnz_group_step_finish(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms) { DNZ_GROUP_PHASE(w->group_finish(g, global_watermark_ms)) }
+int32_t dnz_group_step(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms) {
+  int32_t rc = dnz_group_step_begin(g, w);
+  if (rc == DNZ_OK) rc = dnz_group_step_pack(g, w);
+  return rc != DNZ_OK ? rc : dnz_group_step_finish(g, w, global_watermark_ms);
 }
 
 }  // extern "C"

@@ -195,6 +195,41 @@ int32_t dnz_window_export_partials(dnz_window* w, int64_t watermark_ms, dnz_part
 int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, const int64_t* src_counts,
                                    const uint8_t* key_bytes, const int64_t* src_key_bytes, int64_t pane_lo, int64_t pane_hi);
 
+/* ---- fused pane exchange: the library owns the communicator.  One rank per GPU.  The six host-driven calls
+ * above collapse into ONE collective call per step; the data path has no host synchronisation and no library collective:
+ * every rank packs the partial states of the keys it does not own and writes them straight into the owner's receive ring in
+ * the owner's HBM with P2P stores over NVLink (CUDA IPC mappings), ring space is reserved with remote atomics, the streams of
+ * different ranks are ordered by interprocess CUDA events, the owner merges and emits (dnz_exchange.cu).  Scalars that the HOSTS need per step
+ * (local watermark -> global watermark) travel through a POSIX shared-memory block.  The only thing asked of the caller is a
+ * rendezvous all-gather at creation (the role the ncclUniqueId broadcast plays for NCCL). */
+typedef struct dnz_group dnz_group;
+/* all-gather `bytes` bytes from every rank into recv[rank * bytes]; returns 0 on success */
+typedef int32_t (*dnz_allgather_fn)(void* ctx, const void* send, void* recv, int64_t bytes);
+typedef struct {
+  uint32_t abi_version;     /* DNZ_ABI_VERSION */
+  int32_t rank, world;      /* world <= 32, all ranks on one node */
+  int32_t device;           /* CUDA device of this rank */
+  int64_t ring_entries;     /* packets one rank can RECEIVE per step (0 = 8 Mi); one packet per (pane, group) partial state */
+  int64_t ring_key_bytes;   /* key bytes one rank can receive per step (0 = 256 MiB) */
+} dnz_group_config;
+int32_t dnz_group_create(const dnz_group_config* cfg, dnz_allgather_fn allgather, void* ctx, dnz_group** out);
+/* all `world` ranks inside this process (out[world]); devices[r] may repeat (tests on one GPU) */
+int32_t dnz_group_create_local(int32_t world, const int32_t* devices, int64_t ring_entries, int64_t ring_key_bytes, dnz_group** out);
+void dnz_group_destroy(dnz_group* g);
+/* puts the operator into exchange mode as rank `g.rank` of `g.world` (before its first batch).  expected_groups of the operator
+ * must cover the GLOBAL key set: an owner interns keys it has never seen in a batch of its own. */
+int32_t dnz_group_attach(dnz_group* g, dnz_window* w);
+/* One exchange step = dnz_group_step_begin (aggregate what is queued, publish the local watermark) + dnz_group_step_pack (global
+ * watermark; pack the closed panes' partial states into the owners' rings) + dnz_group_step_finish (merge what the peers sent,
+ * emit), everything enqueued on the operator's stream; streams of different ranks are ordered by interprocess CUDA events.
+ * COLLECTIVE: every rank calls it the same number of times.  Multi-process callers use dnz_group_step; a process that drives
+ * several ranks calls each phase for all of its ranks before the next phase.  Emitted rows are fetched with dnz_window_poll /
+ * poll_device(_ready) as usual. */
+int32_t dnz_group_step_begin(dnz_group* g, dnz_window* w);
+int32_t dnz_group_step_pack(dnz_group* g, dnz_window* w);
+int32_t dnz_group_step_finish(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms);
+int32_t dnz_group_step(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms);
+
 /* ---- Arrow<->device buffer manager helpers ---------------------------------------------------------- */
 /* Reserves the device staging area for host batches up front (both halves of the double buffer, `bytes_per_launch`
  * each; ~40 B per row of max_rows_per_launch for the sensor schema) so that a fresh operator does not pay for

@@ -97,3 +97,61 @@ def test_exchange_over_nccl():
                           "--master-port", str(port), os.path.join(root, "tests", "mgpu_exchange_worker.py")],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and "NCCL exchange ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.timeout(120, method="thread")
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("L,S,filt", [(1000, 0, None), (4000, 1000, ("max", ">", 100))])
+def test_fused_group_exchange_equals_one_operator(world, L, S, filt):
+    """The library-owned communicator (dnz_group, all ranks in this process on one GPU): packets are written straight into the
+    owners' receive rings by the pack kernel (remote-atomic reservation + P2P stores + flags), merged by the owner, emitted by the
+    owner -- ONE collective call per step, no host-driven transfer."""
+    from denormalized_b200 import ExchangeGroup
+    from tests.helpers import gpu_window
+    rng = np.random.default_rng(11 * world + L + S)
+    batches, t_end = _stream(rng, 48, 1500, 700, 200, long_keys=True)
+    close = (t_end // 1000 + 1) * 1000 + 2 * L
+    want = run_oracle_batches(batches + [rows_to_batch([(close, 1.0, b"sentinel")])], L, S, filt)
+    groups = ExchangeGroup.create_local([0] * world, ring_entries=1 << 16, ring_key_bytes=4 << 20)
+    wins = [gpu_window(L, S, filt, expected_groups=2048) for _ in range(world)]
+    for g, w in zip(groups, wins):
+        g.attach(w)
+    got = []
+
+    def step():
+        for g, w in zip(groups, wins):
+            g.step_begin(w)
+        for g, w in zip(groups, wins):
+            g.step_pack(w)
+        gw = [g.step_finish(w) for g, w in zip(groups, wins)]
+        assert len(set(gw)) == 1                       # every rank computed the same global watermark
+        n = 0
+        for w in wins:
+            rb = w.poll()
+            n += rb.num_rows
+            got.extend(record_batch_rows(rb))
+        return n
+    steps_with_rows = 0
+    for i, b in enumerate(batches):
+        wins[i % world].push(to_record_batch(b))
+        if i % (3 * world) == 3 * world - 1:
+            steps_with_rows += step() > 0
+    for w in wins:                                     # every rank sees the end-of-stream marker
+        w.push(to_record_batch(rows_to_batch([(close, 1.0, b"sentinel")])))
+    step()
+    st = [w.stats() for w in wins]
+    for g, w in zip(groups, wins):                     # one more (empty) step makes the packet counters visible
+        g.step_begin(w)
+    for g, w in zip(groups, wins):
+        g.step_pack(w)
+    for g, w in zip(groups, wins):
+        g.step_finish(w)
+    st = [w.stats() for w in wins]
+    for w in wins:
+        w.close()
+    for g in groups:
+        g.close()
+    assert steps_with_rows >= 2 and len(want) > 500
+    assert sum(s["exchanged_out"] for s in st) == sum(s["exchanged_in"] for s in st) > 1000
+    assert_rows_equal(got, want)
+    assert len({(r[0], r[2]) for r in got}) == len(got)
