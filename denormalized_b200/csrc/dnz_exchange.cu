@@ -11,7 +11,7 @@ namespace dnz {
 // ---- pack: thread per group id of one pane; two passes (count, then write) over every pane of the export ----------------
 __global__ void __launch_bounds__(256) k_pack_partials(const __grid_constant__ PackParams P) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P.n_groups) return;
+  if (g >= P.n_groups || g >= min(*P.dict.n_groups, P.dict.gcap)) return;      // n_groups may be an upper bound (fused path)
   const GroupState s = P.st[g];
   const unsigned long long nr = P.nullrows ? P.nullrows[g] : 0ull;
   if (s.cnt == 0.0 && nr == 0ull) return;
@@ -92,7 +92,7 @@ cudaError_t launch_merge_partials(const MergeParams& p, cudaStream_t s) {
 //   [reset the ring half; record: merged]
 //   k_emit ...                 the owner emits the closed windows of ITS keys
 // =================================================================================================
-__global__ void k_xchg_reserve(XchgView X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total) {
+__global__ void k_xchg_reserve(XchgView X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total, uint32_t* err) {
   const int o = threadIdx.x;
   if (o >= X.world || o == X.rank) return;
   const unsigned long long c = owner_cursor[o];
@@ -100,7 +100,7 @@ __global__ void k_xchg_reserve(XchgView X, unsigned long long* owner_cursor, uns
   if (c) {
     base = atomicAdd_system(&X.peer[o].ctl->cursor[X.step & 1], c);
     if ((base >> 32) + (c >> 32) > X.ring_entries || (base & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) > X.ring_key_bytes) {
-      atomicOr(&X.self.ctl->error, 1u);          // the owner's ring is too small for this step: nothing of it is written
+      atomicOr(&X.self.ctl->error, 1u); atomicOr(err, 0x100u);   // the owner's ring is too small for this step: nothing of it is written
       base = ~0ull;
     }
   }
@@ -108,15 +108,15 @@ __global__ void k_xchg_reserve(XchgView X, unsigned long long* owner_cursor, uns
   owner_cursor[o] = 0ull;
   atomicAdd(sent_total, c >> 32);
 }
-cudaError_t launch_xchg_reserve(const XchgView& X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total, cudaStream_t s) {
-  k_xchg_reserve<<<1, MAX_WORLD, 0, s>>>(X, owner_cursor, owner_base, sent_total);
+cudaError_t launch_xchg_reserve(const XchgView& X, unsigned long long* owner_cursor, unsigned long long* owner_base, unsigned long long* sent_total, uint32_t* err, cudaStream_t s) {
+  k_xchg_reserve<<<1, MAX_WORLD, 0, s>>>(X, owner_cursor, owner_base, sent_total, err);
   return cudaGetLastError();
 }
 
 // pass 1 of the fused path: like k_pack_partials' write pass, but the destination is the owner's ring and key_off is absolute
 __global__ void __launch_bounds__(256) k_pack_write_peer(const __grid_constant__ PackParams P, const __grid_constant__ XchgView X, const unsigned long long* __restrict__ owner_base) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P.n_groups) return;
+  if (g >= P.n_groups || g >= min(*P.dict.n_groups, P.dict.gcap)) return;
   const GroupState s = P.st[g];
   const unsigned long long nr = P.nullrows ? P.nullrows[g] : 0ull;
   if (s.cnt == 0.0 && nr == 0ull) return;

@@ -284,6 +284,7 @@ struct dnz_window {
 
   // multi-GPU pane exchange
   int rank = 0, world = 1;
+  bool fused = false;                             // attached to a dnz_group: launches stay asynchronous, emission happens in the group step
   bool has_lwm = false; int64_t lwm = 0;          // local watermark (exchange mode: emission follows the GLOBAL one)
   int64_t exported_pane_upto = INT64_MIN;
   DevBuf d_part_entries, d_part_keys, d_owner_cursor, d_xptrs; PinnedBuf h_xptrs;
@@ -570,6 +571,10 @@ void dnz_window::arena_grow(uint64_t at_least) {
 }
 
 void dnz_window::parse_ctl(const char* h) {
+  if (const uint32_t xe = *reinterpret_cast<const uint32_t*>(h + CTL_MERGE_ERR)) {
+    if (xe & 0x100u) fail(DNZ_ERR_NOMEM, "exchange ring overflow: an owner's ring is smaller than one step's packets (dnz_group_config.ring_entries / ring_key_bytes)");
+    fail(DNZ_ERR_NOMEM, "pane merge failed (flags %u): the dictionary / key arena of this rank is too small for the keys it owns (in exchange mode expected_groups must cover the GLOBAL key set)", xe);
+  }
   n_groups_host = std::min(*reinterpret_cast<const uint32_t*>(h), gcap);
   arena_used_host = *reinterpret_cast<const uint64_t*>(h + 8);
   key_bytes_total_host = *reinterpret_cast<const uint64_t*>(h + 16);
@@ -791,7 +796,7 @@ void dnz_window::seal_current() {
   launch_scan(f);
   f.state = Slot::SEALED; sealed_order.push_back(f.idx);
   while (sealed_order.size() > 1) launch_slot(slot[sealed_order.front()]);
-  if (world > 1 || (cfg.flags & DNZ_FLAG_SYNCHRONOUS)) while (!sealed_order.empty()) launch_slot(slot[sealed_order.front()]);
+  if ((world > 1 && !fused) || (cfg.flags & DNZ_FLAG_SYNCHRONOUS)) while (!sealed_order.empty()) launch_slot(slot[sealed_order.front()]);
   const int next = (fill + 1) % NSLOT;
   if (slot[next].state == Slot::SEALED) launch_slot(slot[next]);
   if (slot[next].state == Slot::LAUNCHED) { while (!launched_order.empty() && slot[next].state == Slot::LAUNCHED) verify(slot[launched_order.front()]); }
@@ -1097,7 +1102,7 @@ void dnz_window::launch_slot(Slot& s) {
     }
     std::vector<Run> runs;
     plan_runs(s, mm, runs);
-    const bool speculative = world == 1 && runs.size() == 1 && !runs[0].dirty && !(cfg.flags & DNZ_FLAG_SYNCHRONOUS);
+    const bool speculative = (world == 1 || fused) && runs.size() == 1 && !runs[0].dirty && !(cfg.flags & DNZ_FLAG_SYNCHRONOUS);
     if (!speculative) while (!launched_order.empty()) verify(slot[launched_order.front()]);
     if (res_consumed) reset_results();
     rotate_result_sets();
@@ -1113,7 +1118,8 @@ void dnz_window::launch_slot(Slot& s) {
           g_tr.mark("agg_launch");
           s.speculative = true; s.t0 = g.t0; s.t1 = g.t1; s.pmin = g.pmin; s.pmax = g.pmax; s.rows_launched = g.rows;
         }
-        emit_normal(r.wm_after, true, &s);
+        if (world > 1) { if (!has_lwm || lwm <= r.wm_after) lwm = r.wm_after; has_lwm = true; }   // fused exchange: the group step emits under the GLOBAL watermark
+        else emit_normal(r.wm_after, true, &s);
         g_tr.mark("emit");
       }
     } else {
@@ -1148,6 +1154,8 @@ void dnz_window::verify(Slot& s) {
     const char* hs = h + s.ctl_off();
     defer_count_host = *reinterpret_cast<const uint64_t*>(hs); defer_flags_host = *reinterpret_cast<const uint32_t*>(hs + 8);
     bool blocked = *reinterpret_cast<const uint32_t*>(hs + 16) != 0;
+    if (defer_count_host && world > 1)
+      fail(DNZ_ERR_NOMEM, "fused exchange: a table overflowed while launches were in flight (%llu rows deferred); size expected_groups for the GLOBAL key set", (unsigned long long)defer_count_host);
     if (defer_count_host) {
       // rare: a table was too small.  Let everything that is enqueued finish (emission behind this launch -- and behind later
       // ones -- found the gate closed and did nothing), replay the deferred rows, then issue the emission again.
@@ -1616,6 +1624,7 @@ int32_t dnz_window_poll(dnz_window* w, struct ArrowArray* out, struct ArrowSchem
   DNZ_TRY(w)
   if (!out) fail(DNZ_ERR_INVALID, "null out");
   w->process_pending(); w->drain();
+  if (w->world > 1) w->fetch_ctl();          // exchange mode: surfaces merge / ring errors of the last step
   if (w->res_consumed) w->reset_results();
   w->export_arrow(out, out_schema, has_output, true);
   DNZ_CATCH(w)
@@ -1832,6 +1841,7 @@ struct dnz_group {
   XchgView view{};
   unsigned long long step = 0;
   DevBuf d_owner_cursor, d_owner_base, d_totals;   // totals: [0] packets sent, [1] packets merged
+  PinnedBuf h_totals; cudaEvent_t totals_ev = nullptr; bool totals_issued = false;
   int phase = 0;                                 // 0 idle, 1 begun, 2 packed
   int64_t my_lwm = INT64_MIN, my_first = INT64_MAX, gwm = INT64_MIN, gfirst = INT64_MAX;
 
@@ -1846,6 +1856,7 @@ struct dnz_group {
   ~dnz_group() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    if (totals_ev) cudaEventDestroy(totals_ev);
     for (int p = 0; p < 2; p++) { if (ev_packed[rank][p]) cudaEventDestroy(ev_packed[rank][p]); if (ev_merged[rank][p]) cudaEventDestroy(ev_merged[rank][p]); }
     if (ipc) {
       for (int r = 0; r < world; r++) if (r != rank) for (int p = 0; p < 2; p++) { if (ev_packed[r][p]) cudaEventDestroy(ev_packed[r][p]); if (ev_merged[r][p]) cudaEventDestroy(ev_merged[r][p]); }
@@ -1869,6 +1880,8 @@ void group_alloc_region(dnz_group* g, unsigned event_flags) {
   CK(cudaMemset(g->region, 0, 4096));
   g->d_owner_cursor.alloc(MAX_WORLD * 8); g->d_owner_base.alloc(MAX_WORLD * 8); g->d_totals.alloc(64);
   CK(cudaMemset(g->d_totals.p, 0, 64));
+  g->h_totals.reserve(64); memset(g->h_totals.p, 0, 64);
+  CK(cudaEventCreateWithFlags(&g->totals_ev, cudaEventDisableTiming));
   for (int p = 0; p < 2; p++) {
     CK(cudaEventCreateWithFlags(&g->ev_packed[g->rank][p], cudaEventDisableTiming | event_flags));
     CK(cudaEventCreateWithFlags(&g->ev_merged[g->rank][p], cudaEventDisableTiming | event_flags));
@@ -1908,18 +1921,15 @@ void group_wait(dnz_group* g, std::atomic<int64_t> (*ctr)[MAX_WORLD], unsigned l
 void dnz_window::group_begin(dnz_group* g) {
   if (world != g->world || rank != g->rank) fail(DNZ_ERR_INVALID, "operator is not attached to this group");
   if (g->phase != 0) fail(DNZ_ERR_INVALID, "dnz_group_step_begin: the previous step of this rank is not finished");
-  process_pending(); drain();
-  fetch_ctl();
-  if (*reinterpret_cast<const uint32_t*>(h_small.as<char>() + CTL_MERGE_ERR)) fail(DNZ_ERR_NOMEM, "pane merge failed: the dictionary / key arena of this rank is too small for the keys it owns (in exchange mode expected_groups must cover the GLOBAL key set)");
-  {
-    h_small.reserve(CTL_BYTES + 64);
-    char* hb = h_small.as<char>() + CTL_BYTES;
-    CK(cudaMemcpyAsync(hb, &g->view.self.ctl->error, 4, cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(hb + 8, g->d_totals.p, 16, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    if (*reinterpret_cast<uint32_t*>(hb)) fail(DNZ_ERR_NOMEM, "exchange ring overflow: an owner's ring is smaller than one step's packets (dnz_group_config.ring_entries / ring_key_bytes)");
-    stats.exchanged_out = (int64_t)reinterpret_cast<unsigned long long*>(hb + 8)[0]; stats.exchanged_in = (int64_t)reinterpret_cast<unsigned long long*>(hb + 8)[1];
+  // everything that has been pushed is enqueued (scan, aggregate); nothing is waited for: the local watermark follows from the
+  // tile scans alone, errors of earlier steps (ring / table overflow) surface when their launches are verified
+  process_pending();
+  while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
+  cudaGetLastError();
+  if (g->totals_issued && cudaEventQuery(g->totals_ev) == cudaSuccess) {
+    stats.exchanged_out = (int64_t)g->h_totals.as<unsigned long long>()[0]; stats.exchanged_in = (int64_t)g->h_totals.as<unsigned long long>()[1];
   }
+  cudaGetLastError();
   g->my_lwm = has_lwm ? lwm : INT64_MIN;
   g->my_first = exported_pane_upto != INT64_MIN ? exported_pane_upto + 1 : (panes.empty() ? INT64_MAX : panes.begin()->first);
   const unsigned long long step = g->step + 1;
@@ -1947,18 +1957,18 @@ void dnz_window::group_pack(dnz_group* g) {
   if (step > 2) for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_merged[r][par], 0));
   CK(cudaMemsetAsync(g->d_owner_cursor.p, 0, MAX_WORLD * 8, stream));
   PackParams P; memset(&P, 0, sizeof P);
-  P.n_groups = n_groups_host; P.rank = rank; P.world = world; P.dict = dict_view();
+  P.n_groups = gcap; P.rank = rank; P.world = world; P.dict = dict_view();      // grid bound; the kernels clamp to the device counter
   P.owner_cursor = g->d_owner_cursor.as<unsigned long long>();
-  if (n_groups_host) {
+  {
     P.pass = 0;
     for (Pane* p : send) {
       P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
       CK(launch_pack_partials(P, stream)); stats.total_launches++;
     }
   }
-  CK(launch_xchg_reserve(X, g->d_owner_cursor.as<unsigned long long>(), g->d_owner_base.as<unsigned long long>(), g->d_totals.as<unsigned long long>(), stream));
+  CK(launch_xchg_reserve(X, g->d_owner_cursor.as<unsigned long long>(), g->d_owner_base.as<unsigned long long>(), g->d_totals.as<unsigned long long>(), reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR)), stream));
   stats.total_launches++;
-  if (n_groups_host) {
+  {
     for (Pane* p : send) {
       P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
       CK(launch_pack_write_peer(P, X, g->d_owner_base.as<unsigned long long>(), stream)); stats.total_launches++;
@@ -2008,6 +2018,8 @@ void dnz_window::group_finish(dnz_group* g, int64_t* gwm_out) {
   }
   CK(cudaMemsetAsync(&g->view.self.ctl->cursor[par], 0, 8, stream));       // the ring half is free again ...
   CK(cudaEventRecord(g->ev_merged[rank][par], stream));                    // ... once this has happened
+  CK(cudaMemcpyAsync(g->h_totals.p, g->d_totals.p, 16, cudaMemcpyDeviceToHost, stream));   // packet counters for dnz_stats (read when complete)
+  CK(cudaEventRecord(g->totals_ev, stream)); g->totals_issued = true;
   // ---- every rank emits the windows of ITS keys that closed under the global watermark
   if (gwm != INT64_MIN) {
     if (res_consumed) reset_results();
@@ -2123,7 +2135,9 @@ void dnz_group_destroy(dnz_group* g) {
 
 int32_t dnz_group_attach(dnz_group* g, dnz_window* w) {
   if (!g) { g_last_error = "null group"; return DNZ_ERR_INVALID; }
-  return dnz_window_set_exchange(w, g->rank, g->world);
+  const int32_t rc = dnz_window_set_exchange(w, g->rank, g->world);
+  if (rc == DNZ_OK) w->fused = g->world > 1;
+  return rc;
 }
 
 #define DNZ_GROUP_PHASE(call)                                                       \

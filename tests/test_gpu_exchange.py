@@ -82,8 +82,10 @@ def test_exchange_rejects_late_batches_for_exchanged_panes():
         w.close()
 
 
+@pytest.mark.timeout(600, method="thread")
 def test_exchange_over_nccl():
-    """Two ranks on two GPUs, packets over NCCL (skipped on single-GPU boxes)."""
+    """Two ranks on two GPUs: the host-driven exchange over NCCL, then the fused exchange over CUDA IPC / P2P (skipped on
+    single-GPU boxes)."""
     import os
     import socket
     import subprocess
@@ -96,7 +98,7 @@ def test_exchange_over_nccl():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), os.path.join(root, "tests", "mgpu_exchange_worker.py")],
                          capture_output=True, text=True, timeout=600, cwd=root)
-    assert out.returncode == 0 and "NCCL exchange ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.returncode == 0 and "NCCL exchange ok" in out.stdout and "fused P2P exchange ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 @pytest.mark.timeout(120, method="thread")
