@@ -183,7 +183,7 @@ def run_reference(args, wl):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([d for _, d in rates]) * 1e3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, wl, 1),
-            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "threads": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference algorithm (oracle/, hash-partitioned over all host cores); the Rust "
                     "reference itself cannot be built in this image"}
@@ -684,10 +684,71 @@ def main():
             log("e2e leg: emitted rows equal the oracle's")
         for w in e_wins:
             w.close()
+        # ---- the same call sequence with PAGEABLE Arrow buffers (what arrow-rs hands over when the decoder does not allocate
+        # through dnz_host_alloc): the library falls back to cudaMemcpyAsync, which the driver stages through its own pinned buffers
+        pageable_e2e = None
+        if rank == 0 or world > 1:
+            import pyarrow as pa
+            p_rows = min(e2e_rows, 134_217_728) // BATCH_ROWS * BATCH_ROWS
+            p_nb = p_rows // BATCH_ROWS
+            schema = d.canonical_schema(); meta_fields = list(schema.field(3).type)
+            barrier_col = pa.array(["no_barrier"] * BATCH_ROWS, pa.utf8())
+            pbatches = []
+            for hbv in batches_from_addresses(hb_addrs, p_nb):          # numpy copies of the pinned buffers = ordinary heap memory
+                ts_b, val_b = pa.py_buffer(hbv.ts.copy()), pa.py_buffer(hbv.val.copy())
+                off_b, kb_b = pa.py_buffer(hbv.key_off.copy()), pa.py_buffer(hbv.key_bytes.copy())
+                tsa = pa.Array.from_buffers(pa.timestamp("ms"), BATCH_ROWS, [None, ts_b])
+                pbatches.append(pa.RecordBatch.from_arrays([pa.Array.from_buffers(pa.int64(), BATCH_ROWS, [None, ts_b]),
+                                                            pa.Array.from_buffers(pa.float64(), BATCH_ROWS, [None, val_b]),
+                                                            pa.Array.from_buffers(pa.utf8(), BATCH_ROWS, [None, off_b, kb_b]),
+                                                            pa.StructArray.from_arrays([barrier_col, tsa], fields=meta_fields)], schema=schema))
+            p_last = T0 + (p_rows - 1) // wl["rows_per_ms"]
+            p_close = (p_last // 1000 + 1) * 1000 + 2 * wl["window_ms"]
+            n_p = 1 + min(args.steps, 3)
+            p_exp = [export_all(d, pbatches) for _ in range(n_p)]
+            p_wins = [new_window() for _ in range(n_p)]
+            for w_ in p_wins:
+                w_.reserve_input(int(min(launch_rows, p_rows) * (in_bytes / e2e_rows) * 1.05) + (64 << 20))
+
+            def step_pageable(i):
+                h = p_wins[i]._h
+                n_out = 0
+                for k in range(p_nb):
+                    rc = push(h, C.byref(p_exp[i][k]))
+                    if rc:
+                        raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
+                    last = k == p_nb - 1
+                    if last or (k + 1) % GROUP == 0:
+                        rc = (flush(h, p_close) or poll(h, C.byref(ca), C.byref(cs), C.byref(has))) if last else poll_ready(h, C.byref(ca), C.byref(cs), C.byref(has))
+                        if rc:
+                            raise d.DnzError(rc, L.dnz_window_last_error(h).decode())
+                        n_out += ca.length
+                        rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
+                return n_out
+            step_pageable(0)
+            barrier()
+            tp0 = time.perf_counter()
+            for i in range(1, n_p):
+                step_pageable(i)
+            barrier()
+            p_wall = time.perf_counter() - tp0
+            p_bytes = p_wins[-1].stats()["h2d_pageable_bytes"]
+            for w_ in p_wins:
+                w_.close()
+            tpw = torch.tensor([p_wall], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tpw, op=dist.ReduceOp.MAX)
+            p_wall = float(tpw.item())
+            pageable_e2e = {"value": p_rows * world * (n_p - 1) / p_wall, "unit": "rows/s", "rows_per_step": p_rows * world, "steps": n_p - 1,
+                            "h2d_pageable_bytes_per_step": int(p_bytes), "gb_per_s": p_bytes * (n_p - 1) / p_wall / 1e9,
+                            "sample": f"first {p_rows} rows/GPU of the stream in ordinary (pageable) heap memory: cudaMemcpyAsync path, wall clock"}
+            del pbatches, p_exp
         e2e = {"value": e2e_rows * world * args.steps / (ems * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows * world, "ms_per_step": ems / args.steps,
-               "wall_ms_per_step": wall_ms / args.steps, "rows_out_per_step": int(e_out),
-               "sample": f"first {e2e_rows} rows/GPU of the stream, Arrow buffers in pinned host memory (dnz_host_alloc)"}
+               "wall_ms_per_step": wall_ms / args.steps, "rows_out_per_step": int(e_out), "pinned_fraction": 1.0 - pageable / max(h2d, 1),
+               "h2d_gb_per_s": h2d / (ems / args.steps * 1e-3) / 1e9 / 1.0,
+               "sample": f"first {e2e_rows} rows/GPU of the stream, Arrow buffers in pinned host memory (dnz_host_alloc)",
+               "pageable": pageable_e2e}
         del hb, exported
         L.dnz_host_free(base)
 
@@ -698,7 +759,7 @@ def main():
         threads = choose_threads(wl)
         crow = args.cpu_rows or auto_cpu_rows(wl, threads)
         rate, dt, n, _ = cpu_baseline(wl, crow, threads)
-        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "threads": threads, "host_cores": os.cpu_count(), "kind": "port",
                "sample": f"{n} rows ({n // BATCH_ROWS} batches) of the {args.workload} stream, {dt:.1f} s, oracle/ hash-partitioned over {threads} threads"}
 
     if rank == 0:

@@ -18,6 +18,8 @@ _SO = os.path.join(_HERE, "libdnz_gpu.so")
 
 AGG_KINDS = {"count": 0, "min": 1, "max": 2, "avg": 3, "average": 3, "sum": 4}
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
+ABI_VERSION = 2
+TS_CANONICAL, TS_INT64_MILLIS, TS_INT64_SECONDS, TS_STRING_ISO8601 = 0, 1, 2, 3
 FLAG_KERNEL_TIMING = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_NO_HINTS = 4
@@ -58,7 +60,8 @@ class _Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("key_column", C.c_int32), ("n_aggs", C.c_int32),
                 ("aggs", C.POINTER(_Agg)), ("window_ms", C.c_int64), ("slide_ms", C.c_int64), ("has_filter", C.c_int32),
                 ("filter_agg", C.c_int32), ("filter_op", C.c_int32), ("flags", C.c_uint32), ("filter_literal", C.c_double),
-                ("expected_groups", C.c_int64), ("max_rows_per_launch", C.c_int64), ("cuda_stream", C.c_void_p)]
+                ("expected_groups", C.c_int64), ("max_rows_per_launch", C.c_int64), ("cuda_stream", C.c_void_p),
+                ("ts_source", C.c_int32), ("ts_column", C.c_int32), ("ts_format", C.c_char_p)]
 
 
 class DeviceBatchC(C.Structure):
@@ -105,6 +108,7 @@ EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dn
            "dnz_window_last_error", "dnz_window_destroy", "dnz_window_set_exchange", "dnz_window_reserve_input", "dnz_window_process", "dnz_window_export_partials",
            "dnz_window_import_partials", "dnz_host_alloc", "dnz_host_free", "dnz_device_alloc", "dnz_device_free",
            "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free",
+           "dnz_window_checkpoint", "dnz_window_restore", "dnz_blob_free",
            "dnz_group_create", "dnz_group_create_local", "dnz_group_destroy", "dnz_group_attach", "dnz_group_step_begin",
            "dnz_group_step_pack", "dnz_group_step_finish", "dnz_group_step"]
 
@@ -171,6 +175,11 @@ def lib():
         L.dnz_synth_generate.restype = C.c_int32
         L.dnz_synth_generate.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(DeviceBatchC), C.c_int64]
+        L.dnz_window_checkpoint.restype = C.c_int32
+        L.dnz_window_checkpoint.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.dnz_window_restore.restype = C.c_int32
+        L.dnz_window_restore.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.dnz_blob_free.argtypes = [C.c_void_p]
         L.dnz_group_create.restype = C.c_int32
         L.dnz_group_create.argtypes = [C.POINTER(GroupConfigC), ALLGATHER_FN, C.c_void_p, C.POINTER(C.c_void_p)]
         L.dnz_group_create_local.restype = C.c_int32
@@ -257,14 +266,16 @@ class GpuStreamingWindow:
     aggs: list of (kind, input column name, alias); filt: (alias, op, literal) or None."""
 
     def __init__(self, schema: pa.Schema, key, aggs, window_ms, slide_ms=0, filt=None, *, device=0, flags=0,
-                 expected_groups=0, max_rows_per_launch=0, cuda_stream=None):
+                 expected_groups=0, max_rows_per_launch=0, cuda_stream=None, timestamp=None):
         self._L = lib()
         self._h = C.c_void_p()
         names = schema.names
         self._aliases = [a[2].encode() for a in aggs]
         arr = (_Agg * len(aggs))(*[_Agg(AGG_KINDS[k], names.index(col), al) for (k, col, _), al in zip(aggs, self._aliases)])
-        cfg = _Config(1, device, names.index(key), len(aggs), arr, int(window_ms), int(slide_ms or 0), 0, 0, 0, flags, 0.0,
-                      expected_groups, max_rows_per_launch, cuda_stream)
+        ts_source, ts_column, ts_format = timestamp if timestamp else (0, 0, None)      # (TS_* kind, column name, chrono format)
+        self._ts_format = ts_format.encode() if ts_format else None
+        cfg = _Config(ABI_VERSION, device, names.index(key), len(aggs), arr, int(window_ms), int(slide_ms or 0), 0, 0, 0, flags, 0.0,
+                      expected_groups, max_rows_per_launch, cuda_stream, ts_source, names.index(ts_column) if ts_source else 0, self._ts_format)
         if filt is not None:
             alias, op, lit = filt
             cfg.has_filter, cfg.filter_agg, cfg.filter_op, cfg.filter_literal = 1, [a[2] for a in aggs].index(alias), OPS[op], float(lit)
@@ -336,6 +347,18 @@ class GpuStreamingWindow:
                 "count": get(r.count, np.int64, n), "min": get(r.min, np.float64, n), "max": get(r.max, np.float64, n),
                 "avg": get(r.avg, np.float64, n), "sum": get(r.sum, np.float64, n), "agg_valid": av,
                 "window_start": get(r.window_start_ms, np.int64, n), "window_end": get(r.window_end_ms, np.int64, n)}
+
+    def checkpoint(self) -> bytes:
+        """Serialised device state (dictionary, open panes, stream clock): dnz_window_checkpoint."""
+        blob, n = C.c_void_p(), C.c_int64(0)
+        self._check(self._L.dnz_window_checkpoint(self._h, C.byref(blob), C.byref(n)))
+        try:
+            return C.string_at(blob, n.value)
+        finally:
+            self._L.dnz_blob_free(blob)
+
+    def restore(self, blob: bytes):
+        self._check(self._L.dnz_window_restore(self._h, blob, len(blob)))
 
     def flush(self, watermark_ms: int):
         self._check(self._L.dnz_window_flush(self._h, int(watermark_ms)))
@@ -415,7 +438,7 @@ class ExchangeGroup:
             except Exception:          # noqa: BLE001 -- reported as a failed rendezvous by the library
                 return 1
         fn = ALLGATHER_FN(cb)
-        cfg = GroupConfigC(1, rank, world, device, ring_entries, ring_key_bytes)
+        cfg = GroupConfigC(ABI_VERSION, rank, world, device, ring_entries, ring_key_bytes)
         h = C.c_void_p()
         rc = L.dnz_group_create(C.byref(cfg), fn, None, C.byref(h))
         if rc != 0:

@@ -10,6 +10,9 @@
 //                    (trigger_windows / evaluate, :220-253, :609-629; continuous/mod.rs:64-89; FilterExec)
 //
 // No tensor-core work exists on this path (no dense contraction); the kernels are HBM/L2-transaction bound.
+#include <algorithm>
+#include <cstring>
+
 #include "dnz_device.cuh"
 
 namespace dnz {
@@ -135,9 +138,8 @@ __global__ void __launch_bounds__(256, 3) k_tile_scan(const BatchDesc* __restric
       }
       bool aligned = ((reinterpret_cast<uintptr_t>(bd.ts + row0) | reinterpret_cast<uintptr_t>(bd.val + row0) |
                        reinterpret_cast<uintptr_t>(bd.off + row0) | reinterpret_cast<uintptr_t>(bd.bytes)) & 15u) == 0;
-      if (allow_fast && (bd.flags & BATCH_BULK_OK) && aligned && !bd.ts_valid && !bd.val_valid && !bd.key_valid &&
-          td.byte_len <= BCAP && cnt > 0)
-        td.flags |= TILE_FAST;
+      if (allow_fast && (bd.flags & BATCH_BULK_OK) && aligned && !bd.ts_valid && !bd.val_valid && !bd.key_valid && cnt > 0)
+        td.flags |= td.byte_len <= BCAP ? TILE_FAST : (TILE_FAST | TILE_KEYS_GLOBAL);
       tiles[t] = td;
       acc_bytes += (unsigned long long)td.byte_len; acc_tiles += 1;
       if (td.flags & TILE_FAST) acc_fast += 1;
@@ -245,7 +247,8 @@ struct __align__(16) StageHdr {   // the consumers read the first two 16 B words
   uint32_t tile_rel, pane_rel;  // tile index inside the launch; pane index relative to PaneTable::pane0 (when mbase != nullptr)
   long long pane_lo;
   unsigned long long rowseq0;   // (batch arrival seq << 32) | first row of the tile inside its batch
-  uint32_t pad[4];
+  const uint8_t* gbytes;        // TILE_KEYS_GLOBAL: the batch's key byte buffer (offsets are absolute)
+  uint32_t pad[2];
 };
 static_assert(sizeof(StageHdr) == 64, "header size");
 struct __align__(128) Stage {
@@ -289,6 +292,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volat
 __device__ __noinline__ uint64_t agg_probe_slow(const AggParams& P, const uint8_t* key_smem, uint32_t len) {
   KeyRef k; load_key<true>(key_smem, len, k);
   uint32_t slot = 0; uint32_t g = dict_lookup(P.dict, k, true, &slot);
+  return ((uint64_t)slot << 32) | g;
+}
+__device__ __noinline__ uint64_t agg_probe_slow_global(const AggParams& P, const uint8_t* key_gmem, uint32_t len) {
+  KeyRef k; load_key<false>(key_gmem, len, k);
+  uint32_t slot = 0; uint32_t g = dict_lookup(P.dict, k, false, &slot);
   return ((uint64_t)slot << 32) | g;
 }
 // Accumulate one staged row through the general per-row path (pane from the timestamp, late panes, +-0.0, ...).
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
     // dependent global loads that would otherwise serialise per tile) into shared memory; lane 0 then feeds the ring.
     auto fetch = [&](int64_t t, TileFetch& d) {
       StageHdr h; h.mbase = nullptr; h.tag = 0; h.pane_lo = 0; h.rowseq0 = 0; h.n_rows = 0; h.flags = 0; h.a0 = 0; h.tile_rel = 0;
-      h.pane_rel = 0; h.pad[0] = h.pad[1] = h.pad[2] = h.pad[3] = 0;
+      h.pane_rel = 0; h.gbytes = nullptr; h.pad[0] = h.pad[1] = 0;
       d.nts = d.noff = d.nby = 0;
       if (t < P.tile_end) {
         const TileDesc td = P.tiles[t];
@@ -386,7 +394,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
         if (td.flags & TILE_FAST) {
           d.gts = bd.ts + td.row0; d.gval = bd.val + td.row0; d.goff = bd.off + td.row0; d.gby = bd.bytes + h.a0;
           d.nts = round16((uint32_t)td.n_rows * 8u); d.noff = round16(((uint32_t)td.n_rows + 1u) * 4u);
-          d.nby = round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
+          d.nby = (td.flags & TILE_KEYS_GLOBAL) ? 0u : round16((uint32_t)(td.byte0 + td.byte_len - h.a0));
+          h.gbytes = bd.bytes;
           if (td.flags & TILE_PANE_UNIFORM) {
             int64_t pi = td.pane_lo - P.panes.pane0;
             if (pi >= 0 && pi < P.panes.n_panes && P.panes.late[pi] == nullptr) {
@@ -475,7 +484,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
       GroupState* const mbase = reinterpret_cast<GroupState*>(((uint64_t)h1.y << 32) | h1.x);
       const double v = st.val[r];
       const int32_t o0 = st.off[r], o1 = st.off[r + 1];
-      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = live ? (uint32_t)(o0 - h0.z) : 0u;
+      const bool keys_global = (h0.y & TILE_KEYS_GLOBAL) != 0;          // warp-uniform: the key bytes were not staged
+      const uint32_t klen = live ? (uint32_t)(o1 - o0) : 0u, kb = (live && !keys_global) ? (uint32_t)(o0 - h0.z) : 0u;
       const uint32_t addr = smem_u32(st.bytes) + kb, q = addr & ~3u, mis = addr & 3u, sh = mis * 8u;
       uint32_t a[5];
 #pragma unroll
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
       const uint32_t bhi = (uint32_t)__double2hiint(v), blo = (uint32_t)__double2loint(v);
       const bool plain = mbase != nullptr && (bhi & 0x7FF00000u) != 0x7FF00000u && ((bhi << 1) | blo) != 0u;
       uint32_t gid = 0; uint64_t hint = 0;
-      bool need_slow = live && klen > (uint32_t)INLINE_KEY, park = false, hit = false;
+      bool need_slow = live && (klen > (uint32_t)INLINE_KEY || keys_global), park = false, hit = false;
       // ONE dictionary probe (32 B sector, carries the group's min/max hint)
       if (live && !need_slow) {
         uint64_t sa, sb, sc, sd;
@@ -516,7 +526,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_aggregate(const __grid_const
         }
         qcount += __popc(bal);
       }
-      if (need_slow) { const uint64_t gs = agg_probe_slow(P, st.bytes + kb, klen); gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true; }
+      if (need_slow) {
+        const uint64_t gs = keys_global ? agg_probe_slow_global(P, H.gbytes + o0, klen) : agg_probe_slow(P, st.bytes + kb, klen);
+        gid = (uint32_t)gs; idx = (uint32_t)(gs >> 32); hint = 0; hit = true;
+      }
       uint32_t pk = 0;
       if (hit) {
         if (gid >= GID_DEFER_ARENA) defer_row(P.defer, h1.z, r, gid == GID_DEFER_GROUPS ? DEFER_GROUPS_FULL : DEFER_ARENA_FULL);
@@ -758,6 +771,114 @@ cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
 }
 
 // =================================================================================================
+// k_ts_convert: the step BEFORE the path -- canonical event time from a raw column, as array_to_timestamp_array does
+// (physical_plan/utils/time.rs:59-94).  Thread per row; blockIdx.y = batch.
+//   kind 2  Int64 seconds      ts * 1000
+//   kind 3  Utf8, chrono format NaiveDateTime::parse_from_str(s, fmt).and_utc().timestamp_millis()
+// Supported specifiers: %Y %m %d %H %M %S %f %.f %3f %6f %9f %.3f %.6f %.9f %F %T %% and literals (whitespace in the format
+// matches any run of whitespace).  A string that does not match raises the error flag (the reference unwraps and panics).
+// =================================================================================================
+__device__ __forceinline__ bool ts_digits(const uint8_t* s, int& i, int n, int min_d, int max_d, long long& out) {
+  int d = 0; long long v = 0;
+  while (d < max_d && i < n && s[i] >= '0' && s[i] <= '9') { v = v * 10 + (s[i] - '0'); i++; d++; }
+  out = v;
+  return d >= min_d;
+}
+__device__ bool ts_parse(const uint8_t* s, int n, const TsFormat& F, long long* out_ms) {
+  long long Y = 1970, mo = 1, D = 1, H = 0, Mi = 0, S = 0, nanos = 0;
+  int i = 0;
+  for (int f = 0; f < F.len; f++) {
+    const char c = F.fmt[f];
+    if (c == ' ' || c == '\t' || c == '\n') { while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n')) i++; continue; }
+    if (c != '%') { if (i >= n || s[i] != (uint8_t)c) return false; i++; continue; }
+    char sp = F.fmt[++f];
+    bool dot = false; int fixed = 0;
+    if (sp == '.') { dot = true; sp = F.fmt[++f]; }
+    if (sp == '3' || sp == '6' || sp == '9') { fixed = sp - '0'; sp = F.fmt[++f]; }
+    long long v = 0;
+    switch (sp) {
+      case 'Y': { bool neg = false; if (i < n && (s[i] == '-' || s[i] == '+')) { neg = s[i] == '-'; i++; } const bool sg = neg || (i > 0 && s[i - 1] == '+'); if (!ts_digits(s, i, n, 1, sg ? 6 : 4, v)) return false; Y = neg ? -v : v; break; }   // chrono: more than 4 year digits need a sign
+      case 'm': if (!ts_digits(s, i, n, 1, 2, v) || v < 1 || v > 12) return false; mo = v; break;
+      case 'd': if (!ts_digits(s, i, n, 1, 2, v) || v < 1 || v > 31) return false; D = v; break;
+      case 'H': if (!ts_digits(s, i, n, 1, 2, v) || v > 23) return false; H = v; break;
+      case 'M': if (!ts_digits(s, i, n, 1, 2, v) || v > 59) return false; Mi = v; break;
+      case 'S': if (!ts_digits(s, i, n, 1, 2, v) || v > 60) return false; S = v; break;
+      case 'f': {
+        if (dot) {                                   // %.f / %.3f ...: optional for %.f, fraction of a second
+          if (i < n && s[i] == '.') {
+            i++;
+            int d0 = i;
+            if (!ts_digits(s, i, n, fixed ? fixed : 1, fixed ? fixed : 9, v)) return false;
+            int nd = i - d0; for (int k = nd; k < 9; k++) v *= 10;
+            while (!fixed && i < n && s[i] >= '0' && s[i] <= '9') i++;      // digits beyond nanoseconds are dropped
+            nanos = v;
+          } else if (fixed) return false;
+        } else if (fixed) {                          // %3f / %6f / %9f: exactly that many fraction digits, no dot
+          if (!ts_digits(s, i, n, fixed, fixed, v)) return false;
+          for (int k = fixed; k < 9; k++) v *= 10;
+          nanos = v;
+        } else {                                     // %f: NANOSECONDS as a number (up to 9 digits)
+          if (!ts_digits(s, i, n, 1, 9, v)) return false;
+          nanos = v;
+        }
+        break;
+      }
+      case '%': if (i >= n || s[i] != '%') return false; i++; break;
+      default: return false;
+    }
+  }
+  if (i != n) return false;                          // trailing input
+  // days from civil (proleptic Gregorian), then seconds
+  const long long y = mo <= 2 ? Y - 1 : Y;
+  const long long era = (y >= 0 ? y : y - 399) / 400;
+  const long long yoe = y - era * 400;
+  const long long doy = (153 * (mo + (mo > 2 ? -3 : 9)) + 2) / 5 + D - 1;
+  const long long doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  const long long days = era * 146097 + doe - 719468;
+  {   // reject dates that do not exist (31 April, 29 February of a common year)
+    const bool leap = (Y % 4 == 0 && Y % 100 != 0) || Y % 400 == 0;
+    const int mdays[12] = {31, leap ? 29 : 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (D > mdays[mo - 1]) return false;
+  }
+  long long secs = days * 86400 + H * 3600 + Mi * 60 + (S == 60 ? 59 : S);
+  if (S == 60) nanos += 1000000000ll;                // chrono keeps the leap second in the nanosecond field
+  *out_ms = secs * 1000 + nanos / 1000000;
+  return true;
+}
+__global__ void __launch_bounds__(256) k_ts_convert(const TsJob* __restrict__ jobs, int kind, const __grid_constant__ TsFormat F, uint32_t* error) {
+  const TsJob j = jobs[blockIdx.y];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < j.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (kind == 2) { j.dst[i] = reinterpret_cast<const int64_t*>(j.src)[i] * 1000; continue; }
+    const int32_t o0 = j.off[i], o1 = j.off[i + 1];
+    long long ms = 0;
+    if (!ts_parse(j.bytes + o0, o1 - o0, F, &ms)) { atomicOr(error, 1u); ms = 0; }
+    j.dst[i] = ms;
+  }
+}
+cudaError_t launch_ts_convert(const TsJob* jobs, int n_jobs, int64_t max_rows, int kind, const TsFormat& fmt, uint32_t* error, cudaStream_t s) {
+  if (n_jobs <= 0 || max_rows <= 0) return cudaSuccess;
+  const unsigned gx = (unsigned)std::min<int64_t>((max_rows + 255) / 256, 1024);
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    dim3 grid(gx, (unsigned)std::min(n_jobs - j0, 65535));
+    k_ts_convert<<<grid, 256, 0, s>>>(jobs + j0, kind, fmt, error);
+  }
+  return cudaGetLastError();
+}
+bool ts_format_supported(const char* fmt) {
+  if (!fmt) return false;
+  const size_t n = strlen(fmt);
+  if (n == 0 || n >= (size_t)TS_FMT_MAX) return false;
+  for (size_t f = 0; f < n; f++) {
+    if (fmt[f] != '%') continue;
+    char sp = fmt[++f];
+    if (sp == '.') sp = fmt[++f];
+    if (sp == '3' || sp == '6' || sp == '9') { sp = fmt[++f]; if (sp != 'f') return false; }
+    if (!strchr("YmdHMSf%", sp) || sp == 0) return false;
+  }
+  return true;
+}
+
+// =================================================================================================
 // small utilities
 // =================================================================================================
 __global__ void k_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v) {
@@ -839,6 +960,29 @@ cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, Dict
   return cudaGetLastError();
 }
 
+
+// checkpoint restore: re-insert the keys of gid_key[0, n) into an EMPTY table with their original group ids
+__global__ void k_dict_restore(DictView d, uint32_t n) {
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    const GidKey gk = d.gid_key[g];
+    if (gk.len == 0xFFFFFFFFu) { *d.null_gid = g + 1; continue; }
+    const uint64_t h = gk.len <= (uint32_t)INLINE_KEY ? hash_inline(gk.k0, gk.k1, gk.len) : gk.k0;
+    uint32_t idx = (uint32_t)h & d.mask;
+    for (;;) {
+      if (atomicCAS(&d.slots[idx].state, SLOT_EMPTY, SLOT_LOCKED) == SLOT_EMPTY) break;
+      idx = (idx + 1) & d.mask;
+    }
+    DictSlot* s = d.slots + idx;
+    s->k0 = gk.k0; s->k1 = gk.k1; s->hint = 0; s->len = gk.len;
+    __threadfence();
+    s->state = g + 1;
+  }
+}
+cudaError_t launch_dict_restore(DictView d, uint32_t n, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_dict_restore<<<(unsigned)std::min<uint64_t>(((uint64_t)n + 255) / 256, 148 * 16), 256, 0, s>>>(d, n);
+  return cudaGetLastError();
+}
 
 __global__ void k_clear_hints(DictSlot* slots, uint32_t cap) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) slots[i].hint = 0;

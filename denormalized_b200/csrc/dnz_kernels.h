@@ -19,6 +19,7 @@ enum : int32_t {
   TILE_PANE_UNIFORM = 2,  // every valid timestamp of the tile falls in pane_lo
   TILE_EMPTY = 4,         // no valid timestamp
   TILE_END = 8,           // (stage header only) no more tiles for this CTA
+  TILE_KEYS_GLOBAL = 16,  // with TILE_FAST: timestamps / values / offsets are staged, but the key bytes exceed the stage (long keys): read from global
 };
 
 struct BatchDesc {
@@ -176,6 +177,7 @@ cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);
 cudaError_t launch_dict_rehash(const DictSlot* old_slots, uint32_t old_cap, DictView nd, cudaStream_t s);
 cudaError_t launch_clear_hints(DictSlot* slots, uint32_t cap, cudaStream_t s);
+cudaError_t launch_dict_restore(DictView d, uint32_t n, cudaStream_t s);
 cudaError_t agg_kernel_setup();
 
 // exchange (multi-GPU, dnz_exchange.cu)
@@ -203,6 +205,13 @@ cudaError_t launch_merge_ring(const MergeParams& p, const XchgView& X, unsigned 
 struct CopyDesc { const void* src; void* dst; uint64_t bytes; uint64_t first_piece; };   // pieces of 256 KiB, prefix over the list
 constexpr uint64_t COPY_PIECE = 256 * 1024;
 cudaError_t launch_gather_copy(const CopyDesc* descs, uint32_t n, unsigned int* cursor, cudaStream_t s);
+
+// input-contract producer: canonical timestamps from a raw column (array_to_timestamp_array, utils/time.rs:59-94)
+struct TsJob { const void* src; const int32_t* off; const uint8_t* bytes; int64_t* dst; int64_t n; };    // src: i64 values (kinds 2); off/bytes: Utf8 (kind 3)
+constexpr int TS_FMT_MAX = 64;
+struct TsFormat { char fmt[TS_FMT_MAX]; int32_t len; };
+cudaError_t launch_ts_convert(const TsJob* jobs, int n_jobs, int64_t max_rows, int kind, const TsFormat& fmt, uint32_t* error, cudaStream_t s);
+bool ts_format_supported(const char* fmt);
 
 // synthetic generator (dnz_synth.cu)
 cudaError_t launch_synth(int64_t row0, int64_t n_rows, int64_t batch_rows, uint64_t seed, int64_t groups,

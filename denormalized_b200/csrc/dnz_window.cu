@@ -92,6 +92,7 @@ AllocCtx& alloc_ctx() {
 void* dev_alloc(size_t n) {
   AllocCtx& c = alloc_ctx();
   void* p = nullptr;
+  if (g_trace && n >= (256ull << 20)) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fprintf(stderr, "[dnz] alloc %.2f GB (device free %.1f of %.1f GB)\n", n / 1e9, fr / 1e9, tot / 1e9); }
   if (c.async_ok) { CK(cudaMallocAsync(&p, n, c.s)); CK(cudaStreamSynchronize(c.s)); }
   else CK(cudaMalloc(&p, n));
   return p;
@@ -198,6 +199,8 @@ struct Slot {
   // tile scan
   DevBuf d_batches, d_tiles, d_minmax; PinnedBuf h_batches, h_minmax; cudaEvent_t scan_done = nullptr;
   std::vector<BatchDesc> bds; int64_t n_tiles = 0; bool scanned = false;
+  // canonical timestamps still to be derived from raw columns of this superbatch (k_ts_convert, before the scan)
+  std::vector<TsJob> ts_jobs; int64_t ts_max_rows = 0; DevBuf d_ts_jobs; PinnedBuf h_ts_jobs;
   // aggregate launch (its own staging: the async copies read these buffers when the stream gets there)
   DevBuf d_ptrs, d_defer[2]; PinnedBuf h_ptrs;
   PinnedBuf snap; cudaEvent_t done = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -226,7 +229,7 @@ struct ResultSet {
 };
 
 enum { COL_COUNT = 0, COL_MIN = 1, COL_MAX = 2, COL_AVG = 3, COL_SUM = 4 };
-constexpr size_t CTL_BYTES = 256, CTL_MERGE_ERR = 224;
+constexpr size_t CTL_BYTES = 256, CTL_MERGE_ERR = 224, CTL_TS_ERR = 228;
 
 }  // namespace
 
@@ -236,6 +239,7 @@ struct dnz_window {
   std::vector<dnz_agg> aggs; std::vector<std::string> aliases;
   std::string key_name;
   int key_col = -1, val_col = -1, meta_col = -1, ts_child = -1, n_input_cols = 0;
+  int ts_source = DNZ_TS_CANONICAL, ts_col = -1; TsFormat ts_fmt{};      // input-contract producer
   int dev = 0; int sm_count = 148;
   cudaStream_t stream = nullptr; bool own_stream = false;
   cudaStream_t copy_stream = nullptr;
@@ -251,7 +255,9 @@ struct dnz_window {
   //   +224  pane-merge error flags (exchange)
   DevBuf d_ctl;
   char* ctl(size_t off) const { return d_ctl.as<char>() + off; }
-  uint32_t dict_cap = 0, gcap = 0; uint64_t arena_cap = 0;
+  uint32_t dict_cap = 0, gcap = 0;
+  uint64_t arena_cap = 0;     // LOGICAL capacity handed to the kernels (<= arena.bytes): bounds what launches in flight can add
+
   // host knowledge of the device counters: exact as of the last inspected snapshot ("known"), plus what launches enqueued since
   // then can have added at most ("bound")
   uint32_t n_groups_host = 0; uint64_t key_bytes_total_host = 0, arena_used_host = 0;
@@ -305,6 +311,7 @@ struct dnz_window {
   void dict_alloc(uint32_t new_gcap);
   void dict_grow();
   void arena_grow(uint64_t at_least);
+  void arena_trim();
   void fetch_ctl();
   void parse_ctl(const char* h);
   template <class F> void for_each_live_pane(F f);
@@ -346,6 +353,8 @@ struct dnz_window {
   bool set_drained(ResultSet& r);
   void export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking);
   void export_device(dnz_device_result* out, bool blocking);
+  void checkpoint(std::vector<char>& blob);
+  void restore(const char* blob, size_t bytes);
   void fill_schema(ArrowSchema* schema);
 };
 
@@ -453,17 +462,34 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
     aliases.push_back(a.alias ? a.alias : (a.kind == DNZ_AGG_COUNT ? "count" : a.kind == DNZ_AGG_MIN ? "min" : a.kind == DNZ_AGG_MAX ? "max" : a.kind == DNZ_AGG_AVG ? "average" : "sum"));
   }
   for (size_t i = 0; i < aggs.size(); i++) aggs[i].alias = aliases[i].c_str();
-  meta_col = -1;
-  for (int i = 0; i < n_input_cols; i++)
-    if (schema->children[i]->name && strcmp(schema->children[i]->name, "_streaming_internal_metadata") == 0) meta_col = i;
-  if (meta_col < 0) fail(DNZ_ERR_INVALID, "input schema lacks the `_streaming_internal_metadata` struct column");
-  const ArrowSchema* ms = schema->children[meta_col];
-  if (strcmp(ms->format, "+s") != 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` must be a struct");
-  ts_child = -1;
-  for (int i = 0; i < ms->n_children; i++)
-    if (ms->children[i]->name && strcmp(ms->children[i]->name, "canonical_timestamp") == 0) ts_child = i;
-  if (ts_child < 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` lacks `canonical_timestamp`");
-  if (strncmp(ms->children[ts_child]->format, "tsm:", 4) != 0) fail(DNZ_ERR_INVALID, "`canonical_timestamp` must be Timestamp(Millisecond)");
+  ts_source = c->ts_source; ts_col = -1;
+  if (ts_source == DNZ_TS_CANONICAL) {
+    meta_col = -1;
+    for (int i = 0; i < n_input_cols; i++)
+      if (schema->children[i]->name && strcmp(schema->children[i]->name, "_streaming_internal_metadata") == 0) meta_col = i;
+    if (meta_col < 0) fail(DNZ_ERR_INVALID, "input schema lacks the `_streaming_internal_metadata` struct column");
+    const ArrowSchema* ms = schema->children[meta_col];
+    if (strcmp(ms->format, "+s") != 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` must be a struct");
+    ts_child = -1;
+    for (int i = 0; i < ms->n_children; i++)
+      if (ms->children[i]->name && strcmp(ms->children[i]->name, "canonical_timestamp") == 0) ts_child = i;
+    if (ts_child < 0) fail(DNZ_ERR_INVALID, "`_streaming_internal_metadata` lacks `canonical_timestamp`");
+    if (strncmp(ms->children[ts_child]->format, "tsm:", 4) != 0) fail(DNZ_ERR_INVALID, "`canonical_timestamp` must be Timestamp(Millisecond)");
+  } else {
+    // raw decoded batches: the canonical timestamp is derived here (kafka_stream_read.rs:236-268, utils/time.rs:59-94)
+    if (ts_source < DNZ_TS_INT64_MILLIS || ts_source > DNZ_TS_STRING_ISO8601) fail(DNZ_ERR_INVALID, "bad ts_source %d", ts_source);
+    if (c->ts_column < 0 || c->ts_column >= n_input_cols) fail(DNZ_ERR_INVALID, "ts_column out of range");
+    ts_col = c->ts_column;
+    const char* tf = schema->children[ts_col]->format;
+    if (ts_source == DNZ_TS_STRING_ISO8601) {
+      if (strcmp(tf, "u") != 0) fail(DNZ_ERR_INVALID, "timestamp column must be Utf8 for TimestampUnit::StringIso8601 (format '%s')", tf);
+      std::string f = c->ts_format ? c->ts_format : "";
+      for (const auto& kv : {std::pair<const char*, const char*>{"%F", "%Y-%m-%d"}, {"%T", "%H:%M:%S"}})
+        for (size_t at; (at = f.find(kv.first)) != std::string::npos;) f.replace(at, 2, kv.second);
+      if (!ts_format_supported(f.c_str())) fail(DNZ_ERR_UNSUPPORTED, "timestamp format '%s' is not supported (specifiers: %%Y %%m %%d %%H %%M %%S %%f %%.f %%3f %%6f %%9f %%.3f %%.6f %%.9f %%F %%T %%%%)", c->ts_format ? c->ts_format : "");
+      memset(&ts_fmt, 0, sizeof ts_fmt); memcpy(ts_fmt.fmt, f.data(), f.size()); ts_fmt.len = (int32_t)f.size();
+    } else if (strcmp(tf, "l") != 0) fail(DNZ_ERR_INVALID, "timestamp column must be Int64 for TimestampUnit::Int64Millis / Int64Seconds (format '%s')", tf);
+  }
   if (c->has_filter && (c->filter_agg < 0 || c->filter_agg >= c->n_aggs || c->filter_op < DNZ_OP_GT || c->filter_op > DNZ_OP_NEQ))
     fail(DNZ_ERR_INVALID, "bad filter");
 
@@ -564,13 +590,23 @@ void dnz_window::dict_grow() {
 void dnz_window::arena_grow(uint64_t at_least) {
   uint64_t ncap = std::max<uint64_t>(arena_cap * 2, at_least);
   ncap = round_up(ncap, 1 << 20);
-  DevBuf na; na.alloc(ncap);
-  CK(cudaMemcpyAsync(na.p, arena.p, arena_cap, cudaMemcpyDeviceToDevice, stream));
-  CK(cudaStreamSynchronize(stream));
-  arena = std::move(na); arena_cap = ncap;
+  if (ncap > arena.bytes) {
+    DevBuf na; na.alloc(ncap);
+    CK(cudaMemcpyAsync(na.p, arena.p, arena_cap, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    arena = std::move(na);
+  }
+  arena_cap = ncap;
+}
+// After a replay the arena holds what it needs: pull the logical capacity back to "used + slack" so that the upper bounds
+// derived from the free space (result sizing) stay tight; the memory stays allocated and the next overflow just raises it.
+void dnz_window::arena_trim() {
+  const uint64_t want = round_up(arena_used_host + std::max<uint64_t>(64ull << 20, arena_used_host / 4), 1 << 20);
+  if (want < arena_cap && arena_used_host <= want) arena_cap = std::max<uint64_t>(want, 1 << 20);
 }
 
 void dnz_window::parse_ctl(const char* h) {
+  if (*reinterpret_cast<const uint32_t*>(h + CTL_TS_ERR)) fail(DNZ_ERR_DATA, "a timestamp string does not match the format (the reference unwraps the parse error and panics)");
   if (const uint32_t xe = *reinterpret_cast<const uint32_t*>(h + CTL_MERGE_ERR)) {
     if (xe & 0x100u) fail(DNZ_ERR_NOMEM, "exchange ring overflow: an owner's ring is smaller than one step's packets (dnz_group_config.ring_entries / ring_key_bytes)");
     fail(DNZ_ERR_NOMEM, "pane merge failed (flags %u): the dictionary / key arena of this rank is too small for the keys it owns (in exchange mode expected_groups must cover the GLOBAL key set)", xe);
@@ -686,9 +722,9 @@ void dnz_window::push_host(ArrowArray* batch) {
     const int64_t po = batch->offset;
     const ArrowArray* key = batch->children[key_col];
     const ArrowArray* val = batch->children[val_col];
-    const ArrowArray* meta = batch->children[meta_col];
-    const ArrowArray* ts = meta->children[ts_child];
-    if (key->length < po + n || val->length < po + n || ts->length < po + meta->offset + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
+    const ArrowArray* meta = ts_source == DNZ_TS_CANONICAL ? batch->children[meta_col] : nullptr;
+    const ArrowArray* ts = meta ? meta->children[ts_child] : batch->children[ts_col];
+    if (key->length < po + n || val->length < po + n || ts->length < po + (meta ? meta->offset : 0) + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
     // page-locked sources (dnz_host_alloc / cudaHostRegister) are device-readable: queue them for the gather kernel;
     // pageable sources go through cudaMemcpyAsync (staged by the driver)
     auto enqueue_copy = [&](void* d, const void* src, size_t bytes) {
@@ -717,10 +753,34 @@ void dnz_window::push_host(ArrowArray* batch) {
       vbit = (int32_t)(eff_off & 7);
     };
     // timestamps
-    int64_t to = po + meta->offset + ts->offset;
-    pb.d.ts = (const int64_t*)copy_in((const int64_t*)buf_at(ts, 1) + to, (size_t)n * 8);
-    copy_bitmap(ts, to, pb.d.ts_valid, pb.d.ts_vbit);
-    if (meta->null_count != 0 && buf_at(meta, 0)) fail(DNZ_ERR_UNSUPPORTED, "null `_streaming_internal_metadata` structs are not supported");
+    if (ts_source == DNZ_TS_CANONICAL) {
+      int64_t to = po + meta->offset + ts->offset;
+      pb.d.ts = (const int64_t*)copy_in((const int64_t*)buf_at(ts, 1) + to, (size_t)n * 8);
+      copy_bitmap(ts, to, pb.d.ts_valid, pb.d.ts_vbit);
+      if (meta->null_count != 0 && buf_at(meta, 0)) fail(DNZ_ERR_UNSUPPORTED, "null `_streaming_internal_metadata` structs are not supported");
+    } else {
+      // array_to_timestamp_array (utils/time.rs:59-94): Int64 values are taken as they are (the validity bitmap is ignored there
+      // too); a NULL string is unwrapped -> panic
+      const int64_t to = po + ts->offset;
+      if (ts_source == DNZ_TS_INT64_MILLIS) {
+        pb.d.ts = (const int64_t*)copy_in((const int64_t*)buf_at(ts, 1) + to, (size_t)n * 8);
+      } else if (ts_source == DNZ_TS_INT64_SECONDS) {
+        const void* raw = copy_in((const int64_t*)buf_at(ts, 1) + to, (size_t)n * 8);
+        int64_t* dst = (int64_t*)arena_in.alloc((size_t)n * 8);
+        c.ts_jobs.push_back(TsJob{raw, nullptr, nullptr, dst, n}); c.ts_max_rows = std::max(c.ts_max_rows, n);
+        pb.d.ts = dst;
+      } else {
+        if (ts->null_count != 0 && buf_at(ts, 0)) fail(DNZ_ERR_DATA, "NULL timestamp string (the reference unwraps it and panics)");
+        const int32_t* hoff = (const int32_t*)buf_at(ts, 1) + to;
+        const int32_t* doff = (const int32_t*)copy_in(hoff, (size_t)(n + 1) * 4);
+        const int64_t o0 = hoff[0], o1 = hoff[n];
+        uint8_t* db = (uint8_t*)arena_in.alloc((size_t)(o1 - o0) + 16);
+        if (o1 > o0) enqueue_copy(db, (const uint8_t*)buf_at(ts, 2) + o0, (size_t)(o1 - o0));
+        int64_t* dst = (int64_t*)arena_in.alloc((size_t)n * 8);
+        c.ts_jobs.push_back(TsJob{nullptr, doff, db - o0, dst, n}); c.ts_max_rows = std::max(c.ts_max_rows, n);
+        pb.d.ts = dst;
+      }
+    }
     // values
     int64_t vo = po + val->offset;
     pb.d.val = (const double*)copy_in((const double*)buf_at(val, 1) + vo, (size_t)n * 8);
@@ -824,7 +884,7 @@ void dnz_window::launch_scan(Slot& s) {
   const size_t nb = s.batches.size();
   s.bds.resize(nb); s.n_tiles = 0; s.scanned = true;
   for (size_t i = 0; i < nb; i++) { s.bds[i] = s.batches[i].d; s.bds[i].tile0 = s.n_tiles; s.n_tiles += (s.bds[i].n_rows + TILE - 1) / TILE; }
-  if (s.n_tiles == 0) return;            // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
+  if (s.n_tiles == 0) { s.ts_jobs.clear(); return; }            // only empty batches: no trigger (grouped_window_agg_stream.rs:331,:343-345)
   // the scan picks the LAST batch with tile0 <= t: empty batches in the middle share their successor's tile0 and are
   // never chosen; trailing empties get a tile0 past the end
   for (size_t i = nb; i-- > 0;) { if (s.bds[i].n_rows == 0) s.bds[i].tile0 = s.n_tiles + 1; else break; }
@@ -832,6 +892,15 @@ void dnz_window::launch_scan(Slot& s) {
   s.h_batches.reserve(nb * sizeof(BatchDesc)); s.h_minmax.reserve(nb * sizeof(BatchMinMax));
   memcpy(s.h_batches.p, s.bds.data(), nb * sizeof(BatchDesc));
   if (s.copies) CK(cudaStreamWaitEvent(stream, s.copy_done, 0));
+  if (!s.ts_jobs.empty()) {           // canonical timestamps from the raw column: the step before the path (utils/time.rs:59-94)
+    const size_t jb = s.ts_jobs.size() * sizeof(TsJob);
+    s.h_ts_jobs.reserve(jb); s.d_ts_jobs.reserve(jb);
+    memcpy(s.h_ts_jobs.p, s.ts_jobs.data(), jb);
+    CK(cudaMemcpyAsync(s.d_ts_jobs.p, s.h_ts_jobs.p, jb, cudaMemcpyHostToDevice, stream));
+    CK(launch_ts_convert(s.d_ts_jobs.as<TsJob>(), (int)s.ts_jobs.size(), s.ts_max_rows, ts_source, ts_fmt, reinterpret_cast<uint32_t*>(ctl(CTL_TS_ERR)), stream));
+    stats.total_launches++;
+    s.ts_jobs.clear(); s.ts_max_rows = 0;
+  }
   CK(cudaMemcpyAsync(s.d_batches.p, s.h_batches.p, nb * sizeof(BatchDesc), cudaMemcpyHostToDevice, stream));
   bool allow_fast = !(cfg.flags & DNZ_FLAG_FORCE_GENERIC);
   CK(launch_tile_scan(s.d_batches.as<BatchDesc>(), (int64_t)nb, s.n_tiles, pane_ms, s.d_tiles.as<TileDesc>(), s.d_minmax.as<BatchMinMax>(), allow_fast, stream));
@@ -1038,6 +1107,7 @@ void dnz_window::resolve_deferred(Slot& s, const RunGeom& g, bool dirty, int64_t
     n_in = *reinterpret_cast<const uint64_t*>(h); flags = *reinterpret_cast<const uint32_t*>(h + 8);
     in_list = out_list;
   }
+  arena_trim();
 }
 
 // Aggregates one run and triggers, waiting for the device after the launch (late batches, several runs in one superbatch,
@@ -1175,7 +1245,7 @@ void dnz_window::verify(Slot& s) {
 void dnz_window::release_slot(Slot& s) {
   if (s.copies) cudaEventSynchronize(s.copy_done);
   for (auto& pb : s.batches) if (pb.has_moved && pb.moved.release) pb.moved.release(&pb.moved);
-  s.batches.clear(); s.gather.clear(); s.rows = 0; s.copies = false; s.arena.reset(); s.scanned = false; s.n_tiles = 0;
+  s.batches.clear(); s.gather.clear(); s.ts_jobs.clear(); s.ts_max_rows = 0; s.rows = 0; s.copies = false; s.arena.reset(); s.scanned = false; s.n_tiles = 0;
   for (auto& p : s.retired) if (pane_pool.size() < 16) pane_pool.push_back(std::move(p));
   s.retired.clear(); s.emit_starts.clear(); s.speculative = false; s.add_rows_bound = s.add_bytes_bound = 0; s.rows_launched = 0;
   auto it = std::find(launched_order.begin(), launched_order.end(), s.idx);
@@ -1209,7 +1279,7 @@ void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
   if (need_rows <= R().row_cap && need_bytes <= R().byte_cap) return;
   auto grow = [&](DevBuf& b, size_t elem, uint64_t used, uint64_t cap) { b.regrow_on(stream, (size_t)cap * elem + 64, b.p ? (size_t)used * elem : 0); };
   if (need_rows > R().row_cap) {
-    uint64_t cap = std::max<uint64_t>(need_rows, R().row_cap * 2);
+    uint64_t cap = std::max<uint64_t>(need_rows, R().row_cap + R().row_cap / 2);
     const uint64_t used = std::min(R().rows, R().row_cap);
     grow(R().key_off, 4, used, cap + 1); grow(R().key_valid, 1, used, cap); grow(R().count, 8, used, cap);
     grow(R().mn, 8, used, cap); grow(R().mx, 8, used, cap); grow(R().avg, 8, used, cap); grow(R().sum, 8, used, cap);
@@ -1217,7 +1287,7 @@ void dnz_window::ensure_result_capacity(uint64_t add_rows, uint64_t add_bytes) {
     R().row_cap = cap;
   }
   if (need_bytes > R().byte_cap) {
-    uint64_t cap = std::max<uint64_t>(need_bytes, R().byte_cap * 2);
+    uint64_t cap = std::max<uint64_t>(need_bytes, R().byte_cap + R().byte_cap / 2);
     grow(R().key_bytes, 1, std::min(R().bytes, R().byte_cap), cap);
     R().byte_cap = cap;
   }
@@ -1472,6 +1542,83 @@ void dnz_window::export_device(dnz_device_result* out, bool blocking) {
 
 
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// checkpoint / restore (include/dnz_gpu.h)
+namespace {
+struct CkptHeader {
+  char magic[8];                 // "DNZCKPT1"
+  int64_t window_ms, slide_ms; int32_t n_aggs, flags;          // flags: 1 has_wm, 2 need_nullrows, 4 need_fz, 8 has_lwm
+  int64_t wm, emitted_upto, next_seq, lwm, exported_pane_upto;
+  uint32_t n_groups, null_gid_plus1; uint64_t arena_used, key_bytes_total;
+  int64_t n_panes;
+  // followed by: GidKey[n_groups], arena bytes[round8(arena_used)], then per pane
+  //   { int64 id; int64 has_nullrows; int64 has_fz; GroupState[n_groups]; u64 nullrows[n_groups] (if); u64 fz[n_groups] (if) }
+};
+}  // namespace
+
+void dnz_window::checkpoint(std::vector<char>& blob) {
+  process_pending(); drain();
+  fetch_ctl();
+  for (auto& r : rs) if (r.rows > r.exp_rows) fail(DNZ_ERR_INVALID, "checkpoint with emitted rows that have not been polled");
+  const char* h = h_small.as<char>();
+  CkptHeader H; memset(&H, 0, sizeof H);
+  memcpy(H.magic, "DNZCKPT1", 8);
+  H.window_ms = L; H.slide_ms = S; H.n_aggs = (int32_t)aggs.size();
+  H.flags = (has_wm ? 1 : 0) | (need_nullrows ? 2 : 0) | (need_fz ? 4 : 0) | (has_lwm ? 8 : 0);
+  H.wm = wm; H.emitted_upto = emitted_upto; H.next_seq = next_seq; H.lwm = lwm; H.exported_pane_upto = exported_pane_upto;
+  H.n_groups = n_groups_host; H.null_gid_plus1 = *reinterpret_cast<const uint32_t*>(h + 4);
+  H.arena_used = std::min<uint64_t>(arena_used_host, arena_cap); H.key_bytes_total = key_bytes_total_host;
+  H.n_panes = (int64_t)panes.size();
+  const size_t ng = H.n_groups, ab = round_up(H.arena_used, 8);
+  size_t total = sizeof H + ng * sizeof(GidKey) + ab;
+  for (auto& kv : panes) total += 24 + ng * sizeof(GroupState) + (kv.second->nullrows.p ? ng * 8 : 0) + (kv.second->fz.p ? ng * 8 : 0);
+  blob.resize(total);
+  char* p = blob.data();
+  memcpy(p, &H, sizeof H); p += sizeof H;
+  auto d2h = [&](const void* src, size_t n) { if (n) CK(cudaMemcpy(p, src, n, cudaMemcpyDeviceToHost)); p += n; };
+  d2h(gid_key.p, ng * sizeof(GidKey));
+  d2h(arena.p, ab);
+  for (auto& kv : panes) {
+    int64_t meta[3] = {kv.first, kv.second->nullrows.p ? 1 : 0, kv.second->fz.p ? 1 : 0};
+    memcpy(p, meta, 24); p += 24;
+    d2h(kv.second->st.p, ng * sizeof(GroupState));
+    if (meta[1]) d2h(kv.second->nullrows.p, ng * 8);
+    if (meta[2]) d2h(kv.second->fz.p, ng * 8);
+  }
+}
+
+void dnz_window::restore(const char* blob, size_t bytes) {
+  if (stats.rows_in != 0 || n_groups_host != 0 || !panes.empty()) fail(DNZ_ERR_INVALID, "restore needs a fresh operator");
+  if (bytes < sizeof(CkptHeader)) fail(DNZ_ERR_INVALID, "checkpoint blob too short");
+  CkptHeader H; memcpy(&H, blob, sizeof H);
+  if (memcmp(H.magic, "DNZCKPT1", 8) != 0) fail(DNZ_ERR_INVALID, "not a checkpoint blob");
+  if (H.window_ms != L || H.slide_ms != S || H.n_aggs != (int32_t)aggs.size()) fail(DNZ_ERR_INVALID, "checkpoint was taken with another window / aggregate configuration");
+  const size_t ng = H.n_groups, ab = round_up(H.arena_used, 8);
+  const char* p = blob + sizeof H; const char* end = blob + bytes;
+  auto need = [&](size_t n) { if ((size_t)(end - p) < n) fail(DNZ_ERR_INVALID, "checkpoint blob truncated"); };
+  CK(cudaStreamSynchronize(stream));
+  while (gcap < ng + ng / 8 + 1) dict_grow();                      // (nothing to rehash yet)
+  if (ab + (1 << 20) > arena_cap) arena_grow(ab + (1 << 20));
+  need(ng * sizeof(GidKey)); if (ng) CK(cudaMemcpy(gid_key.p, p, ng * sizeof(GidKey), cudaMemcpyHostToDevice)); p += ng * sizeof(GidKey);
+  need(ab); if (ab) CK(cudaMemcpy(arena.p, p, ab, cudaMemcpyHostToDevice)); p += ab;
+  struct { uint32_t n_groups, null_gid; uint64_t arena_used, key_bytes_total; } c0{H.n_groups, 0u, H.arena_used, H.key_bytes_total};
+  CK(cudaMemcpy(ctl(0), &c0, sizeof c0, cudaMemcpyHostToDevice));
+  CK(launch_dict_restore(dict_view(), H.n_groups, stream)); stats.total_launches++;      // sets null_gid for the NULL-key group
+  need_nullrows = (H.flags & 2) != 0; need_fz = (H.flags & 4) != 0;
+  for (int64_t i = 0; i < H.n_panes; i++) {
+    need(24); int64_t meta[3]; memcpy(meta, p, 24); p += 24;
+    Pane* pn = get_pane(meta[0], true);                              // zero-filled for gcap groups
+    CK(cudaStreamSynchronize(stream));
+    need(ng * sizeof(GroupState)); if (ng) CK(cudaMemcpy(pn->st.p, p, ng * sizeof(GroupState), cudaMemcpyHostToDevice)); p += ng * sizeof(GroupState);
+    if (meta[1]) { if (!pn->nullrows.p) { need_nullrows = true; ensure_side_arrays(pn); CK(cudaStreamSynchronize(stream)); } need(ng * 8); if (ng) CK(cudaMemcpy(pn->nullrows.p, p, ng * 8, cudaMemcpyHostToDevice)); p += ng * 8; }
+    if (meta[2]) { if (!pn->fz.p) { need_fz = true; ensure_side_arrays(pn); CK(cudaStreamSynchronize(stream)); } need(ng * 8); if (ng) CK(cudaMemcpy(pn->fz.p, p, ng * 8, cudaMemcpyHostToDevice)); p += ng * 8; }
+  }
+  has_wm = (H.flags & 1) != 0; wm = H.wm; emitted_upto = H.emitted_upto; next_seq = H.next_seq;
+  has_lwm = (H.flags & 8) != 0; lwm = H.lwm; exported_pane_upto = H.exported_pane_upto;
+  CK(cudaStreamSynchronize(stream));
+  fetch_ctl();
+}
 
 // ------------------------------------------------------------------------------------------------
 // pane exchange (see include/dnz_gpu.h)
@@ -1731,6 +1878,25 @@ int32_t dnz_window_import_partials(dnz_window* w, const uint8_t* entries, const 
   DNZ_CATCH(w)
 }
 
+
+int32_t dnz_window_checkpoint(dnz_window* w, void** blob, int64_t* bytes) {
+  DNZ_TRY(w)
+  if (!blob || !bytes) fail(DNZ_ERR_INVALID, "null out");
+  std::vector<char> b;
+  w->checkpoint(b);
+  void* m = malloc(b.size() ? b.size() : 1);
+  if (!m) fail(DNZ_ERR_NOMEM, "out of host memory");
+  memcpy(m, b.data(), b.size());
+  *blob = m; *bytes = (int64_t)b.size();
+  DNZ_CATCH(w)
+}
+int32_t dnz_window_restore(dnz_window* w, const void* blob, int64_t bytes) {
+  DNZ_TRY(w)
+  if (!blob || bytes <= 0) fail(DNZ_ERR_INVALID, "null blob");
+  w->restore(static_cast<const char*>(blob), (size_t)bytes);
+  DNZ_CATCH(w)
+}
+void dnz_blob_free(void* blob) { free(blob); }
 
 void* dnz_host_alloc(int64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 64)) == cudaSuccess ? p : nullptr; }
 void dnz_host_free(void* p) { if (p) cudaFreeHost(p); }

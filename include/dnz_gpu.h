@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DNZ_ABI_VERSION 1
+#define DNZ_ABI_VERSION 2
 
 /* status codes */
 #define DNZ_OK 0
@@ -34,6 +34,8 @@ extern "C" {
 enum { DNZ_AGG_COUNT = 0, DNZ_AGG_MIN = 1, DNZ_AGG_MAX = 2, DNZ_AGG_AVG = 3, DNZ_AGG_SUM = 4 };
 /* BinaryExpr operators of the post-aggregate DataStream::filter(predicate) (datastream.rs:94-105) */
 enum { DNZ_OP_GT = 0, DNZ_OP_GTE = 1, DNZ_OP_LT = 2, DNZ_OP_LTE = 3, DNZ_OP_EQ = 4, DNZ_OP_NEQ = 5 };
+
+enum { DNZ_TS_CANONICAL = 0, DNZ_TS_INT64_MILLIS = 1, DNZ_TS_INT64_SECONDS = 2, DNZ_TS_STRING_ISO8601 = 3 };   /* TimestampUnit (kafka_config.rs) */
 
 #define DNZ_FLAG_KERNEL_TIMING 1u  /* record CUDA events around every aggregate-kernel launch (dnz_stats) */
 #define DNZ_FLAG_FORCE_GENERIC 2u  /* testing: disable the TMA-staged fast path                           */
@@ -68,6 +70,16 @@ typedef struct {
   int64_t expected_groups;   /* capacity hint (0 = default); tables grow on demand                  */
   int64_t max_rows_per_launch; /* rows aggregated per kernel launch (0 = default 64 Mi)             */
   void* cuda_stream;         /* optional caller-owned cudaStream_t for all work (NULL = own stream) */
+  /* Input-contract producer: where the event time comes from.  DNZ_TS_CANONICAL (0, default): the batch carries
+   * `_streaming_internal_metadata.canonical_timestamp` as the reference's Kafka reader attaches it
+   * (datasource/kafka/kafka_stream_read.rs:222-271).  Otherwise the batch is the RAW decoded batch and the library derives the
+   * canonical timestamp itself, on the device, from top-level column `ts_column` as `array_to_timestamp_array` does
+   * (physical_plan/utils/time.rs:59-94): Int64 milliseconds, Int64 seconds (x 1000) or a Utf8 ISO-8601 string parsed with the
+   * chrono format `ts_format` (NaiveDateTime::parse_from_str(..).and_utc().timestamp_millis()); the constant `barrier_batch`
+   * column is never materialised.  A NULL or unparsable timestamp is DNZ_ERR_DATA (the reference unwraps and panics). */
+  int32_t ts_source;         /* DNZ_TS_* */
+  int32_t ts_column;
+  const char* ts_format;     /* DNZ_TS_STRING_ISO8601 only, e.g. "%Y-%m-%dT%H:%M:%S%.f" */
 } dnz_window_config;
 
 typedef struct dnz_window dnz_window;
@@ -159,6 +171,18 @@ int64_t dnz_window_watermark(const dnz_window* w);
 const char* dnz_window_last_error(const dnz_window* w);
 /* replaces: Drop for GroupedWindowAggStream */
 void dnz_window_destroy(dnz_window* w);
+
+/* ---- checkpoint / restore of the device state ----------------------------------------------------------
+ * replaces: the barrier hook of GroupedWindowAggStream, which serialises its open frames into the state backend and reloads them
+ * at start-up (grouped_window_agg_stream.rs:84-102, :357-417, :631-649; utils/serialization.rs:130-241).  The reference stores
+ * the accumulator states per frame WITHOUT the group keys; this blob is self-contained: stream clock (watermark,
+ * emission horizon, batch sequence), the key dictionary in group-id order (inline keys + long-key arena) and every open pane
+ * (count/sum/min/max states, null-row counts, first-zero marks).  Layout: dnz_window.cu, `CkptHeader`.  Everything that was pushed is
+ * aggregated first; emitted rows must have been polled.  The blob is allocated with malloc and freed with dnz_blob_free.
+ * dnz_window_restore loads it into a FRESH operator created with the same window / aggregate configuration. */
+int32_t dnz_window_checkpoint(dnz_window* w, void** blob, int64_t* bytes);
+int32_t dnz_window_restore(dnz_window* w, const void* blob, int64_t bytes);
+void dnz_blob_free(void* blob);
 
 /* ---- multi-GPU pane exchange: replaces RepartitionExec(Hash(group keys))
  * (physical_optimizer/coalesce_before_streaming_window_aggregate.rs:63-73) when the input is NOT key-partitioned.

@@ -82,6 +82,8 @@ def lib():
         L.orc_synth_fill.restype = C.c_int64
         L.orc_synth_fill.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ts_convert.restype = C.c_int64
+        L.orc_ts_convert.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -282,3 +284,22 @@ def synth_batch(row0, n, *, seed=42, groups=1000, rows_per_ms=1000, t0_ms=1_700_
 def sort_rows(rows):
     """Parity is on the multiset of rows sorted by (window_start, key) (SURVEY.md §8a rule 4)."""
     return sorted(rows, key=lambda r: (r[0], r[1], r[2] is None, r[2] or b"", r[7] if len(r) > 7 else 0))
+
+
+def ts_convert(unit, values=None, strings=None, fmt=None) -> np.ndarray:
+    """array_to_timestamp_array (utils/time.rs:59-94): unit 1 Int64Millis, 2 Int64Seconds, 3 StringIso8601(fmt)."""
+    L = lib()
+    if unit in (1, 2):
+        v = np.ascontiguousarray(values, np.int64)
+        out = np.empty(len(v), np.int64)
+        rc = L.orc_ts_convert(unit, len(v), v.ctypes.data, None, None, None, out.ctypes.data)
+    else:
+        bs = [x if isinstance(x, bytes) else x.encode() for x in strings]
+        off = np.zeros(len(bs) + 1, np.int32)
+        off[1:] = np.cumsum([len(b) for b in bs])
+        kb = np.frombuffer(b"".join(bs) + b"\0", np.uint8).copy()
+        out = np.empty(len(bs), np.int64)
+        rc = L.orc_ts_convert(3, len(bs), None, off.ctypes.data, kb.ctypes.data, fmt.encode(), out.ctypes.data)
+    if rc:
+        raise ValueError(f"row {rc - 1} does not parse")
+    return out

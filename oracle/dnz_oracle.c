@@ -581,3 +581,84 @@ int64_t orc_synth_fill(int64_t row0, int64_t n, uint64_t seed, int64_t groups, i
   }
   return o;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Input-contract producer: canonical event time from a raw column.            */
+/* Restates array_to_timestamp_array (crates/core/src/physical_plan/utils/time.rs:59-94):        */
+/*   Int64Millis   values as they are (the validity bitmap is not consulted)                     */
+/*   Int64Seconds  ts * 1000                                                                     */
+/*   StringIso8601 chrono 0.4 NaiveDateTime::parse_from_str(s, fmt).unwrap().and_utc()           */
+/*                 .timestamp_millis()  (chrono is a crates.io dependency, not under              */
+/*                 /root/reference: published strftime semantics restated for the specifiers      */
+/*                 %Y %m %d %H %M %S %f %.f %3f %6f %9f %.3f %.6f %.9f %% and literals)           */
+/* Returns 0, or the 1-based index of the first row that does not parse (the reference panics).   */
+static int ts_digits_c(const uint8_t* s, int* i, int n, int min_d, int max_d, long long* out) {
+  int d = 0; long long v = 0;
+  while (d < max_d && *i < n && s[*i] >= '0' && s[*i] <= '9') { v = v * 10 + (s[*i] - '0'); (*i)++; d++; }
+  *out = v;
+  return d >= min_d;
+}
+static int ts_parse_c(const uint8_t* s, int n, const char* fmt, long long* out_ms) {
+  long long Y = 1970, mo = 1, D = 1, H = 0, Mi = 0, S = 0, nanos = 0, v;
+  int i = 0;
+  for (const char* f = fmt; *f; f++) {
+    char c = *f;
+    if (c == ' ' || c == '\t' || c == '\n') { while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n')) i++; continue; }
+    if (c != '%') { if (i >= n || s[i] != (uint8_t)c) return 0; i++; continue; }
+    char sp = *++f; int dot = 0, fixed = 0;
+    if (sp == '.') { dot = 1; sp = *++f; }
+    if (sp == '3' || sp == '6' || sp == '9') { fixed = sp - '0'; sp = *++f; }
+    switch (sp) {
+      case 'Y': { int neg = 0; if (i < n && (s[i] == '-' || s[i] == '+')) { neg = s[i] == '-'; i++; } int sg = neg || (i > 0 && s[i - 1] == '+'); if (!ts_digits_c(s, &i, n, 1, sg ? 6 : 4, &v)) return 0; Y = neg ? -v : v; break; }   /* chrono: more than 4 year digits need a sign */
+      case 'm': if (!ts_digits_c(s, &i, n, 1, 2, &v) || v < 1 || v > 12) return 0; mo = v; break;
+      case 'd': if (!ts_digits_c(s, &i, n, 1, 2, &v) || v < 1 || v > 31) return 0; D = v; break;
+      case 'H': if (!ts_digits_c(s, &i, n, 1, 2, &v) || v > 23) return 0; H = v; break;
+      case 'M': if (!ts_digits_c(s, &i, n, 1, 2, &v) || v > 59) return 0; Mi = v; break;
+      case 'S': if (!ts_digits_c(s, &i, n, 1, 2, &v) || v > 60) return 0; S = v; break;
+      case 'f':
+        if (dot) {
+          if (i < n && s[i] == '.') {
+            i++; int d0 = i;
+            if (!ts_digits_c(s, &i, n, fixed ? fixed : 1, fixed ? fixed : 9, &v)) return 0;
+            for (int k = i - d0; k < 9; k++) v *= 10;
+            while (!fixed && i < n && s[i] >= '0' && s[i] <= '9') i++;
+            nanos = v;
+          } else if (fixed) return 0;
+        } else if (fixed) {
+          if (!ts_digits_c(s, &i, n, fixed, fixed, &v)) return 0;
+          for (int k = fixed; k < 9; k++) v *= 10;
+          nanos = v;
+        } else { if (!ts_digits_c(s, &i, n, 1, 9, &v)) return 0; nanos = v; }
+        break;
+      case '%': if (i >= n || s[i] != '%') return 0; i++; break;
+      default: return 0;
+    }
+  }
+  if (i != n) return 0;
+  {
+    int leap = (Y % 4 == 0 && Y % 100 != 0) || Y % 400 == 0;
+    int mdays[12] = {31, leap ? 29 : 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (D > mdays[mo - 1]) return 0;
+  }
+  long long y = mo <= 2 ? Y - 1 : Y;
+  long long era = (y >= 0 ? y : y - 399) / 400, yoe = y - era * 400;
+  long long doy = (153 * (mo + (mo > 2 ? -3 : 9)) + 2) / 5 + D - 1;
+  long long doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  long long days = era * 146097 + doe - 719468;
+  long long secs = days * 86400 + H * 3600 + Mi * 60 + (S == 60 ? 59 : S);
+  if (S == 60) nanos += 1000000000ll;
+  *out_ms = secs * 1000 + nanos / 1000000;
+  return 1;
+}
+int64_t orc_ts_convert(int32_t unit, int64_t n, const int64_t* ints, const int32_t* off, const uint8_t* bytes, const char* fmt, int64_t* out) {
+  for (int64_t i = 0; i < n; i++) {
+    if (unit == 1) out[i] = ints[i];
+    else if (unit == 2) out[i] = ints[i] * 1000;
+    else {
+      long long ms = 0;
+      if (!ts_parse_c(bytes + off[i], off[i + 1] - off[i], fmt, &ms)) return i + 1;
+      out[i] = ms;
+    }
+  }
+  return 0;
+}

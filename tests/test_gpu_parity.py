@@ -325,3 +325,38 @@ def test_device_ready_poll_hands_out_every_row_once():
     want = run_oracle_batches(hb, 1000)
     assert_rows_equal(got, want)
     w.close(); dev.free()
+
+
+@pytest.mark.parametrize("L,S", [(1000, 0), (3000, 1000)])
+def test_checkpoint_restore_resumes_the_stream(L, S):
+    """the device state (dictionary incl. long keys, open panes with null-row counts and first-zero marks, stream
+    clock) survives dnz_window_checkpoint -> a fresh operator -> dnz_window_restore; the resumed stream emits what an
+    uninterrupted one does, batch by batch."""
+    from tests.helpers import gpu_window, to_record_batch, record_batch_rows
+    rng = np.random.default_rng(42 + L)
+    raw = random_stream(rng, 30, 120, 25, span_ms=350, null_frac=0.1)
+    for b in (3, 9, 16, 22):          # +-0.0 / NaN / inf states on both sides of the checkpoint (no f64 overflow: that is summation-order dependent)
+        raw[b] += [(T0 + b * 350 + 7, -0.0, b"zero"), (T0 + b * 350 + 8, 0.0, b"zero"), (T0 + b * 350 + 9, float("nan"), b"nan"),
+                   (T0 + b * 350 + 9, float("inf"), b"inf"), (T0 + b * 350 + 10, None, b"onlynull")]
+    batches = [rows_to_batch(r) for r in raw] + [sentinel(T0 + 30 * 350 + 3 * L)]
+    want = run_oracle_batches(batches, L, S)
+    got = []
+    w = gpu_window(L, S, expected_groups=16)
+    for i, b in enumerate(batches[:14]):
+        w.push(to_record_batch(b)); got += record_batch_rows(w.poll(), i)
+    blob = w.checkpoint()
+    st0 = w.stats()
+    w.close()
+    w2 = gpu_window(L, S)                                  # different capacity hint: the restore sizes the tables itself
+    w2.restore(blob)
+    assert w2.stats()["groups"] == st0["groups"] and w2.watermark is not None
+    for i, b in enumerate(batches[14:], start=14):
+        w2.push(to_record_batch(b)); got += record_batch_rows(w2.poll(), i)
+    w2.close()
+    assert len(blob) > 1000 and len(want) > 50
+    assert_rows_equal(got, want, check_seq=True)
+    from denormalized_b200 import DnzError
+    w3 = gpu_window(L + 1000, S)
+    with pytest.raises(DnzError):                          # another window configuration
+        w3.restore(blob)
+    w3.close()
