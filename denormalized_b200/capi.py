@@ -19,6 +19,7 @@ _SO = os.path.join(_HERE, "libdnz_gpu.so")
 AGG_KINDS = {"count": 0, "min": 1, "max": 2, "avg": 3, "average": 3, "sum": 4}
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 ABI_VERSION = 2
+NO_KEY = -1          # DNZ_NO_KEY: `.window([], aggs, ..)`
 TS_CANONICAL, TS_INT64_MILLIS, TS_INT64_SECONDS, TS_STRING_ISO8601 = 0, 1, 2, 3
 FLAG_KERNEL_TIMING = 1
 FLAG_FORCE_GENERIC = 2
@@ -274,7 +275,7 @@ class GpuStreamingWindow:
         arr = (_Agg * len(aggs))(*[_Agg(AGG_KINDS[k], names.index(col), al) for (k, col, _), al in zip(aggs, self._aliases)])
         ts_source, ts_column, ts_format = timestamp if timestamp else (0, 0, None)      # (TS_* kind, column name, chrono format)
         self._ts_format = ts_format.encode() if ts_format else None
-        cfg = _Config(ABI_VERSION, device, names.index(key), len(aggs), arr, int(window_ms), int(slide_ms or 0), 0, 0, 0, flags, 0.0,
+        cfg = _Config(ABI_VERSION, device, NO_KEY if key is None else names.index(key), len(aggs), arr, int(window_ms), int(slide_ms or 0), 0, 0, 0, flags, 0.0,
                       expected_groups, max_rows_per_launch, cuda_stream, ts_source, names.index(ts_column) if ts_source else 0, self._ts_format)
         if filt is not None:
             alias, op, lit = filt

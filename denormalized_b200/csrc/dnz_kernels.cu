@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_scan(const BatchDesc* __restric
     const BatchDesc bd = batches[lo];
     const int64_t row0 = (t - bd.tile0) * TILE;
     const int n = (int)min((int64_t)TILE, bd.n_rows - row0);
-    const int32_t o_lane = lane < 2 ? bd.off[row0 + (lane ? n : 0)] : 0;      // key byte range: in flight while the timestamps stream
+    const int32_t o_lane = (lane < 2 && bd.off) ? bd.off[row0 + (lane ? n : 0)] : 0;      // key byte range: in flight while the timestamps stream (no key column: ungrouped)
     long long mn = INT64_MAX, mx = INT64_MIN; int cnt = 0;
     const long long* ts = reinterpret_cast<const long long*>(bd.ts) + row0;
     if (!bd.ts_valid && (reinterpret_cast<uintptr_t>(ts) & 15u) == 0) {
@@ -633,6 +633,116 @@ cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n
   if (!n_entries) return cudaSuccess;
   uint64_t gb = (n_entries + 255) / 256; int grid = (int)(gb < 148 * 8 ? gb : 148 * 8);
   k_deferred<<<grid, 256, 0, s>>>(p, n_entries, in);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// k_aggregate_ungrouped: `.window([], aggs, ..)` -- WindowAggStream in Partial mode (streaming_window.rs:640-828): no key, one
+// accumulator set per window.  Pure streaming reduction: a CTA owns a contiguous chunk of tiles, keeps {count, sum, min, max}
+// of the pane it is in in registers, and flushes one set of reductions when the pane changes.  Accumulator semantics are those
+// of DataFusion's row accumulators, NOT of the grouped ones: count of non-null values, sum by plain addition, min / max over
+// IEEE totalOrder (arrow `compute::min/max` + ScalarValue total_cmp: -0.0 < +0.0, NaN above +inf) -- so the state keeps
+// maxk = ord(v) and mink = ~ord(v), both reduced with max, zero = "no value" (decided by the count).
+// State layout per pane: GroupState[0] = {cnt, sum, mink, maxk}; nullrows[0] counts rows whose value is NULL.
+// =================================================================================================
+struct UAcc { double cnt, sum; unsigned long long mink, maxk, nulls; };
+__device__ __forceinline__ void uacc_add(UAcc& a, bool val_ok, double v) {
+  if (!val_ok) { a.nulls++; return; }
+  const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v));
+  a.cnt += 1.0; a.sum += v; a.mink = max(a.mink, ~o); a.maxk = max(a.maxk, o);
+}
+__device__ void uacc_flush(UAcc& a, GroupState* m, GroupState* l, unsigned long long* nm, unsigned long long* nl, double* s_red) {
+  // block reduction (256 threads): warp shuffles, then warp 0 over the 8 partials
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) {
+    a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o); a.sum += __shfl_xor_sync(0xffffffffu, a.sum, o);
+    a.mink = max(a.mink, __shfl_xor_sync(0xffffffffu, a.mink, o)); a.maxk = max(a.maxk, __shfl_xor_sync(0xffffffffu, a.maxk, o));
+    a.nulls += __shfl_xor_sync(0xffffffffu, a.nulls, o);
+  }
+  unsigned long long* s_u = reinterpret_cast<unsigned long long*>(s_red);
+  __syncthreads();
+  if (lane == 0) { s_red[warp * 5 + 0] = a.cnt; s_red[warp * 5 + 1] = a.sum; s_u[warp * 5 + 2] = a.mink; s_u[warp * 5 + 3] = a.maxk; s_u[warp * 5 + 4] = a.nulls; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cnt = 0, sum = 0; unsigned long long mink = 0, maxk = 0, nulls = 0; bool first = true;
+    for (int w = 0; w < 8; w++) {
+      if (s_red[w * 5] != 0.0) { sum = first ? s_red[w * 5 + 1] : sum + s_red[w * 5 + 1]; first = false; cnt += s_red[w * 5]; }
+      mink = max(mink, s_u[w * 5 + 2]); maxk = max(maxk, s_u[w * 5 + 3]); nulls += s_u[w * 5 + 4];
+    }
+    for (int k = 0; k < 2; k++) {
+      GroupState* d = k ? l : m; unsigned long long* dn = k ? nl : nm;
+      if (!d) continue;
+      if (cnt != 0.0) { red_add_f64(&d->cnt, cnt); red_add_f64(&d->sum, sum); red_max_u64(&d->minkey, mink); red_max_u64(&d->maxkey, maxk); }
+      if (nulls && dn) red_add_u64(dn, nulls);
+    }
+  }
+  a.cnt = 0; a.sum = 0; a.mink = 0; a.maxk = 0; a.nulls = 0;
+}
+__global__ void __launch_bounds__(256) k_aggregate_ungrouped(const __grid_constant__ AggParams P) {
+  __shared__ double s_red[8 * 5];
+  const int64_t n_tiles = P.tile_end - P.tile_begin;
+  const int64_t chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = P.tile_begin + (int64_t)blockIdx.x * chunk, t1 = min(P.tile_end, t0 + chunk);
+  UAcc a; a.cnt = 0; a.sum = 0; a.mink = 0; a.maxk = 0; a.nulls = 0;
+  int64_t cur = INT64_MIN;                                  // pane the register accumulators belong to (block-uniform)
+  auto flush = [&]() {
+    if (cur == INT64_MIN) return;
+    const int64_t pi = cur - P.panes.pane0;
+    if (pi >= 0 && pi < P.panes.n_panes) uacc_flush(a, P.panes.main[pi], P.panes.late[pi], P.panes.nullrows_main[pi], P.panes.nullrows_late[pi], s_red);
+    cur = INT64_MIN;
+  };
+  for (int64_t t = t0; t < t1; t++) {
+    const TileDesc td = P.tiles[t];
+    if (td.flags & TILE_EMPTY) continue;
+    const BatchDesc bd = P.batches[td.batch];
+    const bool uniform = (td.flags & TILE_PANE_UNIFORM) != 0 && bd.ts_valid == nullptr;
+    if (uniform && td.pane_lo != cur) { flush(); cur = td.pane_lo; }
+    if (!uniform) flush();
+    for (int r = threadIdx.x; r < td.n_rows; r += blockDim.x) {
+      const int64_t row = (int64_t)td.row0 + r;
+      const bool val_ok = !bd.val_valid || bit_at(bd.val_valid, bd.val_vbit + row);
+      const double v = val_ok ? __ldg(bd.val + row) : 0.0;
+      if (uniform) { uacc_add(a, val_ok, v); continue; }
+      // tile spans panes or has NULL timestamps: per-row reductions (rare)
+      if (bd.ts_valid && !bit_at(bd.ts_valid, bd.ts_vbit + row)) continue;
+      const int64_t pi = bd.ts[row] / P.panes.pane_ms - P.panes.pane0;
+      if (pi < 0 || pi >= P.panes.n_panes) continue;
+      for (int k = 0; k < 2; k++) {
+        GroupState* d = k ? P.panes.late[pi] : P.panes.main[pi]; unsigned long long* dn = k ? P.panes.nullrows_late[pi] : P.panes.nullrows_main[pi];
+        if (!d) continue;
+        if (!val_ok) { if (dn) red_add_u64(dn, 1ull); continue; }
+        const unsigned long long o = ord_bits((unsigned long long)__double_as_longlong(v));
+        red_add_f64(&d->cnt, 1.0); red_add_f64(&d->sum, v); red_max_u64(&d->minkey, ~o); red_max_u64(&d->maxkey, o);
+      }
+    }
+  }
+  flush();
+}
+// one thread per closed window: combine its panes into one partial state (count +, sum + in ascending pane order, mink / maxk max)
+__global__ void k_ungrouped_collect(const UWindow* __restrict__ wins, int n, UState* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const UWindow w = wins[i];
+  UState r; r.cnt = 0; r.sum = 0.0; r.mink = 0; r.maxk = 0; r.nulls = 0;
+  bool first = true;
+  for (int p = 0; p < w.n; p++) {
+    if (!w.st[p]) continue;
+    const GroupState s = *w.st[p];
+    if (s.cnt != 0.0) { r.sum = first ? s.sum : r.sum + s.sum; first = false; r.cnt += (unsigned long long)s.cnt; }
+    r.mink = max(r.mink, s.minkey); r.maxk = max(r.maxk, s.maxkey);
+    if (w.nr[p]) r.nulls += *w.nr[p];
+  }
+  out[i] = r;
+}
+cudaError_t launch_ungrouped_collect(const UWindow* wins, int n, UState* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_ungrouped_collect<<<(n + 63) / 64, 64, 0, s>>>(wins, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_aggregate_ungrouped(const AggParams& p, int sm_count, cudaStream_t s) {
+  const int64_t n_tiles = p.tile_end - p.tile_begin;
+  if (n_tiles <= 0) return cudaSuccess;
+  k_aggregate_ungrouped<<<(unsigned)std::min<int64_t>(n_tiles, (int64_t)sm_count * 8), 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 

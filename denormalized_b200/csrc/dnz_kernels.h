@@ -172,6 +172,11 @@ cudaError_t launch_aggregate(const AggParams& p, int sm_count, cudaStream_t s);
 int aggregate_grid(int64_t n_tiles, int sm_count);
 cudaError_t launch_merge_private(const AggParams& p, int grid, cudaStream_t s);
 cudaError_t launch_aggregate_generic(const AggParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_aggregate_ungrouped(const AggParams& p, int sm_count, cudaStream_t s);
+// ungrouped windows: the panes of one closed window -> one partial state (read back by the host-side Final stage)
+struct UWindow { const GroupState* st[MAX_WINDOW_PANES]; const unsigned long long* nr[MAX_WINDOW_PANES]; int32_t n, pad; };
+struct UState { unsigned long long cnt; double sum; unsigned long long mink, maxk, nulls; };
+cudaError_t launch_ungrouped_collect(const UWindow* wins, int n, UState* out, cudaStream_t s);
 cudaError_t launch_deferred(const AggParams& p, const DeferEntry* in, uint64_t n_entries, cudaStream_t s);
 cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);

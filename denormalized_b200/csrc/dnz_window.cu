@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -288,6 +289,22 @@ struct dnz_window {
   cudaStream_t d2h_stream = nullptr;
   bool res_consumed = false;
 
+  // ungrouped windows `.window([], aggs, ..)`: the device reduces rows into panes; the Partial stage's per-batch
+  // emission schedule and the whole Final stage (streaming_window.rs:882-1051) run on the host over one 40 B state per window
+  bool ungrouped = false;
+  std::set<int64_t> u_created;                  // Partial frames that exist (window starts)
+  struct UEmission { std::vector<std::vector<int64_t>> pbs; size_t first = 0, count = 0; cudaEvent_t ev = nullptr; };
+  std::deque<UEmission> u_pending;              // emissions whose partial states are on their way to the host
+  std::vector<cudaEvent_t> u_event_pool;
+  DevBuf d_uwins, d_ustates; PinnedBuf h_uwins, h_ustates; size_t u_ring = 0, u_head = 0;   // UState / UWindow slots, bump-allocated; reset when nothing is pending
+  struct UFrame { int64_t end = 0; uint64_t cnt = 0; double sum = 0; bool has = false; double mn = 0, mx = 0; };
+  std::map<int64_t, UFrame> u_final; std::set<int64_t> u_seen; bool u_has_fwm = false; int64_t u_fwm = 0;
+  struct URow { int64_t ws, we; int64_t cnt; double mn, mx, avg, sum; bool valid; };
+  std::vector<URow> u_out;
+  void ungrouped_collect(bool wait);
+  void ungrouped_final(const std::vector<URow>& pb);
+  void export_ungrouped(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking);
+
   // multi-GPU pane exchange
   int rank = 0, world = 1;
   bool fused = false;                             // attached to a dnz_group: launches stay asynchronous, emission happens in the group step
@@ -333,6 +350,7 @@ struct dnz_window {
   void prealloc();
   struct Run { size_t b0, b1; bool dirty; int64_t horizon, wm_after; };
   void plan_runs(Slot& s, const std::vector<BatchMinMax>& mm, std::vector<Run>& runs);
+  void ungrouped_emit_run(Slot* sl, const std::vector<BatchMinMax>* mm, const Run* r, int64_t flush_wm);
   struct RunGeom { int64_t t0 = 0, t1 = 0, pmin = INT64_MAX, pmax = INT64_MIN, rows = 0; double alg_bytes = 0; bool val_nulls = false; };
   RunGeom run_geometry(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r);
   void prepare_panes(Slot& s, const std::vector<BatchMinMax>& mm, const Run& r, const RunGeom& g);
@@ -445,11 +463,16 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   if (c->n_aggs <= 0 || !c->aggs) fail(DNZ_ERR_INVALID, "no aggregate expressions");
   if (!schema->format || strcmp(schema->format, "+s") != 0) fail(DNZ_ERR_INVALID, "input schema must be a struct (RecordBatch)");
   n_input_cols = (int)schema->n_children;
-  if (c->key_column < 0 || c->key_column >= n_input_cols) fail(DNZ_ERR_INVALID, "key_column out of range");
-  key_col = c->key_column;
-  const ArrowSchema* ks = schema->children[key_col];
-  if (strcmp(ks->format, "u") != 0) fail(DNZ_ERR_UNSUPPORTED, "group key column '%s' has format '%s'; only Utf8 keys are implemented", ks->name, ks->format);
-  key_name = ks->name ? ks->name : "key";
+  if (c->key_column == DNZ_NO_KEY) {       // `.window([], aggs, ..)`: WindowAggStream (Partial) -> FullWindowAggStream (Final)
+    ungrouped = true; key_col = -1; key_name = "";
+    if (c->has_filter) fail(DNZ_ERR_UNSUPPORTED, "a fused filter on an ungrouped window is not implemented");
+  } else {
+    if (c->key_column < 0 || c->key_column >= n_input_cols) fail(DNZ_ERR_INVALID, "key_column out of range");
+    key_col = c->key_column;
+    const ArrowSchema* ks = schema->children[key_col];
+    if (strcmp(ks->format, "u") != 0) fail(DNZ_ERR_UNSUPPORTED, "group key column '%s' has format '%s'; only Utf8 keys are implemented", ks->name, ks->format);
+    key_name = ks->name ? ks->name : "key";
+  }
   val_col = -1;
   for (int i = 0; i < c->n_aggs; i++) {
     const dnz_agg& a = c->aggs[i];
@@ -525,8 +548,15 @@ void dnz_window::init(const dnz_window_config* c, const ArrowSchema* schema) {
   uint64_t eg = c->expected_groups > 0 ? (uint64_t)c->expected_groups : (1ull << 16);
   uint64_t g0 = 1024; while (g0 < eg + eg / 8) g0 <<= 1;
   if (g0 > (1ull << 29)) fail(DNZ_ERR_INVALID, "expected_groups too large");
+  if (ungrouped) g0 = 1024;
   dict_alloc((uint32_t)g0);
   arena_cap = 1 << 20; arena.alloc(arena_cap);
+  if (ungrouped) {
+    need_nullrows = true;
+    u_ring = 4096;
+    d_uwins.alloc(u_ring * sizeof(UWindow)); d_ustates.alloc(u_ring * sizeof(UState));
+    h_uwins.reserve(u_ring * sizeof(UWindow)); h_ustates.reserve(u_ring * sizeof(UState));
+  }
   prealloc();
   CK(cudaStreamSynchronize(stream));
 }
@@ -720,8 +750,8 @@ void dnz_window::push_host(ArrowArray* batch) {
   pb.d.n_rows = n; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
   if (n > 0) {
     const int64_t po = batch->offset;
-    const ArrowArray* key = batch->children[key_col];
     const ArrowArray* val = batch->children[val_col];
+    const ArrowArray* key = ungrouped ? val : batch->children[key_col];
     const ArrowArray* meta = ts_source == DNZ_TS_CANONICAL ? batch->children[meta_col] : nullptr;
     const ArrowArray* ts = meta ? meta->children[ts_child] : batch->children[ts_col];
     if (key->length < po + n || val->length < po + n || ts->length < po + (meta ? meta->offset : 0) + n) fail(DNZ_ERR_INVALID, "child arrays shorter than the batch");
@@ -786,6 +816,7 @@ void dnz_window::push_host(ArrowArray* batch) {
     pb.d.val = (const double*)copy_in((const double*)buf_at(val, 1) + vo, (size_t)n * 8);
     copy_bitmap(val, vo, pb.d.val_valid, pb.d.val_vbit);
     // keys
+    if (!ungrouped) {
     int64_t ko = po + key->offset;
     const int32_t* hoff = (const int32_t*)buf_at(key, 1) + ko;
     pb.d.off = (const int32_t*)copy_in(hoff, (size_t)(n + 1) * 4);
@@ -797,6 +828,7 @@ void dnz_window::push_host(ArrowArray* batch) {
     if (o1 > a0) enqueue_copy(db, hb + a0, (size_t)(o1 - a0));
     pb.d.bytes = db - a0;     // only [o0, o1) is ever dereferenced
     copy_bitmap(key, ko, pb.d.key_valid, pb.d.key_vbit);
+    }
     c.copies = true;
   }
   pb.has_moved = true; pb.moved = *batch; batch->release = nullptr;   // moved
@@ -811,12 +843,12 @@ void dnz_window::push_dev(const dnz_device_batch* b, int64_t nb) {
     const dnz_device_batch& s = b[i];
     if (s.n_rows < 0) fail(DNZ_ERR_INVALID, "device batch %lld: negative row count", (long long)i);
     if (s.n_rows >= (1ll << 31)) fail(DNZ_ERR_UNSUPPORTED, "batch with >= 2^31 rows");
-    if (s.n_rows > 0 && (!s.ts || !s.val || !s.key_off || !s.key_bytes)) fail(DNZ_ERR_INVALID, "device batch %lld: null column pointer", (long long)i);
+    if (s.n_rows > 0 && (!s.ts || !s.val || (!ungrouped && (!s.key_off || !s.key_bytes)))) fail(DNZ_ERR_INVALID, "device batch %lld: null column pointer", (long long)i);
     if (cur().rows > 0 && cur().rows + s.n_rows > max_rows) seal_current();
     Slot& c = cur();
     PendingBatch pb;
-    pb.d.ts = s.ts; pb.d.val = s.val; pb.d.off = s.key_off; pb.d.bytes = s.key_bytes;
-    pb.d.ts_valid = s.ts_valid; pb.d.val_valid = s.val_valid; pb.d.key_valid = s.key_valid;
+    pb.d.ts = s.ts; pb.d.val = s.val; pb.d.off = ungrouped ? nullptr : s.key_off; pb.d.bytes = ungrouped ? nullptr : s.key_bytes;
+    pb.d.ts_valid = s.ts_valid; pb.d.val_valid = s.val_valid; pb.d.key_valid = ungrouped ? nullptr : s.key_valid;
     pb.d.n_rows = s.n_rows; pb.d.seq = next_seq++; pb.d.flags = BATCH_BULK_OK;
     pb.key_bytes = -1;
     c.batches.push_back(pb);
@@ -1055,7 +1087,7 @@ void dnz_window::launch_aggregate_pass(Slot& s, const RunGeom& g, AggParams& P, 
   const int64_t np = g.pmax - g.pmin + 1;
   const int agg_grid = aggregate_grid(g.t1 - g.t0, sm_count);
   const size_t priv_bytes = (size_t)agg_grid * (size_t)np * gcap * sizeof(GroupState);
-  const bool use_priv = !dirty && gcap <= 8192 && priv_bytes <= (256ull << 20) && !(cfg.flags & (DNZ_FLAG_FORCE_GENERIC | DNZ_FLAG_NO_PRIVATE));
+  const bool use_priv = !ungrouped && !dirty && gcap <= 8192 && priv_bytes <= (256ull << 20) && !(cfg.flags & (DNZ_FLAG_FORCE_GENERIC | DNZ_FLAG_NO_PRIVATE));
   if (use_priv) {
     d_priv.reserve(priv_bytes);
     CK(cudaMemsetAsync(d_priv.p, 0, priv_bytes, stream));
@@ -1063,7 +1095,8 @@ void dnz_window::launch_aggregate_pass(Slot& s, const RunGeom& g, AggParams& P, 
   }
   s.timed = (cfg.flags & DNZ_FLAG_KERNEL_TIMING) != 0; s.alg_bytes = g.alg_bytes;
   if (s.timed) CK(cudaEventRecord(s.ev0, stream));
-  if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
+  if (ungrouped) CK(launch_aggregate_ungrouped(P, sm_count, stream));
+  else if (cfg.flags & DNZ_FLAG_FORCE_GENERIC) CK(launch_aggregate_generic(P, sm_count, stream));
   else CK(launch_aggregate(P, sm_count, stream));
   if (use_priv) { CK(launch_merge_private(P, agg_grid, stream)); stats.total_launches++; }
   if (s.timed) CK(cudaEventRecord(s.ev1, stream));
@@ -1130,6 +1163,16 @@ void dnz_window::execute_run_sync(Slot& s, const std::vector<BatchMinMax>& mm, c
   }
   g_tr.mark("post_agg");
   // ---- process_watermark + trigger_windows
+  if (ungrouped) {
+    ungrouped_emit_run(nullptr, &mm, &r, 0);
+    if (r.dirty) {
+      CK(cudaStreamSynchronize(stream));
+      for (auto& kv : late_panes) if (pane_pool.size() < 16) pane_pool.push_back(std::move(kv.second));
+      late_panes.clear();
+    }
+    g_tr.mark("emit");
+    return;
+  }
   if (r.dirty) {
     // windows that were already emitted (end <= horizon) and received rows from this batch are re-opened and emitted
     // again immediately with ONLY this batch's rows (§8a-3)
@@ -1189,6 +1232,7 @@ void dnz_window::launch_slot(Slot& s) {
           s.speculative = true; s.t0 = g.t0; s.t1 = g.t1; s.pmin = g.pmin; s.pmax = g.pmax; s.rows_launched = g.rows;
         }
         if (world > 1) { if (!has_lwm || lwm <= r.wm_after) lwm = r.wm_after; has_lwm = true; }   // fused exchange: the group step emits under the GLOBAL watermark
+        else if (ungrouped) ungrouped_emit_run(&s, &mm, &r, 0);
         else emit_normal(r.wm_after, true, &s);
         g_tr.mark("emit");
       }
@@ -1368,7 +1412,7 @@ void dnz_window::emit_windows(const std::vector<int64_t>& starts, const std::map
 // ------------------------------------------------------------------------------------------------
 void dnz_window::fill_schema(ArrowSchema* schema) {
   auto* sp = new SchemaPrivate();
-  size_t nc = 1 + aggs.size() + 2;
+  size_t nc = (ungrouped ? 0 : 1) + aggs.size() + 2;
   sp->names.reserve(nc);
   auto add = [&](const std::string& name, const char* fmt, int64_t flags) {
     sp->names.push_back(name);
@@ -1377,7 +1421,7 @@ void dnz_window::fill_schema(ArrowSchema* schema) {
     c->format = fmt; c->flags = flags; c->release = release_child_schema;
     sp->children.push_back(std::move(c));
   };
-  add(key_name, "u", ARROW_FLAG_NULLABLE);
+  if (!ungrouped) add(key_name, "u", ARROW_FLAG_NULLABLE);
   for (size_t i = 0; i < aggs.size(); i++) add(aliases[i], agg_format(aggs[i].kind), aggs[i].kind == DNZ_AGG_COUNT ? 0 : ARROW_FLAG_NULLABLE);
   add("window_start_time", "tsm:", 0);     // continuous/mod.rs:42-62: Timestamp(ms, None), non-null
   add("window_end_time", "tsm:", 0);
@@ -1393,6 +1437,7 @@ void dnz_window::fill_schema(ArrowSchema* schema) {
 // snapshot has fired; the non-blocking poll simply leaves rows of still-running emits for the next call.  The device->host
 // copies run on their own stream, never behind queued input.
 void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking) {
+  if (ungrouped) { export_ungrouped(out, schema, has_output, blocking); return; }
   if (blocking) { CK(cudaStreamSynchronize(stream)); }
   else {
     while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
@@ -1506,6 +1551,7 @@ void dnz_window::export_arrow(ArrowArray* out, ArrowSchema* schema, int32_t* has
 // key_off entries are offsets into `key_bytes` (the set's byte buffer); key_bytes_len is the offset at which the last returned
 // key ends.
 void dnz_window::export_device(dnz_device_result* out, bool blocking) {
+  if (ungrouped) fail(DNZ_ERR_UNSUPPORTED, "ungrouped windows finish on the host (Final stage): use dnz_window_poll / dnz_window_poll_ready");
   memset(out, 0, sizeof *out);
   ResultSet* r = nullptr; uint64_t r0 = 0, r1 = 0, b1 = 0;
   if (blocking) fetch_ctl();
@@ -1544,6 +1590,185 @@ void dnz_window::export_device(dnz_device_result* out, bool blocking) {
 // ------------------------------------------------------------------------------------------------
 
 // ------------------------------------------------------------------------------------------------
+// ungrouped windows (include/dnz_gpu.h, DNZ_NO_KEY)
+namespace {
+// get_windows_for_watermark (streaming_window.rs:1053-1086), whole-second snap (:1088-1094): the frames a batch creates
+void reference_windows(int64_t mn, int64_t mx, int64_t L, int64_t S, std::vector<int64_t>& out) {
+  auto snap = [&](int64_t ts) { const int64_t wl = L / 1000, t = ts / 1000; return (t / wl) * wl * 1000; };
+  if (S > 0) { for (int64_t cur = snap(mn - L); cur <= mx; cur += S) { const int64_t end = cur + L; if (mn > end || mx < cur) continue; out.push_back(cur); } }
+  else for (int64_t cur = snap(mn); cur <= mx; cur += L) out.push_back(cur);
+}
+inline unsigned long long unord_bits_h(unsigned long long o) { return (o & 0x8000000000000000ull) ? (o & ~0x8000000000000000ull) : ~o; }
+inline int total_cmp_d(double a, double b) {
+  long long x, y; memcpy(&x, &a, 8); memcpy(&y, &b, 8);
+  x ^= (long long)(((unsigned long long)(x >> 63)) >> 1); y ^= (long long)(((unsigned long long)(y >> 63)) >> 1);
+  return x < y ? -1 : x > y ? 1 : 0;
+}
+}  // namespace
+
+// The Partial stage's emission schedule for one run (or a flush): per batch, the frames it creates and the frames its watermark
+// closes -- one "partial batch" (PB) per batch, exactly what WindowAggStream::trigger_windows hands to the Final stage -- and the
+// collection of the closed windows' states from the device (one kernel + one small D2H per run).
+void dnz_window::ungrouped_emit_run(Slot* sl, const std::vector<BatchMinMax>* mm, const Run* r, int64_t flush_wm) {
+  UEmission em;
+  std::vector<std::pair<int64_t, bool>> wins;          // (window start, from the late panes)
+  auto close_upto = [&](int64_t w, int64_t horizon, bool dirty) {
+    std::vector<int64_t> pb;
+    for (auto it = u_created.begin(); it != u_created.end();) {
+      if (*it + L <= w) { pb.push_back(*it); wins.emplace_back(*it, dirty && *it + L <= horizon); it = u_created.erase(it); } else ++it;
+    }
+    if (!pb.empty()) em.pbs.push_back(std::move(pb));
+  };
+  if (r) {
+    std::vector<int64_t> tmp;
+    for (size_t i = r->b0; i < r->b1; i++) {
+      const BatchMinMax& b = (*mm)[i];
+      if (b.n_valid == 0) continue;
+      tmp.clear(); reference_windows(b.ts_min, b.ts_max, L, S, tmp);
+      for (int64_t st : tmp) u_created.insert(st);
+      if (!has_wm || wm <= b.ts_min) { wm = b.ts_min; has_wm = true; }       // process_watermark
+      close_upto(wm, r->horizon, r->dirty);
+    }
+  } else {                                             // dnz_window_flush (tests): one trigger at the given watermark
+    if (!has_wm || wm <= flush_wm) { wm = flush_wm; has_wm = true; }
+    close_upto(wm, 0, false);
+  }
+  if (!wins.empty()) {
+    const size_t n = wins.size();
+    if (n > u_ring) fail(DNZ_ERR_UNSUPPORTED, "%zu windows closed by one run (limit %zu)", n, u_ring);
+    if (u_head + n > u_ring) { ungrouped_collect(true); u_head = 0; }              // staging full: take in what is on its way first
+    const size_t at = u_head;
+    UWindow* hw = h_uwins.as<UWindow>() + at;
+    for (size_t i = 0; i < n; i++) {
+      UWindow& W = hw[i]; memset(&W, 0, sizeof W);
+      const int64_t p0 = wins[i].first / pane_ms;
+      W.n = panes_per_window;
+      for (int j = 0; j < panes_per_window; j++) {
+        Pane* pn = nullptr;
+        if (wins[i].second) { auto it = late_panes.find(p0 + j); if (it != late_panes.end()) pn = it->second.get(); }
+        else pn = find_pane(p0 + j);
+        W.st[j] = pn ? pn->st.as<GroupState>() : nullptr; W.nr[j] = pn ? pn->nullrows.as<unsigned long long>() : nullptr;
+      }
+    }
+    CK(cudaMemcpyAsync(d_uwins.as<UWindow>() + at, hw, n * sizeof(UWindow), cudaMemcpyHostToDevice, stream));
+    CK(launch_ungrouped_collect(d_uwins.as<UWindow>() + at, (int)n, d_ustates.as<UState>() + at, stream)); stats.total_launches++;
+    CK(cudaMemcpyAsync(h_ustates.as<UState>() + at, d_ustates.as<UState>() + at, n * sizeof(UState), cudaMemcpyDeviceToHost, stream));
+    if (u_event_pool.empty()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); u_event_pool.push_back(e); }
+    em.ev = u_event_pool.back(); u_event_pool.pop_back();
+    CK(cudaEventRecord(em.ev, stream));
+    em.first = at; em.count = n; u_head += n;
+    stats.windows_emitted += (int64_t)n;
+    u_pending.push_back(std::move(em));
+  }
+  emitted_upto = std::max(emitted_upto, wm);
+  retire_panes(sl);
+}
+
+// FullWindowAggStream::poll_next_inner (streaming_window.rs:934-1032) for one partial batch
+void dnz_window::ungrouped_final(const std::vector<URow>& pb) {
+  if (pb.empty()) return;
+  int64_t start = pb[0].ws, end = pb[0].we;
+  for (const URow& x : pb) { start = std::max(start, x.ws); end = std::max(end, x.we); }      // "these batches should only have 1 row"
+  const bool cached = u_final.count(start) != 0;
+  if (u_seen.count(start) && !cached) return;                                                // late data for a finalized window: dropped
+  UFrame& f = u_final[start];
+  if (!cached) f.end = end;
+  u_seen.insert(start);
+  for (const URow& x : pb) {                               // merge_batch of every row of the batch into THAT frame
+    f.cnt += (uint64_t)x.cnt;
+    if (x.valid) {
+      f.sum += x.sum;
+      if (!f.has) { f.mn = x.mn; f.mx = x.mx; f.has = true; }
+      else { if (total_cmp_d(x.mn, f.mn) < 0) f.mn = x.mn; if (total_cmp_d(x.mx, f.mx) > 0) f.mx = x.mx; }
+    }
+  }
+  if (!u_has_fwm || start > u_fwm) { u_fwm = start; u_has_fwm = true; }
+  for (auto it = u_final.begin(); it != u_final.end();) {                                    // finalize_windows: watermark > window end
+    if (u_fwm > it->second.end) {
+      const UFrame& g = it->second;
+      u_out.push_back(URow{it->first, g.end, (int64_t)g.cnt, g.has ? g.mn : 0.0, g.has ? g.mx : 0.0, g.has ? g.sum / (double)g.cnt : 0.0, g.sum, g.has});
+      it = u_final.erase(it);
+    } else ++it;
+  }
+}
+
+// feed the partial batches whose states have arrived to the Final stage (in emission order)
+void dnz_window::ungrouped_collect(bool wait) {
+  while (!u_pending.empty()) {
+    UEmission& em = u_pending.front();
+    if (wait) CK(cudaEventSynchronize(em.ev));
+    else if (cudaEventQuery(em.ev) != cudaSuccess) { cudaGetLastError(); break; }
+    const UState* st = h_ustates.as<UState>() + em.first;
+    size_t k = 0;
+    for (const auto& pb : em.pbs) {
+      std::vector<URow> rows;
+      for (int64_t ws : pb) {
+        const UState& u = st[k++];
+        URow x; x.ws = ws; x.we = ws + L; x.cnt = (int64_t)u.cnt; x.valid = u.cnt != 0; x.sum = u.sum; x.avg = 0;
+        unsigned long long bmn = unord_bits_h(~u.mink), bmx = unord_bits_h(u.maxk);
+        memcpy(&x.mn, &bmn, 8); memcpy(&x.mx, &bmx, 8);
+        rows.push_back(x);
+      }
+      ungrouped_final(rows);
+    }
+    u_event_pool.push_back(em.ev);
+    u_pending.pop_front();
+    if (u_pending.empty()) u_head = 0;
+  }
+}
+
+void dnz_window::export_ungrouped(ArrowArray* out, ArrowSchema* schema, int32_t* has_output, bool blocking) {
+  if (blocking) CK(cudaStreamSynchronize(stream));
+  else { while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]); cudaGetLastError(); }
+  ungrouped_collect(blocking);
+  const size_t n = u_out.size();
+  auto* ep = new ExportPrivate();
+  std::unique_ptr<ExportPrivate> guard(ep);
+  const size_t total = 8 * round_up(n * 8 + 8, 64) + round_up((n + 7) / 8 + 8, 64) + 1024;
+  ep->block = g_pinned_pool.get(total, ep->block_cap);
+  size_t used = 0;
+  auto take = [&](size_t bytes) -> void* { void* p = (char*)ep->block + used; used += round_up(std::max<size_t>(bytes, 8), 64); return p; };
+  int64_t* cnt = (int64_t*)take(n * 8); double* mn = (double*)take(n * 8); double* mx = (double*)take(n * 8); double* avg = (double*)take(n * 8);
+  double* sum = (double*)take(n * 8); int64_t* ws = (int64_t*)take(n * 8); int64_t* we = (int64_t*)take(n * 8);
+  uint8_t* bm = (uint8_t*)take((n + 7) / 8 + 8); memset(bm, 0, (n + 7) / 8 + 8);
+  int64_t nulls = 0;
+  for (size_t i = 0; i < n; i++) {
+    const URow& x = u_out[i];
+    cnt[i] = x.cnt; mn[i] = x.mn; mx[i] = x.mx; avg[i] = x.avg; sum[i] = x.valid ? x.sum : 0.0; ws[i] = x.ws; we[i] = x.we;
+    if (x.valid) bm[i >> 3] |= (uint8_t)(1u << (i & 7)); else nulls++;
+  }
+  uint8_t* abm = nulls ? bm : nullptr;
+  auto add_child = [&](std::vector<const void*> bufs, int64_t nl) {
+    ep->buffers.push_back(std::move(bufs));
+    auto c = std::make_unique<ArrowArray>(); memset(c.get(), 0, sizeof(ArrowArray));
+    c->length = (int64_t)n; c->null_count = nl; c->n_buffers = (int64_t)ep->buffers.back().size();
+    c->buffers = ep->buffers.back().data(); c->release = release_child;
+    ep->children.push_back(std::move(c));
+  };
+  ep->buffers.reserve(aggs.size() + 4);
+  for (auto& a : aggs) {
+    switch (a.kind) {
+      case DNZ_AGG_COUNT: add_child({nullptr, cnt}, 0); break;
+      case DNZ_AGG_MIN: add_child({abm, mn}, nulls); break;
+      case DNZ_AGG_MAX: add_child({abm, mx}, nulls); break;
+      case DNZ_AGG_AVG: add_child({abm, avg}, nulls); break;
+      default: add_child({abm, sum}, nulls); break;
+    }
+  }
+  add_child({nullptr, ws}, 0); add_child({nullptr, we}, 0);
+  for (auto& c : ep->children) ep->child_ptrs.push_back(c.get());
+  ep->buffers.push_back({nullptr});
+  memset(out, 0, sizeof(*out));
+  out->length = (int64_t)n; out->n_buffers = 1; out->buffers = ep->buffers.back().data();
+  out->n_children = (int64_t)ep->children.size(); out->children = ep->child_ptrs.data(); out->release = release_array;
+  out->private_data = guard.release();
+  if (schema) fill_schema(schema);
+  if (has_output) *has_output = n > 0;
+  stats.rows_out += (int64_t)n;
+  u_out.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
 // checkpoint / restore (include/dnz_gpu.h)
 namespace {
 struct CkptHeader {
@@ -1558,6 +1783,7 @@ struct CkptHeader {
 }  // namespace
 
 void dnz_window::checkpoint(std::vector<char>& blob) {
+  if (ungrouped) fail(DNZ_ERR_UNSUPPORTED, "checkpoint of an ungrouped window is not implemented");
   process_pending(); drain();
   fetch_ctl();
   for (auto& r : rs) if (r.rows > r.exp_rows) fail(DNZ_ERR_INVALID, "checkpoint with emitted rows that have not been polled");
@@ -1808,7 +2034,8 @@ int32_t dnz_window_flush(dnz_window* w, int64_t watermark_ms) {
   w->process_pending(); w->drain();
   if (w->res_consumed) w->reset_results();
   w->rotate_result_sets();
-  w->emit_normal(watermark_ms, false, nullptr);
+  if (w->ungrouped) w->ungrouped_emit_run(nullptr, nullptr, nullptr, watermark_ms);
+  else w->emit_normal(watermark_ms, false, nullptr);
   DNZ_CATCH(w)
 }
 
@@ -1835,6 +2062,7 @@ void dnz_window_destroy(dnz_window* w) { delete w; }
 int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
   DNZ_TRY(w)
   if (world < 1 || rank < 0 || rank >= world) fail(DNZ_ERR_INVALID, "bad rank/world");
+  if (w->ungrouped && world > 1) fail(DNZ_ERR_UNSUPPORTED, "ungrouped windows have no key to partition by");
   if (world > MAX_WORLD) fail(DNZ_ERR_UNSUPPORTED, "world > %d", MAX_WORLD);
   if (w->stats.rows_in > 0 && world != w->world) fail(DNZ_ERR_INVALID, "set_exchange must precede the first batch");
   w->rank = rank; w->world = world;

@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define DNZ_ABI_VERSION 2
+#define DNZ_NO_KEY (-1)           /* key_column: no group key -- `.window([], aggs, ..)`, the ungrouped window */
 
 /* status codes */
 #define DNZ_OK 0
@@ -57,7 +58,13 @@ typedef struct {
   uint32_t abi_version;      /* DNZ_ABI_VERSION                                                     */
   int32_t device;            /* CUDA device ordinal                                                 */
   int32_t key_column;        /* top-level index of the Utf8 group-key column (one plain column,
-                                planner/streaming_window.rs:36-66)                                  */
+                                planner/streaming_window.rs:36-66), or DNZ_NO_KEY: the ungrouped window --
+                                one partition of the Partial -> Final chain the planner builds for an empty
+                                group_by (planner/streaming_window.rs:133-153; WindowAggStream
+                                streaming_window.rs:640-828 on the device, FullWindowAggStream :882-1051 on
+                                the host over one 40 B state per window).  Output: aggregates, window_start_time,
+                                window_end_time; a window is emitted once a window that starts after its end has
+                                closed (the reference's Final stage), late partial results are dropped.  */
   int32_t n_aggs;
   const dnz_agg* aggs;
   int64_t window_ms;         /* PhysicalStreamingWindowType::{Tumbling(len) | Sliding(len, slide)}  */

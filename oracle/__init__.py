@@ -82,6 +82,15 @@ def lib():
         L.orc_synth_fill.restype = C.c_int64
         L.orc_synth_fill.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_u_create.restype = C.c_void_p
+        L.orc_u_create.argtypes = [C.POINTER(_Config)]
+        L.orc_u_destroy.argtypes = [C.c_void_p]
+        L.orc_u_push.restype = C.c_int64
+        L.orc_u_push.argtypes = [C.c_void_p, C.POINTER(_Batch)]
+        L.orc_u_get_results.argtypes = [C.c_void_p, C.POINTER(_Result)]
+        L.orc_u_clear_results.argtypes = [C.c_void_p]
+        L.orc_u_last_error.restype = C.c_char_p
+        L.orc_u_last_error.argtypes = [C.c_void_p]
         L.orc_ts_convert.restype = C.c_int64
         L.orc_ts_convert.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
         _lib = L
@@ -132,7 +141,7 @@ def _rows(res: _Result):
     def arr(ptr, dt, m):
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(m * np.dtype(dt).itemsize,)).view(dt).copy()
     off = arr(res.key_off, np.int32, n + 1)
-    kb = arr(res.key_bytes, np.uint8, max(int(off[-1]), 1)).tobytes()
+    kb = arr(res.key_bytes, np.uint8, max(int(off[-1]), 1)).tobytes() if res.key_bytes else b""
     knull = arr(res.key_isnull, np.uint8, n)
     cnt = arr(res.count, np.int64, n)
     mn, mx, av = arr(res.min, np.float64, n), arr(res.max, np.float64, n), arr(res.avg, np.float64, n)
@@ -199,6 +208,41 @@ class OracleWindow:
     def close(self):
         if self._h:
             self._L.orc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleUngrouped:
+    """`.window([], aggs, ..)`: one partition of the Partial -> Final chain (rows: key is always None)."""
+
+    def __init__(self, window_ms, slide_ms=0):
+        self._L = lib()
+        cfg = _mkcfg(window_ms, slide_ms, None)
+        self._h = self._L.orc_u_create(C.byref(cfg))
+
+    def push(self, b: Batch) -> int:
+        cb = b._c()
+        r = self._L.orc_u_push(self._h, C.byref(cb))
+        if r < 0:
+            raise RuntimeError(self._L.orc_u_last_error(self._h).decode())
+        return int(r)
+
+    def results(self, clear=True):
+        res = _Result()
+        self._L.orc_u_get_results(self._h, C.byref(res))
+        rows = _rows(res)
+        if clear:
+            self._L.orc_u_clear_results(self._h)
+        return rows
+
+    def close(self):
+        if self._h:
+            self._L.orc_u_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -662,3 +662,128 @@ int64_t orc_ts_convert(int32_t unit, int64_t n, const int64_t* ints, const int32
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Ungrouped windows: `.window([], aggs, len, slide)`.                          */
+/* planner/streaming_window.rs:133-153 builds StreamingWindowExec(Partial) -> StreamingWindowExec */
+/* (Final); one partition of that chain is restated here:                                        */
+/*   WindowAggStream::poll_next_inner   streaming_window.rs:791-828  (Partial: per-batch windows,  */
+/*                                       PartialWindowAggFrame::push = two filters + aggregate_batch)*/
+/*   FullWindowAggStream::poll_next_inner :934-1032 (Final: frame keyed by the MAX window start of  */
+/*                                       the incoming batch, seen_windows late drop, finalize when  */
+/*                                       watermark > window end, watermark = max window START seen) */
+/* Row accumulators of DataFusion 42 (not the grouped ones): CountAccumulator; Min/MaxAccumulator   */
+/* = arrow compute::min/max + ScalarValue total_cmp (IEEE totalOrder); AvgAccumulator state         */
+/* [count u64, sum f64], merged by addition in Final, evaluated as sum / count.                     */
+typedef struct { int64_t start, end; uint64_t cnt; double sum; int has; double mn, mx; int used; } uframe_t;
+struct orc_uwindow {
+  orc_config cfg; int has_wm; int64_t wm;
+  uframe_t* pf; int64_t n_pf, cap_pf;          /* Partial frames, ascending start */
+  uframe_t* ff; int64_t n_ff, cap_ff;          /* Final frames (cached_frames), ascending start */
+  int64_t* seen; int64_t n_seen, cap_seen;     /* seen_windows */
+  int has_fwm; int64_t fwm;                    /* Final watermark (a window START) */
+  results_t res; int64_t seq; char err[160];
+};
+static uframe_t* uf_find_or_insert(uframe_t** arr, int64_t* n, int64_t* cap, int64_t start, int64_t end, int* created) {
+  int64_t lo = 0, hi = *n;
+  while (lo < hi) { int64_t mid = (lo + hi) / 2; if ((*arr)[mid].start < start) lo = mid + 1; else hi = mid; }
+  if (created) *created = 0;
+  if (lo < *n && (*arr)[lo].start == start) return &(*arr)[lo];
+  if (*n + 1 > *cap) { *cap = *cap ? *cap * 2 : 16; *arr = xrealloc(*arr, (size_t)*cap * sizeof(uframe_t)); }
+  memmove(*arr + lo + 1, *arr + lo, (size_t)(*n - lo) * sizeof(uframe_t));
+  uframe_t f; memset(&f, 0, sizeof f); f.start = start; f.end = end;
+  (*arr)[lo] = f; (*n)++;
+  if (created) *created = 1;
+  return &(*arr)[lo];
+}
+orc_uwindow* orc_u_create(const orc_config* cfg) {
+  orc_uwindow* w = calloc(1, sizeof *w);
+  w->cfg = *cfg;
+  return w;
+}
+void orc_u_destroy(orc_uwindow* w) { if (!w) return; free(w->pf); free(w->ff); free(w->seen); results_free(&w->res); free(w); }
+const char* orc_u_last_error(const orc_uwindow* w) { return w->err; }
+void orc_u_clear_results(orc_uwindow* w) { w->res.n = 0; w->res.bytes = 0; }
+void orc_u_get_results(orc_uwindow* w, orc_result* o) {
+  static const int32_t zero_off[1] = {0};
+  o->n = w->res.n; o->key_off = w->res.key_off ? w->res.key_off : zero_off; o->key_bytes = w->res.key_bytes;
+  o->key_isnull = w->res.key_isnull; o->count = w->res.count; o->min = w->res.mn; o->max = w->res.mx; o->avg = w->res.avg;
+  o->agg_isnull = w->res.agg_isnull; o->window_start_ms = w->res.ws; o->window_end_ms = w->res.we; o->emit_seq = w->res.seq;
+}
+/* PartialWindowAggFrame::push: rows with start <= ts < end; accumulators updated with the filtered batch */
+static void uframe_push(uframe_t* f, const orc_batch* b) {
+  for (int64_t i = 0; i < b->n; i++) {
+    if (!bit_get(b->ts_valid, i)) continue;
+    int64_t t = b->ts[i];
+    if (t < f->start || t >= f->end) continue;
+    if (!bit_get(b->val_valid, i)) continue;
+    double v = b->val[i];
+    f->cnt++; f->sum += v;
+    if (!f->has) { f->mn = f->mx = v; f->has = 1; }
+    else { if (total_cmp(v, f->mn) < 0) f->mn = v; if (total_cmp(v, f->mx) > 0) f->mx = v; }
+  }
+}
+int64_t orc_u_push(orc_uwindow* w, const orc_batch* b) {
+  int64_t emitted = 0;
+  if (b->n > 0) {
+    int64_t L = w->cfg.window_ms, S = w->cfg.slide_ms, mn, mx;
+    if (!batch_watermark(b, &mn, &mx)) { snprintf(w->err, sizeof w->err, "all-null canonical_timestamp"); return -1; }
+    if (L / 1000 == 0) { snprintf(w->err, sizeof w->err, "window length < 1 s"); return -2; }
+    if (mn < 0 || (S > 0 && mn - L < 0)) { snprintf(w->err, sizeof w->err, "timestamp before epoch(+window)"); return -3; }
+    /* ---- Partial: get_windows_for_watermark, ensure frames, push */
+    if (S > 0) {
+      for (int64_t cur = snap_to_window_start(mn - L, L); cur <= mx; cur += S) {
+        int64_t end = cur + L;
+        if (mn > end || mx < cur) continue;
+        uframe_push(uf_find_or_insert(&w->pf, &w->n_pf, &w->cap_pf, cur, end, NULL), b);
+      }
+    } else {
+      for (int64_t cur = snap_to_window_start(mn, L); cur <= mx; cur += L)
+        uframe_push(uf_find_or_insert(&w->pf, &w->n_pf, &w->cap_pf, cur, cur + L, NULL), b);
+    }
+    if (!w->has_wm || w->wm <= mn) { w->wm = mn; w->has_wm = 1; }
+    /* trigger_windows: ONE batch with a row per closed frame, ascending start */
+    int64_t keep = 0, n_closed = 0;
+    uframe_t* closed = NULL;
+    for (int64_t i = 0; i < w->n_pf; i++) {
+      if (w->wm >= w->pf[i].end) { closed = xrealloc(closed, (size_t)(n_closed + 1) * sizeof(uframe_t)); closed[n_closed++] = w->pf[i]; }
+      else w->pf[keep++] = w->pf[i];
+    }
+    w->n_pf = keep;
+    /* ---- Final: the partial batch (if it has rows) */
+    if (n_closed > 0) {
+      int64_t start = closed[0].start, end = closed[0].end;
+      for (int64_t i = 1; i < n_closed; i++) { if (closed[i].start > start) start = closed[i].start; if (closed[i].end > end) end = closed[i].end; }
+      int was_seen = 0, cached = 0;
+      for (int64_t i = 0; i < w->n_seen; i++) if (w->seen[i] == start) was_seen = 1;
+      for (int64_t i = 0; i < w->n_ff; i++) if (w->ff[i].start == start) cached = 1;
+      if (!(was_seen && !cached)) {                     /* else: late data for a finalized window, dropped */
+        uframe_t* f = uf_find_or_insert(&w->ff, &w->n_ff, &w->cap_ff, start, end, NULL);
+        if (!was_seen) { if (w->n_seen + 1 > w->cap_seen) { w->cap_seen = w->cap_seen ? w->cap_seen * 2 : 64; w->seen = xrealloc(w->seen, (size_t)w->cap_seen * sizeof(int64_t)); } w->seen[w->n_seen++] = start; }
+        for (int64_t i = 0; i < n_closed; i++) {          /* merge_batch over EVERY row of the batch (the reference assumes one row) */
+          f->cnt += closed[i].cnt;
+          if (closed[i].has) {
+            f->sum += closed[i].sum;
+            if (!f->has) { f->mn = closed[i].mn; f->mx = closed[i].mx; f->has = 1; }
+            else { if (total_cmp(closed[i].mn, f->mn) < 0) f->mn = closed[i].mn; if (total_cmp(closed[i].mx, f->mx) > 0) f->mx = closed[i].mx; }
+          }
+        }
+        if (!w->has_fwm || start > w->fwm) { w->fwm = start; w->has_fwm = 1; }
+        /* finalize_windows: watermark > window_end_time */
+        int64_t k2 = 0;
+        for (int64_t i = 0; i < w->n_ff; i++) {
+          uframe_t* g = &w->ff[i];
+          if (w->fwm > g->end) {
+            int isnull = !g->has;
+            results_push(&w->res, NULL, 0, 1, (int64_t)g->cnt, isnull ? 0.0 : g->mn, isnull ? 0.0 : g->mx, isnull ? 0.0 : g->sum / (double)g->cnt, isnull, g->start, g->end, w->seq);
+            emitted++;
+          } else w->ff[k2++] = *g;
+        }
+        w->n_ff = k2;
+      }
+    }
+    free(closed);
+  }
+  w->seq++;
+  return emitted;
+}

@@ -113,6 +113,16 @@ int64_t orc_synth_fill(int64_t row0, int64_t n, uint64_t seed, int64_t groups, i
                        int64_t t0_ms, int32_t uuid_keys, int64_t key_mul, int64_t key_add,
                        int64_t* ts, double* val, int32_t* key_off, uint8_t* key_bytes);
 
+/* Ungrouped windows `.window([], aggs, ..)`: one partition of the Partial -> Final chain the planner builds
+ * (planner/streaming_window.rs:133-153; streaming_window.rs:640-828, :882-1051).  Results use orc_result with every key NULL. */
+typedef struct orc_uwindow orc_uwindow;
+orc_uwindow* orc_u_create(const orc_config* cfg);
+void orc_u_destroy(orc_uwindow* w);
+int64_t orc_u_push(orc_uwindow* w, const orc_batch* b);
+void orc_u_get_results(orc_uwindow* w, orc_result* out);
+void orc_u_clear_results(orc_uwindow* w);
+const char* orc_u_last_error(const orc_uwindow* w);
+
 /* Canonical event time from a raw column: array_to_timestamp_array (physical_plan/utils/time.rs:59-94).
  * unit: 1 Int64Millis, 2 Int64Seconds, 3 StringIso8601(fmt).  Returns 0, or 1 + the index of the first unparsable row. */
 int64_t orc_ts_convert(int32_t unit, int64_t n, const int64_t* ints, const int32_t* off, const uint8_t* bytes, const char* fmt, int64_t* out);
