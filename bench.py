@@ -471,6 +471,10 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        allms = [None] * world
+        dist.all_gather_object(allms, round(ms / args.steps, 2))
+        log(f"device-resident ms/step per rank: {allms}")
     log(f"device-resident: {ms / args.steps:.2f} ms/step")
     if not lazy:
         stats = [w.stats() for w in wins]
@@ -523,8 +527,9 @@ def main():
             raw = out.cpu().numpy().tobytes()
             return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(world)]
         # one packet per (closed pane, group) a rank holds for a key owned elsewhere: size the receive rings for one step
-        panes_per_step = max(2, (GROUP * BATCH_ROWS) // max(1, wl["rows_per_ms"] * (wl["slide_ms"] or wl["window_ms"])) + 2)
-        ring_entries = int(min(1 << 30, max(1 << 20, 1.25 * min(G, GROUP * BATCH_ROWS) * panes_per_step)))
+        XSTEP = int(os.environ.get('DNZ_BENCH_XSTEP', '2'))          # superbatches (64 Mi rows each) per exchange step
+        panes_per_step = max(2, (XSTEP * GROUP * BATCH_ROWS) // max(1, wl["rows_per_ms"] * (wl["slide_ms"] or wl["window_ms"])) + 2)
+        ring_entries = int(min(1 << 30, max(1 << 20, 1.25 * min(G, XSTEP * GROUP * BATCH_ROWS) * panes_per_step)))
         grp = ExchangeGroup.create(rank, world, local, rendezvous, ring_entries=ring_entries,
                                    ring_key_bytes=int(min((1 << 31) - 4096, ring_entries * (40 if wl["uuid"] else 16))))
 
@@ -533,14 +538,15 @@ def main():
                 if capture is not None and r.n_rows:
                     capture.append(w.fetch_device_result(r, max_keys=0))
                 return r.n_rows
-            for g0 in range(0, devx.n_batches, GROUP):
+            for gi, g0 in enumerate(range(0, devx.n_batches, GROUP)):
                 n = min(GROUP, devx.n_batches - g0)
                 w.push_device(array=C.cast(C.byref(devx.array, g0 * C.sizeof(d.capi.DeviceBatchC)), C.POINTER(d.capi.DeviceBatchC)), n=n)
-                grp.step(w)                                     # COLLECTIVE: aggregate, global watermark, pack -> peers' rings, merge, emit
+                if gi % XSTEP == XSTEP - 1:
+                    grp.step(w)                                 # COLLECTIVE: global watermark, pack -> peers' rings, merge, emit (nothing waited for)
                 while take(w.poll_device_ready()):
                     pass
             w.push_device(endm)
-            grp.step(w)
+            grp.flush(w)                                        # end of stream: process + three steps (publish | pack | merge + emit)
             while take(w.poll_device()):
                 pass
             return w.stats()["rows_out"]
@@ -558,6 +564,9 @@ def main():
             xo = step_exchange(w)
         x1.record(stream)
         barrier()
+        allx = [None] * world
+        dist.all_gather_object(allx, round(x0.elapsed_time(x1) / args.steps, 2))
+        log(f"exchange ms/step per rank: {allx}")
         tx = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device="cuda"); dist.all_reduce(tx, op=dist.ReduceOp.MAX)
         to = torch.tensor([xo], dtype=torch.int64, device="cuda"); dist.all_reduce(to)
         xs = [w.stats() for w in xw]
@@ -572,7 +581,7 @@ def main():
                     "agg_kernel_ms": xagg_ms, "agg_algorithmic_bytes": xagg_bytes, "agg_launches": sum(s_["agg_launches"] for s_ in xs),
                     "launches": sum(s_["total_launches"] for s_ in xs),
                     "what": f"{rows} rows/GPU of ONE {G}-key stream dealt to {world} GPUs (NOT key-partitioned: every rank sees every key); "
-                            "per 64 Mi rows/GPU one fused exchange step of the library-owned communicator (dnz_group): global watermark, "
+                            f"per {XSTEP * 64} Mi rows/GPU one fused exchange step of the library-owned communicator (dnz_group): global watermark, "
                             "closed panes' partial states packed by owner = key hash % world and written straight into the owners' "
                             "receive rings over NVLink (remote-atomic reservation + P2P stores, interprocess CUDA events), owner merge, "
                             "owners emit; no NCCL / host copy in the data path"}

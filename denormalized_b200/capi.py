@@ -111,7 +111,7 @@ EXPORTS = ["dnz_window_create", "dnz_window_push", "dnz_window_push_device", "dn
            "dnz_device_count", "dnz_memcpy", "dnz_synth_generate", "dnz_synth_bytes", "dnz_synth_free",
            "dnz_window_checkpoint", "dnz_window_restore", "dnz_blob_free",
            "dnz_group_create", "dnz_group_create_local", "dnz_group_destroy", "dnz_group_attach", "dnz_group_step_begin",
-           "dnz_group_step_pack", "dnz_group_step_finish", "dnz_group_step"]
+           "dnz_group_step_pack", "dnz_group_step_finish", "dnz_group_step", "dnz_group_flush"]
 
 _lib = None
 
@@ -191,7 +191,7 @@ def lib():
         for name in ("dnz_group_step_begin", "dnz_group_step_pack"):
             getattr(L, name).restype = C.c_int32
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
-        for name in ("dnz_group_step_finish", "dnz_group_step"):
+        for name in ("dnz_group_step_finish", "dnz_group_step", "dnz_group_flush"):
             getattr(L, name).restype = C.c_int32
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.dnz_synth_bytes.restype = C.c_int64
@@ -480,6 +480,13 @@ class ExchangeGroup:
         """One collective exchange step; returns the global watermark (None before every rank has one)."""
         v = C.c_int64(0)
         self._check(self._L.dnz_group_step(self._h, w._h, C.byref(v)), w)
+        return None if v.value == -(2 ** 63) else v.value
+
+    def flush(self, w):
+        """COLLECTIVE end of stream: process + three steps (the protocol is pipelined over three steps): everything pushed so far
+        is exchanged and the windows it closes are emitted."""
+        v = C.c_int64(0)
+        self._check(self._L.dnz_group_flush(self._h, w._h, C.byref(v)), w)
         return None if v.value == -(2 ** 63) else v.value
 
     def close(self):

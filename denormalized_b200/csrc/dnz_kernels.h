@@ -146,9 +146,13 @@ struct __align__(16) PartialEntry {
 };
 static_assert(sizeof(PartialEntry) == 64, "packet size");
 constexpr int MAX_WORLD = 32;
+constexpr int PACK_PANES = 32;       // panes per pack launch (a 32-bit mask per group id)
 struct PackParams {
-  const GroupState* st; const unsigned long long* nullrows; const unsigned long long* fz;   // one pane
+  const GroupState* st; const unsigned long long* nullrows; const unsigned long long* fz;   // one pane (host-driven export) ...
   int64_t pane; uint32_t n_groups; int32_t rank, world;
+  // ... or up to PACK_PANES panes in one launch (fused exchange; one thread per group id walks them)
+  int32_t n_multi, pad_multi;
+  const GroupState* mst[PACK_PANES]; const unsigned long long* mnull[PACK_PANES]; const unsigned long long* mfz[PACK_PANES]; int64_t mpane[PACK_PANES];
   DictView dict;
   PartialEntry* entries; uint8_t* key_bytes;     // pass 1 output, grouped by owner
   unsigned long long* owner_cursor;              // [world] (entries << 32) | key bytes, running over all panes of the export

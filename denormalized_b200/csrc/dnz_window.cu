@@ -2070,7 +2070,7 @@ int32_t dnz_window_set_exchange(dnz_window* w, int32_t rank, int32_t world) {
     w->need_nullrows = true; w->need_fz = true; for (auto& kv : w->panes) w->ensure_side_arrays(kv.second.get());
     // staging of the merge's pane table for the largest pane range of one step: page-locked allocations synchronise the device,
     // which must not happen while a peer rank of the same process spins in a wait kernel (dnz_group, local groups)
-    w->h_xptrs.reserve((size_t)7 * (1 << 16) * sizeof(void*)); w->d_xptrs.reserve((size_t)7 * (1 << 16) * sizeof(void*));
+    w->h_xptrs.reserve((size_t)2 * 7 * (1 << 16) * sizeof(void*)); w->d_xptrs.reserve((size_t)2 * 7 * (1 << 16) * sizeof(void*));   // two halves (step parity)
   }
   DNZ_CATCH(w)
 }
@@ -2211,11 +2211,12 @@ void dnz_synth_free(dnz_synth* a) {
 #include <atomic>
 
 namespace {
-struct HostCtl {          // shared by all ranks (POSIX shm or heap); two slots by step parity
-  std::atomic<int64_t> arrived[2][MAX_WORLD];     // phase 1: the local watermark of the step is published
-  std::atomic<int64_t> packed[2][MAX_WORLD];      // phase 2: the "my packets are written" event of the step is recorded
-  std::atomic<int64_t> lwm[2][MAX_WORLD];
-  std::atomic<int64_t> first_pane[2][MAX_WORLD];
+struct HostCtl {          // shared by all ranks (POSIX shm or heap); four slots by step & 3: a rank is never more than two steps ahead
+  std::atomic<int64_t> arrived[4][MAX_WORLD];     // phase 1: the local watermark of the step is published
+  std::atomic<int64_t> packed[4][MAX_WORLD];      // phase 2: the "my packets are written" event of the step is recorded
+  std::atomic<int64_t> finished[4][MAX_WORLD];    // phase 3: the step is issued completely ("merged" event recorded)
+  std::atomic<int64_t> lwm[4][MAX_WORLD];
+  std::atomic<int64_t> first_pane[4][MAX_WORLD];
   std::atomic<int32_t> failed;
 };
 struct GroupShared { HostCtl ctl; };
@@ -2237,7 +2238,13 @@ struct dnz_group {
   DevBuf d_owner_cursor, d_owner_base, d_totals;   // totals: [0] packets sent, [1] packets merged
   PinnedBuf h_totals; cudaEvent_t totals_ev = nullptr; bool totals_issued = false;
   int phase = 0;                                 // 0 idle, 1 begun, 2 packed
-  int64_t my_lwm = INT64_MIN, my_first = INT64_MAX, gwm = INT64_MIN, gfirst = INT64_MAX;
+  // DNZ_TRACE: device timestamps of the step phases (pack start, packed, peers' packets seen, merged, emitted)
+  static constexpr int TSTEPS = 48; cudaEvent_t tev[TSTEPS][5] = {}; int tcount = 0;
+  void tmark(int k, cudaStream_t st) { if (!g_trace || tcount >= TSTEPS) return; if (!tev[tcount][k]) cudaEventCreate(&tev[tcount][k]); cudaEventRecord(tev[tcount][k], st); if (k == 4) tcount++; }
+  struct Range { int64_t gwm = INT64_MIN, first = INT64_MAX, hi = INT64_MIN; bool any = false; };
+  Range sent[2];                                 // what pack of step s sent (by step parity): merged by finish of step s+1
+  bool staged[2] = {false, false};
+  unsigned long long attach_step = 0;            // the step count when the current operator was attached: what was published before belongs to another stream
 
   static XchgRegion carve(void* base, uint64_t ring_entries) {
     XchgRegion r;
@@ -2250,6 +2257,12 @@ struct dnz_group {
   ~dnz_group() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    if (g_trace) for (int i = 0; i < tcount; i++) {
+      float a = 0, b = 0, c = 0, d = 0, gap = 0;
+      cudaEventElapsedTime(&a, tev[i][0], tev[i][1]); cudaEventElapsedTime(&b, tev[i][1], tev[i][2]); cudaEventElapsedTime(&c, tev[i][2], tev[i][3]); cudaEventElapsedTime(&d, tev[i][3], tev[i][4]);
+      if (i) cudaEventElapsedTime(&gap, tev[i - 1][4], tev[i][0]);
+      fprintf(stderr, "[dnz] rank %d xstep %d device: since_prev=%.3f pack=%.3f wait_peers=%.3f merge=%.3f emit=%.3f ms\n", rank, i, gap, a, b, c, d);
+    }
     if (totals_ev) cudaEventDestroy(totals_ev);
     for (int p = 0; p < 2; p++) { if (ev_packed[rank][p]) cudaEventDestroy(ev_packed[rank][p]); if (ev_merged[rank][p]) cudaEventDestroy(ev_merged[rank][p]); }
     if (ipc) {
@@ -2294,7 +2307,7 @@ void group_finish_view(dnz_group* g) {
 // host barrier on one of the per-step counters.  A process that drives all ranks itself must call the phases in order for
 // ALL ranks (begin x world, pack x world, finish x world): waiting would never end there, so it is an error instead.
 void group_wait(dnz_group* g, std::atomic<int64_t> (*ctr)[MAX_WORLD], unsigned long long step, const char* what) {
-  const int s = (int)(step & 1);
+  const int s = (int)(step & 3);
   const auto t0 = std::chrono::steady_clock::now();
   for (int r = 0; r < g->world; r++) {
     int spins = 0;
@@ -2311,115 +2324,156 @@ void group_wait(dnz_group* g, std::atomic<int64_t> (*ctr)[MAX_WORLD], unsigned l
 
 }  // namespace
 
-// ---- phase 1: aggregate what is queued, publish the local watermark of the step
+// The step protocol is PIPELINED over three steps so that no phase waits for something a peer does "now" (a rank whose host
+// thread is descheduled for a millisecond would otherwise idle every GPU of the group -- each has about one aggregate launch
+// queued):
+//     step s   begin   publish this rank's local watermark                                        -> lwm(s)
+//     step s+1 pack    global watermark = min over ranks of lwm(s); the panes it closes are packed and written into the owners'
+//                      rings (half (s+1) & 1)
+//     step s+2 finish  the owners merge what step s+1 wrote, and emit the windows closed under that watermark
+// The only host wait is "every rank has ISSUED step s-1" (finished[s-1]), checked in pack of step s: it orders the interprocess
+// event waits (an event wait captures the record that exists when it is issued) and was normally satisfied a whole step ago.
+// Every rank computes the same watermark / pane range sequence, so `exported_pane_upto` agrees everywhere without being exchanged.
+
+// ---- phase 1: seal what is filling, publish the local watermark of the step
 void dnz_window::group_begin(dnz_group* g) {
   if (world != g->world || rank != g->rank) fail(DNZ_ERR_INVALID, "operator is not attached to this group");
   if (g->phase != 0) fail(DNZ_ERR_INVALID, "dnz_group_step_begin: the previous step of this rank is not finished");
-  // everything that has been pushed is enqueued (scan, aggregate); nothing is waited for: the local watermark follows from the
-  // tile scans alone, errors of earlier steps (ring / table overflow) surface when their launches are verified
-  process_pending();
+  // Nothing is waited for.  A filling superbatch is sealed (its scan is enqueued, the superbatch sealed before it is launched: its
+  // scan results are on the host), but the NEWEST sealed superbatch is not forced -- its scan sits behind the previous aggregate
+  // on the device, waiting for it here would idle the GPU every step.  The local watermark is that of the LAUNCHED batches;
+  // dnz_window_process before the step includes everything pushed.
+  // Errors of earlier steps (ring / table overflow) surface when their launches are verified.
+  if (!cur().batches.empty()) seal_current();
   while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
   cudaGetLastError();
   if (g->totals_issued && cudaEventQuery(g->totals_ev) == cudaSuccess) {
     stats.exchanged_out = (int64_t)g->h_totals.as<unsigned long long>()[0]; stats.exchanged_in = (int64_t)g->h_totals.as<unsigned long long>()[1];
   }
   cudaGetLastError();
-  g->my_lwm = has_lwm ? lwm : INT64_MIN;
-  g->my_first = exported_pane_upto != INT64_MIN ? exported_pane_upto + 1 : (panes.empty() ? INT64_MAX : panes.begin()->first);
   const unsigned long long step = g->step + 1;
-  HostCtl* h = g->hctl; const int s = (int)(step & 1);
-  h->lwm[s][g->rank].store(g->my_lwm, std::memory_order_relaxed);
-  h->first_pane[s][g->rank].store(g->my_first, std::memory_order_relaxed);
-  h->arrived[s][g->rank].store((int64_t)step, std::memory_order_release);
+  HostCtl* h = g->hctl; const int q = (int)(step & 3);
+  h->lwm[q][g->rank].store(has_lwm ? lwm : INT64_MIN, std::memory_order_relaxed);
+  h->first_pane[q][g->rank].store(panes.empty() ? INT64_MAX : panes.begin()->first, std::memory_order_relaxed);
+  h->arrived[q][g->rank].store((int64_t)step, std::memory_order_release);
   g->phase = 1;
+  g_tr.mark("x_begin");
 }
 
-// ---- phase 2: global watermark; pack the closed panes' partial states of the keys owned elsewhere straight into the owners' rings
+// ---- phase 2: the panes closed under the watermark published one step ago go straight into the owners' rings
 void dnz_window::group_pack(dnz_group* g) {
   if (g->phase != 1) fail(DNZ_ERR_INVALID, "dnz_group_step_pack without dnz_group_step_begin");
   const unsigned long long step = g->step + 1;
   const int par = (int)(step & 1);
-  group_wait(g, g->hctl->arrived, step, "begin");
-  int64_t gwm = INT64_MAX, gfirst = INT64_MAX;
-  for (int r = 0; r < world; r++) { gwm = std::min(gwm, g->hctl->lwm[par][r].load(std::memory_order_relaxed)); gfirst = std::min(gfirst, g->hctl->first_pane[par][r].load(std::memory_order_relaxed)); }
-  g->gwm = gwm; g->gfirst = gfirst;
-  XchgView X = g->view; X.step = step;
+  int64_t gwm = INT64_MIN, gfirst = INT64_MAX;
+  if (step >= 2) {
+    group_wait(g, g->hctl->finished, step - 1, "finish");
+    g_tr.mark("x_wait_prev_step");
+    const int q = (int)((step - 1) & 3);
+    if (step - 1 > g->attach_step) gwm = INT64_MAX;          // (the watermarks of step-1 were published by THIS stream's operators)
+    if (step - 1 > g->attach_step) for (int r = 0; r < world; r++) { gwm = std::min(gwm, g->hctl->lwm[q][r].load(std::memory_order_relaxed)); gfirst = std::min(gfirst, g->hctl->first_pane[q][r].load(std::memory_order_relaxed)); }
+  }
+  if (exported_pane_upto != INT64_MIN) gfirst = exported_pane_upto + 1;
   const int64_t hi = gwm == INT64_MIN ? INT64_MIN : floor_div(gwm, pane_ms) - 1;          // panes with end <= global watermark
+  const bool any = gwm != INT64_MIN && gfirst != INT64_MAX && hi >= gfirst;
+  g->sent[par].gwm = gwm; g->sent[par].first = gfirst; g->sent[par].hi = hi; g->sent[par].any = any;
+  XchgView X = g->view; X.step = step;
   std::vector<Pane*> send;
-  if (gwm != INT64_MIN) for (auto& kv : panes) if (kv.first >= g->my_first && kv.first <= hi) send.push_back(kv.second.get());
-  // the owners must have merged step-2, which used the same half of their rings
+  if (any) {
+    if (hi - gfirst + 1 > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one exchange step spans %lld panes", (long long)(hi - gfirst + 1));
+    for (auto& kv : panes) if (kv.first >= gfirst && kv.first <= hi) send.push_back(kv.second.get());
+    exported_pane_upto = hi;                                                                // the same on every rank
+  }
+  // the owners must have merged what step-2 wrote into the same half of their rings (recorded in their finish of step-1)
   if (step > 2) for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_merged[r][par], 0));
+  g->tmark(0, stream);
   CK(cudaMemsetAsync(g->d_owner_cursor.p, 0, MAX_WORLD * 8, stream));
   PackParams P; memset(&P, 0, sizeof P);
   P.n_groups = gcap; P.rank = rank; P.world = world; P.dict = dict_view();      // grid bound; the kernels clamp to the device counter
   P.owner_cursor = g->d_owner_cursor.as<unsigned long long>();
-  {
-    P.pass = 0;
-    for (Pane* p : send) {
-      P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
-      CK(launch_pack_partials(P, stream)); stats.total_launches++;
+  auto for_pane_chunks = [&](auto&& launch) {                 // up to PACK_PANES panes per launch (one thread per group id walks them)
+    for (size_t i0 = 0; i0 < send.size(); i0 += PACK_PANES) {
+      P.n_multi = (int32_t)std::min<size_t>(PACK_PANES, send.size() - i0);
+      for (int j = 0; j < P.n_multi; j++) {
+        Pane* p = send[i0 + j];
+        P.mst[j] = p->st.as<GroupState>(); P.mnull[j] = p->nullrows.as<unsigned long long>(); P.mfz[j] = p->fz.as<unsigned long long>(); P.mpane[j] = p->id;
+      }
+      launch(); stats.total_launches++;
     }
-  }
+  };
+  P.pass = 0;
+  for_pane_chunks([&]() { CK(launch_pack_partials(P, stream)); });
   CK(launch_xchg_reserve(X, g->d_owner_cursor.as<unsigned long long>(), g->d_owner_base.as<unsigned long long>(), g->d_totals.as<unsigned long long>(), reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR)), stream));
   stats.total_launches++;
-  {
-    for (Pane* p : send) {
-      P.st = p->st.as<GroupState>(); P.nullrows = p->nullrows.as<unsigned long long>(); P.fz = p->fz.as<unsigned long long>(); P.pane = p->id;
-      CK(launch_pack_write_peer(P, X, g->d_owner_base.as<unsigned long long>(), stream)); stats.total_launches++;
-    }
-  }
+  for_pane_chunks([&]() { CK(launch_pack_write_peer(P, X, g->d_owner_base.as<unsigned long long>(), stream)); });
   CK(cudaEventRecord(g->ev_packed[rank][par], stream));                    // "all my packets of this step are in the owners' rings"
-  g->hctl->packed[par][g->rank].store((int64_t)step, std::memory_order_release);
+  g->tmark(1, stream);
+  g->hctl->packed[(int)(step & 3)][g->rank].store((int64_t)step, std::memory_order_release);
   g->phase = 2;
+  g_tr.mark("x_pack");
 }
 
-// ---- phase 3: merge what the peers sent, emit the closed windows of this rank's keys
+// ---- phase 3: merge what the peers wrote ONE STEP AGO, emit the windows of this rank's keys closed under that step's watermark
 void dnz_window::group_finish(dnz_group* g, int64_t* gwm_out) {
   if (g->phase != 2) fail(DNZ_ERR_INVALID, "dnz_group_step_finish without dnz_group_step_pack");
   const unsigned long long step = ++g->step;
-  const int par = (int)(step & 1);
   g->phase = 0;
-  group_wait(g, g->hctl->packed, step, "pack");
-  const int64_t gwm = g->gwm, gfirst = g->gfirst;
-  if (gwm_out) *gwm_out = gwm;
-  XchgView X = g->view; X.step = step;
-  const int64_t hi = gwm == INT64_MIN ? INT64_MIN : floor_div(gwm, pane_ms) - 1;
-  for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_packed[r][par], 0));
-  if (gwm != INT64_MIN && gfirst != INT64_MAX && hi >= gfirst) {
-    exported_pane_upto = std::max(exported_pane_upto, hi);                 // the same on every rank
-    const int64_t np = hi - gfirst + 1;
-    if (np > (1 << 16)) fail(DNZ_ERR_UNSUPPORTED, "one exchange step spans %lld panes", (long long)np);
-    for (int64_t p = gfirst; p <= hi; p++) ensure_side_arrays(get_pane(p, true));
-    const size_t pb = (size_t)np * sizeof(void*);
-    h_xptrs.reserve(7 * pb); d_xptrs.reserve(7 * pb);
-    void** hp = h_xptrs.as<void*>();      // (the previous step's table is no longer in use: group_begin drained the stream)
-    for (int64_t p = gfirst; p <= hi; p++) {
-      const size_t k = (size_t)(p - gfirst);
-      Pane* m = get_pane(p, false);
-      hp[0 * np + k] = m->st.p; hp[1 * np + k] = nullptr; hp[2 * np + k] = m->nullrows.p; hp[3 * np + k] = nullptr;
-      hp[4 * np + k] = m->fz.p; hp[5 * np + k] = nullptr; hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m->tag & 0xFFFFFFFFull));
+  if (gwm_out) *gwm_out = INT64_MIN;
+  if (step >= 2) {
+    const unsigned long long mstep = step - 1;                            // the step whose packets are merged now
+    const int mp = (int)(mstep & 1);
+    const dnz_group::Range R = g->sent[mp];
+    if (gwm_out) *gwm_out = R.gwm;
+    XchgView X = g->view; X.step = mstep;
+    // every peer issued pack(mstep) before its finish(mstep), which pack of this step waited for: the records exist
+    for (int r = 0; r < world; r++) if (r != rank) CK(cudaStreamWaitEvent(stream, g->ev_packed[r][mp], 0));
+    g->tmark(2, stream);
+    if (R.any) {
+      const int64_t gfirst = R.first, hi = R.hi;
+      const int64_t np = hi - gfirst + 1;
+      for (int64_t p = gfirst; p <= hi; p++) ensure_side_arrays(get_pane(p, true));
+      const size_t pb = (size_t)np * sizeof(void*);
+      // The pane table is staged in page-locked memory and copied by the stream when it gets there: the staging half may only be
+      // rewritten once the copy issued two steps ago (same half) has executed -- its merge has been recorded in ev_merged[rank][mp].
+      const size_t half_bytes = (size_t)7 * (1 << 16) * sizeof(void*);
+      if (g->staged[mp]) CK(cudaEventSynchronize(g->ev_merged[rank][mp]));
+      g->staged[mp] = true;
+      g_tr.mark("x_sync_merged");
+      void** hp = reinterpret_cast<void**>(h_xptrs.as<char>() + (size_t)mp * half_bytes);
+      char* dxp = d_xptrs.as<char>() + (size_t)mp * half_bytes;
+      for (int64_t p = gfirst; p <= hi; p++) {
+        const size_t k = (size_t)(p - gfirst);
+        Pane* m = get_pane(p, false);
+        hp[0 * np + k] = m->st.p; hp[1 * np + k] = nullptr; hp[2 * np + k] = m->nullrows.p; hp[3 * np + k] = nullptr;
+        hp[4 * np + k] = m->fz.p; hp[5 * np + k] = nullptr; hp[6 * np + k] = reinterpret_cast<void*>((uintptr_t)(m->tag & 0xFFFFFFFFull));
+      }
+      CK(cudaMemcpyAsync(dxp, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
+      MergeParams M; memset(&M, 0, sizeof M);
+      char* dp = dxp;
+      M.panes.pane0 = gfirst; M.panes.n_panes = (int32_t)np; M.panes.pane_ms = pane_ms;
+      M.panes.main = (GroupState* const*)(dp + 0 * pb); M.panes.late = (GroupState* const*)(dp + 1 * pb);
+      M.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); M.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
+      M.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); M.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
+      M.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
+      M.world = world; M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR));
+      CK(launch_merge_ring(M, X, g->d_totals.as<unsigned long long>() + 1, sm_count, stream)); stats.total_launches++;
     }
-    CK(cudaMemcpyAsync(d_xptrs.p, hp, 7 * pb, cudaMemcpyHostToDevice, stream));
-    MergeParams M; memset(&M, 0, sizeof M);
-    char* dp = d_xptrs.as<char>();
-    M.panes.pane0 = gfirst; M.panes.n_panes = (int32_t)np; M.panes.pane_ms = pane_ms;
-    M.panes.main = (GroupState* const*)(dp + 0 * pb); M.panes.late = (GroupState* const*)(dp + 1 * pb);
-    M.panes.nullrows_main = (unsigned long long* const*)(dp + 2 * pb); M.panes.nullrows_late = (unsigned long long* const*)(dp + 3 * pb);
-    M.panes.fz_main = (unsigned long long* const*)(dp + 4 * pb); M.panes.fz_late = (unsigned long long* const*)(dp + 5 * pb);
-    M.panes.tag_main = (const unsigned long long*)(dp + 6 * pb);
-    M.world = world; M.dict = dict_view(); M.error = reinterpret_cast<uint32_t*>(ctl(CTL_MERGE_ERR));
-    CK(launch_merge_ring(M, X, g->d_totals.as<unsigned long long>() + 1, sm_count, stream)); stats.total_launches++;
+    CK(cudaMemsetAsync(&g->view.self.ctl->cursor[mp], 0, 8, stream));       // the ring half is free again ...
+    CK(cudaEventRecord(g->ev_merged[rank][mp], stream));                    // ... once this has happened
+    CK(cudaMemcpyAsync(g->h_totals.p, g->d_totals.p, 16, cudaMemcpyDeviceToHost, stream));   // packet counters for dnz_stats (read when complete)
+    CK(cudaEventRecord(g->totals_ev, stream)); g->totals_issued = true;
+    g->tmark(3, stream);
+    // ---- every rank emits the windows of ITS keys that closed under that watermark
+    if (R.gwm != INT64_MIN) {
+      if (res_consumed) reset_results();
+      rotate_result_sets();
+      emit_normal(R.gwm, false, nullptr);
+    }
+    g->tmark(4, stream);
   }
-  CK(cudaMemsetAsync(&g->view.self.ctl->cursor[par], 0, 8, stream));       // the ring half is free again ...
-  CK(cudaEventRecord(g->ev_merged[rank][par], stream));                    // ... once this has happened
-  CK(cudaMemcpyAsync(g->h_totals.p, g->d_totals.p, 16, cudaMemcpyDeviceToHost, stream));   // packet counters for dnz_stats (read when complete)
-  CK(cudaEventRecord(g->totals_ev, stream)); g->totals_issued = true;
-  // ---- every rank emits the windows of ITS keys that closed under the global watermark
-  if (gwm != INT64_MIN) {
-    if (res_consumed) reset_results();
-    rotate_result_sets();
-    emit_normal(gwm, false, nullptr);
-  }
+  g->hctl->finished[(int)(step & 3)][g->rank].store((int64_t)step, std::memory_order_release);
+  g_tr.mark("x_finish");
+  g_tr.flush("xstep");
 }
 
 namespace {
@@ -2530,7 +2584,7 @@ void dnz_group_destroy(dnz_group* g) {
 int32_t dnz_group_attach(dnz_group* g, dnz_window* w) {
   if (!g) { g_last_error = "null group"; return DNZ_ERR_INVALID; }
   const int32_t rc = dnz_window_set_exchange(w, g->rank, g->world);
-  if (rc == DNZ_OK) w->fused = g->world > 1;
+  if (rc == DNZ_OK) { w->fused = g->world > 1; g->attach_step = g->step; g->sent[0] = g->sent[1] = dnz_group::Range{}; }
   return rc;
 }
 
@@ -2549,6 +2603,11 @@ int32_t dnz_group_step(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms
   int32_t rc = dnz_group_step_begin(g, w);
   if (rc == DNZ_OK) rc = dnz_group_step_pack(g, w);
   return rc != DNZ_OK ? rc : dnz_group_step_finish(g, w, global_watermark_ms);
+}
+int32_t dnz_group_flush(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms) {
+  int32_t rc = dnz_window_process(w, nullptr);
+  for (int i = 0; i < 3 && rc == DNZ_OK; i++) rc = dnz_group_step(g, w, global_watermark_ms);
+  return rc;
 }
 
 }  // extern "C"

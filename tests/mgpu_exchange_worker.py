@@ -69,7 +69,7 @@ def main():
             grp.step(w)
             got += record_batch_rows(w.poll())
     w.push(to_record_batch(rows_to_batch([(close, 1.0, b"sentinel")])))
-    grp.step(w)
+    grp.flush(w)                                  # end of stream: process + three steps (publish | pack | merge + emit)
     got += record_batch_rows(w.poll())
     grp.step(w)                                   # one more (empty) step makes the packet counters visible
     st = w.stats()

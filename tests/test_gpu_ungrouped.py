@@ -47,7 +47,7 @@ def test_ungrouped_in_order_stream(L, S):
 def test_ungrouped_total_order_min_max_and_special_values():
     vals = [float("nan"), -0.0, 0.0, float("inf"), float("-inf"), 5.0, -3.0, None]
     batches = []
-    for b in range(12):
+    for b in range(16):
         rows = [(T0 + b * 500 + i, vals[(b + i) % len(vals)], b"x") for i in range(40)]
         if b == 4:
             rows = [(T0 + b * 500 + i, -0.0 if i % 2 else 0.0, b"x") for i in range(40)]      # a window of zeros only: min -0.0, max +0.0
