@@ -628,13 +628,31 @@ def main():
         hb, in_bytes, base, hb_addrs = pinned_host_batches(d, wl, e2e_rows, rank, world)
         e_last = T0 + (e2e_rows - 1) // wl["rows_per_ms"]
         e_close = (e_last // 1000 + 1) * 1000 + 2 * wl["window_ms"]
-        n_e2e_steps = args.warmup + args.steps
-        n_e2e_total = n_e2e_steps + (0 if args.no_parity else 1)      # + one untimed pass whose output is compared with the oracle
+        launch_rows = args.max_rows_per_launch or (64 << 20)
+        reserve_bytes = int(min(launch_rows, e2e_rows) * (in_bytes / e2e_rows) * 1.05) + (64 << 20)
+        # Every e2e step runs through its own operator, created (and its device staging reserved) before the timed region: three
+        # superbatches in flight x `reserve_bytes` of staging + the deferred-row lists + results ~ 9 GB per operator for cfg 2.
+        # The number of e2e steps is therefore bounded by the free device memory (the device-resident input of the other legs is
+        # released first); `e2e.steps` / `e2e.warmup` say what was run.
+        dev.free()
+        torch.cuda.synchronize()
+        free_dev = torch.cuda.mem_get_info()[0]
+        per_op = 3 * reserve_bytes + 3 * min(launch_rows, max(e2e_rows, 1 << 20)) * 8 + (3 << 29)
+        fit = max(3, int(free_dev * 0.85) // per_op)
+        if world > 1:           # every rank runs the same number of steps
+            tf = torch.tensor([fit], dtype=torch.int64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MIN)
+            fit = int(tf.item())
+        n_parity_ops = 0 if args.no_parity else 1
+        e_warm = min(args.warmup, 3, max(1, fit - 1 - n_parity_ops))
+        e_steps = max(1, min(args.steps, fit - e_warm - n_parity_ops))
+        n_e2e_steps = e_warm + e_steps
+        n_e2e_total = n_e2e_steps + n_parity_ops                      # + one untimed pass whose output is compared with the oracle
+        log(f"e2e: {free_dev / 2**30:.0f} GiB of device memory free, ~{per_op / 2**30:.1f} GiB per operator -> {e_warm} warm-up + {e_steps} timed steps")
         exported = [export_all(d, hb) for _ in range(n_e2e_total)]
         e_wins = [new_window() for _ in range(n_e2e_total)]
-        launch_rows = args.max_rows_per_launch or (64 << 20)
         for w_ in e_wins:       # operator start-up (device staging for host batches) belongs to creation, not to the stream
-            w_.reserve_input(int(min(launch_rows, e2e_rows) * (in_bytes / e2e_rows) * 1.05) + (64 << 20))
+            w_.reserve_input(reserve_bytes)
         ca, cs, has = d.capi.ArrowArrayC(), d.capi.ArrowSchemaC(), C.c_int32(0)
         push, poll, poll_ready, flush = L.dnz_window_push, L.dnz_window_poll, L.dnz_window_poll_ready, L.dnz_window_flush
         rel = C.CFUNCTYPE(None, C.c_void_p)
@@ -663,14 +681,14 @@ def main():
                         rel(ca.release)(C.addressof(ca)); rel(cs.release)(C.addressof(cs))
             return n_out
         log(f"e2e host batches ready: {e2e_rows} rows")
-        for i in range(args.warmup):
+        for i in range(e_warm):
             step_host(i)
         d2h0 = sum(w.stats()["d2h_bytes"] for w in e_wins)
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.warmup, n_e2e_steps):
+        for i in range(e_warm, n_e2e_steps):
             e_out = step_host(i)
         e1.record(stream)
         barrier()
@@ -680,7 +698,7 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ems, wall_ms = float(te[0].item()), float(te[1].item())
-        d2h = (sum(w.stats()["d2h_bytes"] for w in e_wins[:n_e2e_steps]) - d2h0) // args.steps
+        d2h = (sum(w.stats()["d2h_bytes"] for w in e_wins[:n_e2e_steps]) - d2h0) // e_steps
         h2d = e_wins[n_e2e_steps - 1].stats()["h2d_bytes"]
         pageable = e_wins[n_e2e_steps - 1].stats()["h2d_pageable_bytes"]
         if not args.no_parity:
@@ -752,10 +770,11 @@ def main():
                             "h2d_pageable_bytes_per_step": int(p_bytes), "gb_per_s": p_bytes * (n_p - 1) / p_wall / 1e9,
                             "sample": f"first {p_rows} rows/GPU of the stream in ordinary (pageable) heap memory: cudaMemcpyAsync path, wall clock"}
             del pbatches, p_exp
-        e2e = {"value": e2e_rows * world * args.steps / (ems * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows * world, "ms_per_step": ems / args.steps,
-               "wall_ms_per_step": wall_ms / args.steps, "rows_out_per_step": int(e_out), "pinned_fraction": 1.0 - pageable / max(h2d, 1),
-               "h2d_gb_per_s": h2d / (ems / args.steps * 1e-3) / 1e9 / 1.0,
+        e2e = {"value": e2e_rows * world * e_steps / (ems * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows * world, "ms_per_step": ems / e_steps,
+               "wall_ms_per_step": wall_ms / e_steps, "steps": e_steps, "warmup": e_warm,
+               "rows_out_per_step": int(e_out), "pinned_fraction": 1.0 - pageable / max(h2d, 1),
+               "h2d_gb_per_s": h2d / (ems / e_steps * 1e-3) / 1e9 / 1.0,
                "sample": f"first {e2e_rows} rows/GPU of the stream, Arrow buffers in pinned host memory (dnz_host_alloc)",
                "pageable": pageable_e2e}
         del hb, exported
