@@ -174,3 +174,28 @@ def test_mt_partitioned_equals_single_partition():
         got = m.results()
         assert len(want) > 50
         assert_rows_equal(got, want, rel=0.0)
+
+
+@pytest.mark.parametrize("L,S", [(3000, 2000), (1500, 0)])
+def test_non_lattice_geometries_depend_on_batch_boundaries(L, S):
+    """Why the GPU operator rejects L % S != 0 and L that is not a whole number of seconds (DNZ_ERR_UNSUPPORTED): the reference
+    enumerates a batch's windows from snap_to_window_start(batch minimum) in steps of the slide (streaming_window.rs:1053-1094),
+    so on these geometries the SET of windows -- not just their content -- depends on where the stream is cut into batches.  The
+    same 40 rows in one batch, in four batches and in four ragged batches give three different window sets; both the C oracle and
+    the independent Python model say so.  On the lattice geometries (L a whole number of seconds, L % S == 0) the cut does not
+    matter, which is what a pane organisation needs."""
+    rows = [(T0 + 250 * i, float(i), b"a") for i in range(40)]        # 10 s of rows, 4 per second
+    close = [(T0 + 60_000, 1.0, b"z")]
+
+    def window_set(run, cuts, l, s):
+        batches, i = [], 0
+        for c in cuts:
+            batches.append(rows[i:i + c]); i += c
+        return sorted({(r[0], r[1]) for r in run(batches + [close], l, s) if r[2] == b"a"})
+    cuts = ([40], [10, 10, 10, 10], [3, 7, 11, 19])
+    sets = [window_set(run_oracle, c, L, S) for c in cuts]
+    assert sets[0] != sets[1] and sets[1] != sets[2] and sets[0] != sets[2]
+    assert [window_set(run_model, c, L, S) for c in cuts] == sets       # the independent model agrees on every cut
+    for l, s in [(2000, 0), (4000, 1000), (4000, 2000)]:                  # lattice geometries: the cut is irrelevant
+        lattice = [window_set(run_oracle, c, l, s) for c in cuts]
+        assert lattice[0] == lattice[1] == lattice[2]
