@@ -263,6 +263,9 @@ int32_t dnz_group_attach(dnz_group* g, dnz_window* w);
  *                    straight into the owners' rings
  *   step s+2 finish  the owners merge those packets and emit the windows closed under that watermark (returned in
  *                    *global_watermark_ms; INT64_MIN while there is none)
+ * Numerical note: which of +0.0 / -0.0 a min / max reports when both occur in a window is decided by arrival order ("first seen
+ * wins", DataFusion's `if cur > v`); across ranks the order is each rank's LOCAL batch sequence, so the sign of such a zero can
+ * differ from what a single stream would report.  Everything else is bit-identical (count, min, max) or within 1e-9 (avg).
  * dnz_group_flush = dnz_window_process + three steps: everything pushed so far is exchanged and its closed windows are emitted
  * (end of stream, tests). */
 int32_t dnz_group_step_begin(dnz_group* g, dnz_window* w);
