@@ -78,7 +78,19 @@ struct PhysicalStreamingWindowType {
   static PhysicalStreamingWindowType tumbling(Duration l) { return {Tumbling, l, Duration{0}}; }
   static PhysicalStreamingWindowType sliding(Duration l, Duration s) { return {Sliding, l, s}; }
 };
-enum class AggregateMode { Single };      // grouped windows are planned as AggregateMode::Single (planner/streaming_window.rs:154-165)
+// grouped windows are planned as AggregateMode::Single; the ungrouped `.window([], ..)` as Partial -> Final
+// (planner/streaming_window.rs:120-165) -- here ONE operator runs the Partial reduction on the device and the Final stage on
+// the host (include/dnz_gpu.h, DNZ_NO_KEY), so the mirror accepts Single for both.
+enum class AggregateMode { Single };
+
+// TimestampUnit (physical_plan/utils/time.rs:15-19) + KafkaTopicBuilder::with_timestamp (datasource/kafka/kafka_config.rs:171-179):
+// where the event time of a batch comes from.  Without it the batch already carries `_streaming_internal_metadata`.
+struct TimestampUnit {
+  int32_t source = DNZ_TS_CANONICAL; std::string format;
+  static TimestampUnit Int64Millis() { return {DNZ_TS_INT64_MILLIS, {}}; }
+  static TimestampUnit Int64Seconds() { return {DNZ_TS_INT64_SECONDS, {}}; }
+  static TimestampUnit StringIso8601(std::string chrono_format) { return {DNZ_TS_STRING_ISO8601, std::move(chrono_format)}; }
+};
 
 struct AggregateFunctionExpr { int kind; std::string arg_column; std::string alias; };
 struct PhysicalGroupBy { std::vector<std::string> columns; };
@@ -110,6 +122,16 @@ class GroupedWindowAggStream {
     return out;
   }
   int64_t watermark() const { return dnz_window_watermark(h_); }
+  // The barrier hook (grouped_window_agg_stream.rs:357-417): serialise the open frames / reload them into a fresh stream of the
+  // same plan (:84-102).  The reference writes into its SlateDB backend; here the caller owns the bytes.
+  std::vector<uint8_t> checkpoint() {
+    void* blob = nullptr; int64_t n = 0;
+    check(dnz_window_checkpoint(h_, &blob, &n));
+    std::vector<uint8_t> out(static_cast<uint8_t*>(blob), static_cast<uint8_t*>(blob) + n);
+    dnz_blob_free(blob);
+    return out;
+  }
+  void restore(const std::vector<uint8_t>& blob) { check(dnz_window_restore(h_, blob.data(), (int64_t)blob.size())); }
   dnz_stats metrics() const { dnz_stats s{}; dnz_window_stats(h_, &s); return s; }   // ExecutionPlan::metrics()
   dnz_window* handle() { return h_; }
 
@@ -127,7 +149,7 @@ class StreamingWindowExec {
                                      PhysicalStreamingWindowType window_type, std::optional<size_t> upstream_partitioning,
                                      int32_t device = 0) {
     (void)mode;
-    if (group_by.columns.size() != 1) throw DataFusionError(DNZ_ERR_UNSUPPORTED, "GPU streaming window: exactly one plain group-by column is implemented");
+    if (group_by.columns.size() > 1) throw DataFusionError(DNZ_ERR_UNSUPPORTED, "GPU streaming window: at most one plain group-by column is implemented");
     StreamingWindowExec e;
     e.group_by_ = std::move(group_by); e.aggr_ = std::move(aggr_expr); e.filter_ = std::move(filter_expr);
     e.input_schema_ = input_schema; e.window_type_ = window_type; e.upstream_partitioning_ = upstream_partitioning; e.device_ = device;
@@ -143,7 +165,12 @@ class StreamingWindowExec {
     std::vector<dnz_agg> aggs;
     for (auto& a : aggr_) aggs.push_back(dnz_agg{a.kind, col_index(a.arg_column), a.alias.c_str()});
     dnz_window_config c{};
-    c.abi_version = DNZ_ABI_VERSION; c.device = device_; c.key_column = col_index(group_by_.columns[0]);
+    c.abi_version = DNZ_ABI_VERSION; c.device = device_;
+    c.key_column = group_by_.columns.empty() ? DNZ_NO_KEY : col_index(group_by_.columns[0]);      // `.window([], ..)`: WindowAggStream
+    if (timestamp_unit_.source != DNZ_TS_CANONICAL) {
+      c.ts_source = timestamp_unit_.source; c.ts_column = col_index(timestamp_column_);
+      c.ts_format = timestamp_unit_.source == DNZ_TS_STRING_ISO8601 ? timestamp_unit_.format.c_str() : nullptr;
+    }
     c.n_aggs = (int32_t)aggs.size(); c.aggs = aggs.data();
     c.window_ms = window_type_.length.ms; c.slide_ms = window_type_.kind == PhysicalStreamingWindowType::Sliding ? window_type_.slide.ms : 0;
     if (filter_) {
@@ -159,14 +186,20 @@ class StreamingWindowExec {
   }
   // schema(): group key | aggregates | window_start_time | window_end_time (create_schema :1096-1134 + continuous/mod.rs:42-62)
   std::vector<std::string> schema_names() const {
-    std::vector<std::string> n{group_by_.columns[0]};
+    std::vector<std::string> n;
+    if (!group_by_.columns.empty()) n.push_back(group_by_.columns[0]);
     for (auto& a : aggr_) n.push_back(a.alias);
     n.push_back("window_start_time"); n.push_back("window_end_time");
     return n;
   }
   const char* name() const { return "StreamingWindowExec"; }
+  // the source's with_timestamp(column, unit): the operator derives the canonical timestamp itself (utils/time.rs:59-94)
+  StreamingWindowExec& with_timestamp(std::string timestamp_column, TimestampUnit unit) {
+    timestamp_column_ = std::move(timestamp_column); timestamp_unit_ = std::move(unit); return *this;
+  }
 
  private:
+  std::string timestamp_column_; TimestampUnit timestamp_unit_;
   PhysicalGroupBy group_by_; std::vector<AggregateFunctionExpr> aggr_; std::optional<FilterPredicate> filter_;
   const ArrowSchema* input_schema_ = nullptr; PhysicalStreamingWindowType window_type_{PhysicalStreamingWindowType::Tumbling, {0}, {0}};
   std::optional<size_t> upstream_partitioning_; int32_t device_ = 0;
@@ -199,15 +232,47 @@ class DataStream {
     d.filter_ = FilterPredicate{predicate.lhs->name, predicate.op, predicate.rhs->literal};
     return d;
   }
+  // KafkaTopicBuilder::with_timestamp (kafka_config.rs:171-179): the raw event-time column of the source and its unit
+  DataStream with_timestamp(std::string timestamp_column, TimestampUnit unit) const {
+    DataStream d = *this; d.ts_column_ = std::move(timestamp_column); d.ts_unit_ = std::move(unit); return d;
+  }
   StreamingWindowExec plan(int32_t device = 0) const {
     if (!has_window_) throw DataFusionError(DNZ_ERR_INVALID, "no window() in the pipeline");
-    return StreamingWindowExec::try_new(AggregateMode::Single, group_, aggr_, filter_, schema_, window_, std::nullopt, device);
+    StreamingWindowExec e = StreamingWindowExec::try_new(AggregateMode::Single, group_, aggr_, filter_, schema_, window_, std::nullopt, device);
+    if (ts_unit_.source != DNZ_TS_CANONICAL) e.with_timestamp(ts_column_, ts_unit_);
+    return e;
   }
 
  private:
   const ArrowSchema* schema_ = nullptr; PhysicalGroupBy group_; std::vector<AggregateFunctionExpr> aggr_;
   std::optional<FilterPredicate> filter_; PhysicalStreamingWindowType window_{PhysicalStreamingWindowType::Tumbling, {0}, {0}};
   bool has_window_ = false;
+  std::string ts_column_; TimestampUnit ts_unit_;
+};
+
+// RepartitionExec(Hash(group keys), n) for input that is NOT key-partitioned
+// (physical_optimizer/coalesce_before_streaming_window_aggregate.rs:63-73), with the communicator owned by the library: every rank
+// aggregates the batches it is dealt, `step` moves the closed panes' partial states to their owners over NVLink and the owners emit.
+// One group per process and GPU; `allgather` is whatever the deployment has (used twice, at creation).
+class RepartitionGroup {
+ public:
+  RepartitionGroup(int32_t rank, int32_t world, int32_t device, dnz_allgather_fn allgather, void* ctx,
+                   int64_t ring_entries = 0, int64_t ring_key_bytes = 0) {
+    dnz_group_config c{}; c.abi_version = DNZ_ABI_VERSION; c.rank = rank; c.world = world; c.device = device;
+    c.ring_entries = ring_entries; c.ring_key_bytes = ring_key_bytes;
+    const int32_t rc = dnz_group_create(&c, allgather, ctx, &g_);
+    if (rc != DNZ_OK) throw DataFusionError(rc, dnz_window_last_error(nullptr));
+  }
+  RepartitionGroup(const RepartitionGroup&) = delete;
+  ~RepartitionGroup() { if (g_) dnz_group_destroy(g_); }
+  void attach(GroupedWindowAggStream& s) { check(dnz_group_attach(g_, s.handle()), s); }
+  // COLLECTIVE; returns the global watermark under which this step emitted (INT64_MIN: none yet)
+  int64_t step(GroupedWindowAggStream& s) { int64_t wm = 0; check(dnz_group_step(g_, s.handle(), &wm), s); return wm; }
+  int64_t flush(GroupedWindowAggStream& s) { int64_t wm = 0; check(dnz_group_flush(g_, s.handle(), &wm), s); return wm; }
+
+ private:
+  void check(int32_t rc, GroupedWindowAggStream& s) { if (rc != DNZ_OK) throw DataFusionError(rc, dnz_window_last_error(s.handle())); }
+  dnz_group* g_ = nullptr;
 };
 
 }  // namespace denormalized
