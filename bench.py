@@ -591,8 +591,14 @@ def main():
             psx = max(BATCH_ROWS, min(rows, 200_000_000 // world) // BATCH_ROWS * BATCH_ROWS)
             cutx = T0 + psx // wl["rows_per_ms"]
             capx = Capture(cutx, wl["window_ms"])
-            w = xwindow(); step_exchange(w, capx); w.close()
+            w = xwindow(); xo_fresh = step_exchange(w, capx); w.close()
             mine = leg_checksum(capx, cutx, wl["window_ms"])
+            # the timed streams ran through operators attached long before their stream began: they must emit what this one did
+            tfresh = torch.tensor([xo_fresh], dtype=torch.int64, device="cuda"); dist.all_reduce(tfresh)
+            exchange["rows_out_fresh_operator"] = int(tfresh.item())
+            exchange["rows_out_consistent"] = int(tfresh.item()) == int(to.item())
+            if not exchange["rows_out_consistent"]:
+                log(f"exchange leg: the timed streams emitted {int(to.item())} rows per step, a fresh operator {int(tfresh.item())} -- the timed figure is NOT valid")
             del capx
             allsums = [None] * world
             dist.all_gather_object(allsums, mine)
@@ -801,7 +807,12 @@ def main():
                              "algorithmic_bytes_per_row": agg_bytes / max(rows * args.steps, 1)},
                 "e2e": e2e, "cpu_baseline": cpu,
                 "parity_checked": bool(parity) and not args.no_parity, "parity": parity}
-        if exchange:
+        if exchange and not exchange.get("rows_out_consistent", True):
+            # the timed exchange streams did not emit what a fresh operator emits on the same stream: that figure is not a measurement
+            # of the path.  The key-partitioned leg (verified row by row) stays the headline; the exchange leg is kept with its flag.
+            line["exchange"] = exchange
+            line["config"]["note"] = "exchange leg rejected (rows_out_consistent false): headline = key-partitioned leg"
+        elif exchange:
             # N > 1: the headline is the UN-PARTITIONED stream through the fused exchange; the key-partitioned run (no data-path
             # collective, keys generated pre-partitioned) is kept beside it
             line["partitioned"] = {"value": value, "unit": "rows/s", "ms_per_step": ms / args.steps,

@@ -308,6 +308,7 @@ struct dnz_window {
   // multi-GPU pane exchange
   int rank = 0, world = 1;
   bool fused = false;                             // attached to a dnz_group: launches stay asynchronous, emission happens in the group step
+  bool group_started = false;                     // this operator has taken part in a group step (its stream has begun in the group)
   bool has_lwm = false; int64_t lwm = 0;          // local watermark (exchange mode: emission follows the GLOBAL one)
   int64_t exported_pane_upto = INT64_MIN;
   DevBuf d_part_entries, d_part_keys, d_owner_cursor, d_xptrs; PinnedBuf h_xptrs;
@@ -2244,7 +2245,7 @@ struct dnz_group {
   struct Range { int64_t gwm = INT64_MIN, first = INT64_MAX, hi = INT64_MIN; bool any = false; };
   Range sent[2];                                 // what pack of step s sent (by step parity): merged by finish of step s+1
   bool staged[2] = {false, false};
-  unsigned long long attach_step = 0;            // the step count when the current operator was attached: what was published before belongs to another stream
+  unsigned long long attach_step = 0;            // the step count when the current STREAM began (first step of a fresh operator): what was published before belongs to another stream
 
   static XchgRegion carve(void* base, uint64_t ring_entries) {
     XchgRegion r;
@@ -2344,6 +2345,13 @@ void dnz_window::group_begin(dnz_group* g) {
   // on the device, waiting for it here would idle the GPU every step.  The local watermark is that of the LAUNCHED batches;
   // dnz_window_process before the step includes everything pushed.
   // Errors of earlier steps (ring / table overflow) surface when their launches are verified.
+  if (!group_started) {
+    // The first step of a fresh operator begins a new stream in the group (collective: every rank's operator is fresh in the same
+    // step; operators may have been attached long before).  Watermarks published and pane ranges sent before this step belong to
+    // the previous stream: the pipeline restarts empty.
+    group_started = true;
+    g->attach_step = g->step; g->sent[0] = g->sent[1] = dnz_group::Range{};
+  }
   if (!cur().batches.empty()) seal_current();
   while (!launched_order.empty() && cudaEventQuery(slot[launched_order.front()].done) == cudaSuccess) verify(slot[launched_order.front()]);
   cudaGetLastError();
@@ -2584,7 +2592,7 @@ void dnz_group_destroy(dnz_group* g) {
 int32_t dnz_group_attach(dnz_group* g, dnz_window* w) {
   if (!g) { g_last_error = "null group"; return DNZ_ERR_INVALID; }
   const int32_t rc = dnz_window_set_exchange(w, g->rank, g->world);
-  if (rc == DNZ_OK) { w->fused = g->world > 1; g->attach_step = g->step; g->sent[0] = g->sent[1] = dnz_group::Range{}; }
+  if (rc == DNZ_OK) w->fused = g->world > 1;
   return rc;
 }
 

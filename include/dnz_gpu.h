@@ -248,9 +248,9 @@ int32_t dnz_group_create(const dnz_group_config* cfg, dnz_allgather_fn allgather
 int32_t dnz_group_create_local(int32_t world, const int32_t* devices, int64_t ring_entries, int64_t ring_key_bytes, dnz_group** out);
 void dnz_group_destroy(dnz_group* g);
 /* puts the operator into exchange mode as rank `g.rank` of `g.world` (before its first batch).  expected_groups of the operator
- * must cover the GLOBAL key set: an owner interns keys it has never seen in a batch of its own.  COLLECTIVE: a group serves one
- * stream at a time; every rank attaches its operator of the next stream between the same two steps, after dnz_group_flush of
- * the previous one. */
+ * must cover the GLOBAL key set: an owner interns keys it has never seen in a batch of its own.  A group serves one stream at a time: the first
+ * dnz_group_step of a fresh operator begins a new stream (COLLECTIVE: on every rank in the same step, after dnz_group_flush of the
+ * previous stream's operators); operators may be attached any time before. */
 int32_t dnz_group_attach(dnz_group* g, dnz_window* w);
 /* One exchange step = dnz_group_step_begin + dnz_group_step_pack + dnz_group_step_finish, everything enqueued on the operator's
  * stream; streams of different ranks are ordered by interprocess CUDA events.  COLLECTIVE: every rank calls it the same number
