@@ -199,3 +199,51 @@ def test_non_lattice_geometries_depend_on_batch_boundaries(L, S):
     for l, s in [(2000, 0), (4000, 1000), (4000, 2000)]:                  # lattice geometries: the cut is irrelevant
         lattice = [window_set(run_oracle, c, l, s) for c in cuts]
         assert lattice[0] == lattice[1] == lattice[2]
+
+
+@pytest.mark.parametrize("L,S", [(1000, 0), (2000, 0), (4000, 1000), (6000, 2000)])
+@pytest.mark.parametrize("late", [False, True])
+def test_ungrouped_oracle_matches_python_model(L, S, late):
+    """`.window([], aggs, ..)`: the C restatement of the Partial -> Final chain against the independent Python model,
+    batch by batch (emission lag of the Final stage, batches that close several Partial windows at once merged into the frame of the
+    largest start, late partial results dropped), NULL values and windows that only see NULLs included."""
+    from oracle import OracleUngrouped
+    from tests.pymodel import PyUngroupedModel
+    rng = np.random.default_rng(7 * L + S + late)
+    kw = dict(jitter_ms=500, late_every=5, late_shift_ms=2500) if late else dict(null_frac=0.15, ragged=True)
+    raw = random_stream(rng, 60, 200, 3, span_ms=300, **kw)
+    if not late:
+        raw[7] = [(ts, None, k) for ts, _, k in raw[7]]             # a batch of NULL values only
+    o, m = OracleUngrouped(L, S), PyUngroupedModel(L, S)
+    got = []
+    for rows in raw:
+        o.push(rows_to_batch(rows)); got += o.results()
+        m.push(rows)
+    assert len(m.out) > 3
+    assert_rows_equal(got, m.out, check_seq=True)
+
+
+def test_ungrouped_oracle_special_values_match_model():
+    """totalOrder min / max over NaN, +-0.0, +-inf; a window that sees zeros only; windows that only see NULL values."""
+    from oracle import OracleUngrouped
+    from tests.pymodel import PyUngroupedModel
+    vals = [float("nan"), -0.0, 0.0, float("inf"), float("-inf"), 5.0, -3.0, None, -float("nan")]
+    o, m, got = OracleUngrouped(1000, 0), PyUngroupedModel(1000, 0), []
+    for b in range(24):
+        rows = [(T0 + b * 500 + i, vals[(b + i) % len(vals)], b"x") for i in range(40)]
+        if b in (4, 5):
+            rows = [(T0 + b * 500 + i, -0.0 if (i + b) % 2 else 0.0, b"x") for i in range(40)]
+        if b in (8, 9):
+            rows = [(T0 + b * 500 + i, None, b"x") for i in range(10)]
+        if b in (12, 13):
+            rows = [(T0 + b * 500 + i, -0.0, b"x") for i in range(10)]          # only negative zeros: min = max = -0.0, but the
+                                                                                # sum starts from +0.0 (get_or_insert(0.)): avg +0.0
+        o.push(rows_to_batch(rows)); got += o.results()
+        m.push(rows)
+    assert any(r[4] is None and r[3] == 0 for r in m.out)
+    zeros = [r for r in m.out if r[0] == T0 + 2000][0]
+    assert math.copysign(1.0, zeros[4]) == -1.0 and math.copysign(1.0, zeros[5]) == 1.0 and zeros[4] == 0.0 == zeros[5]
+    negz = [r for r in m.out if r[0] == T0 + 6000][0]
+    assert negz[3] == 20 and math.copysign(1.0, negz[4]) == -1.0 and math.copysign(1.0, negz[6]) == 1.0
+    assert_rows_equal(got, m.out, check_seq=True)
+    assert all(math.copysign(1.0, a[6]) == math.copysign(1.0, b[6]) for a, b in zip(got, m.out) if a[6] == 0.0)     # zero signs too
