@@ -287,6 +287,14 @@ def oracle_sample(wl, batches, sample_rows):
     return tab, cut, dt
 
 
+def plan_e2e_steps(fit, warmup, steps, n_parity_ops):
+    """How many warm-up and timed e2e steps run when `fit` operators (one per step, plus the parity pass) fit into device memory:
+    at most 3 warm-ups and `steps` timed steps, never fewer than one of each."""
+    e_warm = min(warmup, 3, max(1, fit - 1 - n_parity_ops))
+    e_steps = max(1, min(steps, fit - e_warm - n_parity_ops))
+    return e_warm, e_steps
+
+
 class Capture(list):
     """Collects a leg's emitted results, keeping only the polls that contain rows of windows ending at or before `cut`."""
 
@@ -650,8 +658,7 @@ def main():
             dist.all_reduce(tf, op=dist.ReduceOp.MIN)
             fit = int(tf.item())
         n_parity_ops = 0 if args.no_parity else 1
-        e_warm = min(args.warmup, 3, max(1, fit - 1 - n_parity_ops))
-        e_steps = max(1, min(args.steps, fit - e_warm - n_parity_ops))
+        e_warm, e_steps = plan_e2e_steps(fit, args.warmup, args.steps, n_parity_ops)
         n_e2e_steps = e_warm + e_steps
         n_e2e_total = n_e2e_steps + n_parity_ops                      # + one untimed pass whose output is compared with the oracle
         log(f"e2e: {free_dev / 2**30:.0f} GiB of device memory free, ~{per_op / 2**30:.1f} GiB per operator -> {e_warm} warm-up + {e_steps} timed steps")
